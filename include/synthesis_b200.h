@@ -202,6 +202,16 @@ int syn_engine_play(syn_engine* e, const uint8_t* moves, const uint32_t* n_moves
                     uint64_t* my_bb, uint64_t* op_bb, uint8_t* height /*[n][9]*/, uint8_t* legal_mask_lo /*[n] cols 0-7*/,
                     uint8_t* legal_mask_hi /*[n] col 8*/, uint8_t* status, float* features /*[n][63] or NULL*/);
 
+/* Optional per-row trace of the NEXT gather (arrays of `capacity` rows like syn_experience, host or
+ * device; NULL to disable): the action played from the row's state, nodes.len() of that ply's
+ * tree, and the root's child visit counts by column.  Not part of the reference's ReplayBuffer;
+ * it is what the parity tests compare ("bit-exact visit counts"). */
+int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, float* child_visits /*[cap][9]*/);
+
+/* Lanes per game: 32 (a warp per game) or 16 (two games per warp).  Default 32, or the value of
+ * the SYN_GROUP_LANES environment variable at syn_engine_create.  Results do not depend on it. */
+int syn_engine_set_group_lanes(syn_engine* e, int lanes);
+
 /* Packed Option<Outcome> (synthesis/src/game.rs:9-14): 0 = None, else kind<<6 | turns with
  * kind 1 = Lose, 2 = Draw, 3 = Win; turns <= 63. */
 #define SYN_OUTCOME_NONE 0u

@@ -1,0 +1,75 @@
+"""Drop-in for the self-play half of synthesis/src/alpha_zero.rs: `gather_experience`
+(alpha_zero.rs:120-169) with the same argument meaning, plus `MCTS.exploit` (mcts.rs:111-121).
+
+    gather_experience(cfg, policy, buffer, seed)
+
+plays `cfg.games_per_train` games on the engine, then — exactly like the reference —
+`buffer.keep_last_n_games(cfg.games_to_keep - cfg.games_per_train)` and `buffer.extend(new)`.
+`policy` is a `Connect4Net` (the reference loads `models/<policy_name>.ot` in every worker,
+alpha_zero.rs:192-194) or a `RolloutPolicy` (the faithful `run_game + RolloutPolicy` composition
+of SURVEY.md §0.3).  `seed` is the iteration index like the reference's call site
+(alpha_zero.rs:49); game g of the call draws from streams derived from (seed, g) — see
+include/syn_streams.h — instead of one stream per worker thread.
+"""
+import numpy as np
+
+from . import _lib as L
+from .config import LearningConfig, MCTSConfig, RolloutConfig, ValueTarget
+from .connect4 import Connect4
+from .data import ReplayBuffer
+from .engine import Engine
+from .policies import Connect4Net, RolloutPolicy
+
+_engines = {}
+
+
+def engine_for(device: int, max_games_in_flight: int, max_explores: int) -> Engine:
+    """One cached engine per (device, capacity): arenas are allocated once, not per iteration."""
+    key = (device, max_games_in_flight, max_explores)
+    if key not in _engines:
+        _engines[key] = Engine(device, max_games_in_flight, max_explores)
+    return _engines[key]
+
+
+def _leaf_kind(policy) -> int:
+    if isinstance(policy, Connect4Net):
+        return L.LEAF_NN
+    if isinstance(policy, RolloutPolicy):
+        return L.LEAF_ROLLOUT
+    raise TypeError("policy must be a Connect4Net or a RolloutPolicy: user-defined Policy/Game objects are host code "
+                    "and cannot run inside the search kernel")
+
+
+def gather_experience(cfg: LearningConfig, policy, buffer: ReplayBuffer, seed: int, *, engine: Engine = None,
+                      device: int = 0, first_game_index: int = 0, return_stats: bool = False):
+    kind = _leaf_kind(policy)
+    n = int(cfg.games_per_train)
+    eng = engine or engine_for(device, min(max(n, 32), 18944), int(cfg.rollout_cfg.num_explores))
+    if kind == L.LEAF_NN:
+        eng.set_weights(policy.blob())
+    arrays, stats, _ = eng.gather(cfg.rollout_cfg, kind, first_game_index, n, seed)
+    # run_n_games returns a buffer whose ids are 1..n (alpha_zero.rs:201-203)
+    arrays["game_ids"] = arrays["game_ids"] - np.uint64(first_game_index)
+    worker = ReplayBuffer.from_arrays(n, arrays)
+    buffer.keep_last_n_games(cfg.games_to_keep - cfg.games_per_train)
+    buffer.extend(worker)
+    return stats if return_stats else None
+
+
+class MCTS:
+    """`MCTS::exploit` (mcts.rs:111-121): build a tree with `explores` explores and return best_action."""
+
+    @staticmethod
+    def exploit(explores: int, cfg: MCTSConfig, policy, game: Connect4, action_selection: int, *, engine: Engine = None,
+                device: int = 0, details: bool = False):
+        kind = _leaf_kind(policy)
+        eng = engine or engine_for(device, 32, int(explores))
+        if kind == L.LEAF_NN:
+            eng.set_weights(policy.blob())
+        rc = RolloutConfig(num_workers=0, num_explores=int(explores), random_actions_until=0, sample_actions_until=0,
+                           stop_games_when_solved=False, value_target=ValueTarget.Q(), action=action_selection, mcts_cfg=cfg)
+        seed = policy.seed if isinstance(policy, RolloutPolicy) else 0
+        out, stats = eng.search(rc, kind, [game.my_bb], [game.op_bb], [seed])
+        if details:
+            return int(out["best_action"][0]), {k: v[0] for k, v in out.items()}, stats
+        return int(out["best_action"][0])

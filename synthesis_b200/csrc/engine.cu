@@ -1,0 +1,511 @@
+// engine.cu — host side of libsynthesis_b200.so: the C ABI declared in include/synthesis_b200.h.
+//
+// Each entry point names the reference interface it replaces in the header.  This file owns
+// device memory (tree arenas, row buffers), launches the kernels of selfplay.cuh on the engine's
+// stream, times them with CUDA events on that stream, and moves results to the caller's buffers.
+// There is no CPU implementation behind any entry point: without a compute-capability-10.x device
+// syn_engine_create fails with SYN_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "selfplay.cuh"
+
+using namespace eng;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return fail(SYN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------ engine
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct syn_engine {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
+    int group_lanes = 32;
+    DevBuf<float4> stat;
+    DevBuf<uint4> meta;
+    DevBuf<float> weights;
+    bool has_weights = false;
+    DevBuf<unsigned int> next_game;
+    DevBuf<unsigned long long> counters;
+    DevBuf<int> error;
+    // per-call row buffers
+    DevBuf<uint64_t> row_my, row_op, row_off;
+    DevBuf<float> row_pi, row_v, row_visits;
+    DevBuf<uint8_t> row_action;
+    DevBuf<uint32_t> row_nodes, game_len;
+    // dense staging for host destinations
+    DevBuf<uint8_t> staging;
+    // search-mode buffers
+    DevBuf<uint64_t> pos_my, pos_op, pos_seed;
+    DevBuf<float> s_visits, s_q;
+    DevBuf<uint8_t> s_csol, s_rsol, s_best;
+    DevBuf<uint32_t> s_nodes;
+    // pending gather
+    bool pending = false;
+    uint32_t pend_games = 0;
+    uint64_t pend_first = 0;
+    uint64_t launches = 0, h2d = 0, d2h = 0;
+    // trace destination (optional)
+    uint8_t* trace_action = nullptr;
+    uint32_t* trace_nodes = nullptr;
+    float* trace_visits = nullptr;
+};
+
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int validate_cfg(const syn_rollout_cfg* cfg, const syn_engine* e) {
+    if (!cfg) return fail(SYN_ERR_INVALID_ARGUMENT, "cfg is NULL");
+    if (cfg->num_explores > e->max_explores)
+        return fail(SYN_ERR_CAPACITY, "num_explores %u exceeds the engine's max_explores %u", cfg->num_explores, e->max_explores);
+    const syn_mcts_cfg& m = cfg->mcts;
+    if (m.exploration_kind > SYN_EXPLORATION_POLYNOMIAL_UCT) return fail(SYN_ERR_INVALID_ARGUMENT, "bad exploration_kind %u", m.exploration_kind);
+    if (m.fpu_kind == SYN_FPU_FUNC)
+        return fail(SYN_ERR_UNSUPPORTED, "Fpu::Func carries host code and cannot run on the device; use SYN_FPU_NORMAL{mean,std} for the shipped closure");
+    if (m.fpu_kind > SYN_FPU_FUNC) return fail(SYN_ERR_INVALID_ARGUMENT, "bad fpu_kind %u", m.fpu_kind);
+    if (m.noise_kind > SYN_NOISE_DIRICHLET) return fail(SYN_ERR_INVALID_ARGUMENT, "bad noise_kind %u", m.noise_kind);
+    if (m.noise_kind == SYN_NOISE_DIRICHLET && !(m.noise_alpha > 0.0f)) return fail(SYN_ERR_INVALID_ARGUMENT, "Dirichlet alpha must be > 0");
+    if (cfg->value_target_kind > SYN_VALUE_Q_TO_Z) return fail(SYN_ERR_INVALID_ARGUMENT, "bad value_target_kind %u", cfg->value_target_kind);
+    if (cfg->action_selection > SYN_ACTION_NUM_VISITS) return fail(SYN_ERR_INVALID_ARGUMENT, "bad action_selection %u", cfg->action_selection);
+    if (cfg->leaf_eval_kind > SYN_LEAF_ROLLOUT) return fail(SYN_ERR_INVALID_ARGUMENT, "bad leaf_eval_kind %u", cfg->leaf_eval_kind);
+    if (cfg->leaf_eval_kind == SYN_LEAF_NN && !e->has_weights)
+        return fail(SYN_ERR_NO_WEIGHTS, "leaf_eval_kind = NN but syn_engine_set_weights has not been called");
+    return SYN_OK;
+}
+
+static size_t nn_smem_bytes(int gpb) { return (size_t)(mlp::WEIGHT_FLOATS + 2 * gpb * mlp::XS + gpb * 64) * sizeof(float); }
+
+constexpr int ROLLOUT_THREADS = 256;
+constexpr int NN_THREADS = 512;
+
+// Launches the self-play kernel for `n` games/positions.  Rows/search buffers must be set in kp.
+static int launch_selfplay(syn_engine* e, KParams& kp) {
+    const int gl = e->group_lanes;
+    const bool nn = kp.cfg.leaf_eval_kind == SYN_LEAF_NN;
+    const int threads = nn ? NN_THREADS : ROLLOUT_THREADS;
+    const int gpb = threads / gl;
+    uint32_t max_blocks = e->max_games / gpb;
+    if (max_blocks == 0) return fail(SYN_ERR_CAPACITY, "max_games_in_flight %u is smaller than one CTA's %d games", e->max_games, gpb);
+    uint32_t want_blocks = (kp.num_games + gpb - 1) / gpb;
+    uint32_t blocks = want_blocks < max_blocks ? want_blocks : max_blocks;
+    if (nn) {
+        uint32_t cap = (uint32_t)e->sm_count; // one CTA per SM: the weights fill most of its shared memory
+        if (blocks > cap) blocks = cap;
+    }
+    if (blocks == 0) blocks = 1;
+    CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
+    if (nn) {
+        size_t smem = nn_smem_bytes(gpb);
+        if (gl == 32) {
+            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_kernel<32, NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            selfplay_nn_kernel<32, NN_THREADS><<<blocks, threads, smem, e->stream>>>(kp);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_kernel<16, NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            selfplay_nn_kernel<16, NN_THREADS><<<blocks, threads, smem, e->stream>>>(kp);
+        }
+    } else {
+        if (gl == 32) selfplay_rollout_kernel<32, ROLLOUT_THREADS><<<blocks, threads, 0, e->stream>>>(kp);
+        else selfplay_rollout_kernel<16, ROLLOUT_THREADS><<<blocks, threads, 0, e->stream>>>(kp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    e->launches += 1;
+    return SYN_OK;
+}
+
+static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) {
+    std::memset(&kp, 0, sizeof(kp));
+    kp.cfg = *cfg;
+    kp.arena_nodes = e->arena_nodes;
+    kp.stat = e->stat.p;
+    kp.meta = e->meta.p;
+    kp.next_game = e->next_game.p;
+    kp.counters = e->counters.p;
+    kp.error = e->error.p;
+    kp.weights = e->weights.p;
+}
+
+static int read_stats(syn_engine* e, syn_stats* stats, float ms) {
+    unsigned long long c[CNT_N];
+    CUDA_TRY(cudaMemcpyAsync(c, e->counters.p, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->explores = c[CNT_EXPLORES]; stats->leaf_evals = c[CNT_LEAF_EVALS]; stats->rows = c[CNT_ROWS];
+        stats->games = c[CNT_GAMES]; stats->trees = c[CNT_TREES]; stats->nodes = c[CNT_NODES];
+        stats->select_levels = c[CNT_SELECT_LEVELS]; stats->children_scanned = c[CNT_CHILDREN_SCANNED];
+        stats->expansions = c[CNT_EXPANSIONS]; stats->children_created = c[CNT_CHILDREN_CREATED];
+        stats->backprop_levels = c[CNT_BACKPROP_LEVELS]; stats->rollout_plies = c[CNT_ROLLOUT_PLIES];
+        stats->device_ns = (uint64_t)((double)ms * 1e6);
+        stats->kernel_launches = e->launches;
+        stats->h2d_bytes = e->h2d;
+        stats->d2h_bytes = e->d2h;
+    }
+    return SYN_OK;
+}
+
+static int check_device_error(syn_engine* e) {
+    int derr = 0;
+    CUDA_TRY(cudaMemcpyAsync(&derr, e->error.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (derr == DERR_ARENA_OVERFLOW) return fail(SYN_ERR_CAPACITY, "a tree outgrew its arena of %u nodes", e->arena_nodes);
+    if (derr == DERR_DEPTH_OVERFLOW) return fail(SYN_ERR_DEVICE_FAULT, "a tree path exceeded 64 levels");
+    if (derr == DERR_BAD_WEIGHTS) return fail(SYN_ERR_DEVICE_FAULT, "WeightedIndex met an all-zero or non-finite search policy (the reference would panic)");
+    if (derr) return fail(SYN_ERR_DEVICE_FAULT, "device error %d", derr);
+    return SYN_OK;
+}
+
+extern "C" {
+
+int syn_abi_version(void) { return SYN_ABI_VERSION; }
+const char* syn_build_info(void) {
+#define SYN_STR2(x) #x
+#define SYN_STR(x) SYN_STR2(x)
+    return "libsynthesis_b200: sm_100a, nvcc " SYN_STR(__CUDACC_VER_MAJOR__) "." SYN_STR(__CUDACC_VER_MINOR__) ", -fmad=false, built " __DATE__;
+}
+const char* syn_last_error(void) { return g_err; }
+
+int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t max_explores, syn_engine** out) {
+    if (!out) return fail(SYN_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SYN_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+    }
+    if (cuda_device < 0 || cuda_device >= ndev) return fail(SYN_ERR_INVALID_ARGUMENT, "cuda_device %d out of range (%d devices)", cuda_device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cuda_device));
+    if (prop.major != 10)
+        return fail(SYN_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cuda_device, prop.major, prop.minor);
+    if (max_games_in_flight == 0 || max_explores == 0) return fail(SYN_ERR_INVALID_ARGUMENT, "max_games_in_flight and max_explores must be > 0");
+    CUDA_TRY(cudaSetDevice(cuda_device));
+    syn_engine* e = new syn_engine();
+    e->device = cuda_device;
+    e->sm_count = prop.multiProcessorCount;
+    const char* glenv = std::getenv("SYN_GROUP_LANES");
+    e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : 32;
+    // round the in-flight game count up to whole CTAs of either kernel
+    uint32_t unit = NN_THREADS / 16;
+    e->max_games = ((max_games_in_flight + unit - 1) / unit) * unit;
+    e->max_explores = max_explores;
+    // nodes.len() <= 1 + 9 * (explores + 1): every visit pushes at most 9 nodes (mcts.rs:384-397)
+    e->arena_nodes = 1u + 9u * (max_explores + 1u) + 7u;
+    e->arena_nodes = (e->arena_nodes + 7u) & ~7u;
+    cudaError_t ce;
+    size_t total = (size_t)e->max_games * e->arena_nodes;
+    if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
+        (ce = e->stat.reserve(total)) != cudaSuccess || (ce = e->meta.reserve(total)) != cudaSuccess ||
+        (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
+        (ce = e->counters.reserve(CNT_N)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
+        int rc = fail(SYN_ERR_CUDA, "engine allocation failed (%zu arena nodes = %.1f MiB): %s", total,
+                      (double)total * 32.0 / 1048576.0, cudaGetErrorString(ce));
+        syn_engine_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return SYN_OK;
+}
+
+void syn_engine_destroy(syn_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    e->stat.release(); e->meta.release(); e->weights.release(); e->next_game.release(); e->counters.release(); e->error.release();
+    e->row_my.release(); e->row_op.release(); e->row_off.release(); e->row_pi.release(); e->row_v.release(); e->row_visits.release();
+    e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
+    e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();
+    e->s_csol.release(); e->s_rsol.release(); e->s_best.release(); e->s_nodes.release();
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int syn_engine_set_group_lanes(syn_engine* e, int lanes) {
+    if (!e || (lanes != 16 && lanes != 32)) return fail(SYN_ERR_INVALID_ARGUMENT, "group lanes must be 16 or 32");
+    e->group_lanes = lanes;
+    return SYN_OK;
+}
+
+int syn_engine_set_weights(syn_engine* e, const float* blob, size_t n_floats) {
+    if (!e || !blob) return fail(SYN_ERR_INVALID_ARGUMENT, "engine or blob is NULL");
+    if (n_floats != SYN_N_WEIGHTS) return fail(SYN_ERR_INVALID_ARGUMENT, "expected %d floats (63-128-96-64-48-12 MLP), got %zu", SYN_N_WEIGHTS, n_floats);
+    CUDA_TRY(cudaSetDevice(e->device));
+    bool dev = is_device_ptr(blob);
+    CUDA_TRY(cudaMemcpyAsync(e->weights.p, blob, n_floats * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (!dev) e->h2d += n_floats * sizeof(float);
+    e->has_weights = true;
+    return SYN_OK;
+}
+
+int syn_engine_gather_launch(syn_engine* e, const syn_rollout_cfg* cfg, uint64_t first_game_index, uint32_t num_games, uint64_t seed) {
+    if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is already in flight; call syn_engine_gather_wait first");
+    int rc = validate_cfg(cfg, e);
+    if (rc) return rc;
+    if (num_games == 0) return fail(SYN_ERR_INVALID_ARGUMENT, "num_games must be > 0");
+    CUDA_TRY(cudaSetDevice(e->device));
+    size_t rows = (size_t)num_games * 63;
+    CUDA_TRY(e->row_my.reserve(rows)); CUDA_TRY(e->row_op.reserve(rows)); CUDA_TRY(e->row_pi.reserve(rows * 9));
+    CUDA_TRY(e->row_v.reserve(rows * 3)); CUDA_TRY(e->row_visits.reserve(rows * 9)); CUDA_TRY(e->row_action.reserve(rows));
+    CUDA_TRY(e->row_nodes.reserve(rows)); CUDA_TRY(e->game_len.reserve(num_games)); CUDA_TRY(e->row_off.reserve(num_games));
+    KParams kp;
+    fill_common(e, kp, cfg);
+    kp.seed = seed; kp.first_game = first_game_index; kp.num_games = num_games; kp.search_mode = 0;
+    kp.row_my = e->row_my.p; kp.row_op = e->row_op.p; kp.row_pi = e->row_pi.p; kp.row_v = e->row_v.p;
+    kp.row_action = e->row_action.p; kp.row_nodes = e->row_nodes.p; kp.row_visits = e->row_visits.p; kp.game_len = e->game_len.p;
+    e->launches = 0;
+    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_N * sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->error.p, 0, sizeof(int), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->game_len.p, 0, num_games * sizeof(uint32_t), e->stream));
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    rc = launch_selfplay(e, kp);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    e->pending = true;
+    e->pend_games = num_games;
+    e->pend_first = first_game_index;
+    return SYN_OK;
+}
+
+// copies a dense device array to a caller pointer (host or device)
+static int deliver(syn_engine* e, void* dst, const void* src_dev, size_t bytes) {
+    if (!dst || bytes == 0) return SYN_OK;
+    bool dev = is_device_ptr(dst);
+    CUDA_TRY(cudaMemcpyAsync(dst, src_dev, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    if (!dev) e->d2h += bytes;
+    return SYN_OK;
+}
+
+int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, float* child_visits) {
+    if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    e->trace_action = action;
+    e->trace_nodes = tree_nodes;
+    e->trace_visits = child_visits;
+    return SYN_OK;
+}
+
+int syn_engine_gather_wait(syn_engine* e, syn_experience* out, syn_stats* stats) {
+    if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    if (!e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "no gather in flight");
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->pending = false;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    int rc = check_device_error(e);
+    if (rc) return rc;
+    const uint32_t n = e->pend_games;
+    if (out) {
+        std::vector<uint32_t> len(n);
+        CUDA_TRY(cudaMemcpyAsync(len.data(), e->game_len.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        e->d2h += n * sizeof(uint32_t);
+        std::vector<uint64_t> off(n);
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) { off[i] = total; total += len[i]; }
+        out->len = (size_t)total;
+        out->games = n;
+        if (total > out->capacity) return fail(SYN_ERR_CAPACITY, "experience needs %llu rows, caller provided %zu", (unsigned long long)total, out->capacity);
+        CUDA_TRY(cudaMemcpyAsync(e->row_off.p, off.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+        e->h2d += n * sizeof(uint64_t);
+        // dense staging layout (only for host destinations; device destinations are written in place)
+        struct Field { void* dst; size_t elt; size_t off; };
+        Field f[11] = {{out->game_ids, 8, 0}, {out->my_bb, 8, 0}, {out->op_bb, 8, 0}, {out->height, 9, 0}, {out->player, 1, 0},
+                       {out->states, 63 * 4, 0}, {out->pis, 9 * 4, 0}, {out->vs, 3 * 4, 0},
+                       {e->trace_action, 1, 0}, {e->trace_nodes, 4, 0}, {e->trace_visits, 9 * 4, 0}};
+        size_t need = 0;
+        for (auto& x : f) {
+            if (x.dst && !is_device_ptr(x.dst)) { x.off = need; need += ((x.elt * total + 255) / 256) * 256; }
+        }
+        CUDA_TRY(e->staging.reserve(need ? need : 256));
+        auto target = [&](int i) -> void* {
+            if (!f[i].dst) return nullptr;
+            return is_device_ptr(f[i].dst) ? f[i].dst : (void*)(e->staging.p + f[i].off);
+        };
+        CompactParams c;
+        std::memset(&c, 0, sizeof(c));
+        c.num_games = n; c.first_game = e->pend_first; c.game_len = e->game_len.p; c.row_off = e->row_off.p;
+        c.row_my = e->row_my.p; c.row_op = e->row_op.p; c.row_pi = e->row_pi.p; c.row_v = e->row_v.p;
+        c.row_action = e->row_action.p; c.row_nodes = e->row_nodes.p; c.row_visits = e->row_visits.p;
+        c.game_ids = (uint64_t*)target(0); c.my_bb = (uint64_t*)target(1); c.op_bb = (uint64_t*)target(2);
+        c.height = (uint8_t*)target(3); c.player = (uint8_t*)target(4); c.states = (float*)target(5);
+        c.pis = (float*)target(6); c.vs = (float*)target(7); c.t_action = (uint8_t*)target(8);
+        c.t_nodes = (uint32_t*)target(9); c.t_visits = (float*)target(10);
+        uint64_t warps = (uint64_t)n * 63;
+        uint32_t blocks = (uint32_t)((warps * 32 + 255) / 256);
+        compact_kernel<<<blocks, 256, 0, e->stream>>>(c);
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        for (int i = 0; i < 11; ++i)
+            if (f[i].dst && !is_device_ptr(f[i].dst)) {
+                rc = deliver(e, f[i].dst, e->staging.p + f[i].off, f[i].elt * total);
+                if (rc) return rc;
+            }
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return read_stats(e, stats, ms);
+}
+
+int syn_engine_gather(syn_engine* e, const syn_rollout_cfg* cfg, uint64_t first_game_index, uint32_t num_games, uint64_t seed,
+                      syn_experience* out, syn_stats* stats) {
+    if (!out) return fail(SYN_ERR_INVALID_ARGUMENT, "out is NULL");
+    if (e) { e->h2d = 0; e->d2h = 0; }
+    int rc = syn_engine_gather_launch(e, cfg, first_game_index, num_games, seed);
+    if (rc) return rc;
+    return syn_engine_gather_wait(e, out, stats);
+}
+
+int syn_engine_search(syn_engine* e, const syn_rollout_cfg* cfg, uint32_t tree_kind, const uint64_t* my_bb, const uint64_t* op_bb,
+                      const uint64_t* seeds, uint32_t n, float* child_visits, uint8_t* child_solution, float* root_q,
+                      uint8_t* root_solution, uint8_t* best_action, uint32_t* num_nodes, syn_stats* stats) {
+    if (!e || !my_bb || !op_bb || !seeds) return fail(SYN_ERR_INVALID_ARGUMENT, "engine, bitboards and seeds must not be NULL");
+    if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is in flight");
+    if (n == 0) return fail(SYN_ERR_INVALID_ARGUMENT, "n_positions must be > 0");
+    if (tree_kind != SYN_TREE_MCTS) return fail(SYN_ERR_UNSUPPORTED, "tree_kind %u: FrozenMCTS is not implemented on the device yet", tree_kind);
+    int rc = validate_cfg(cfg, e);
+    if (rc) return rc;
+    // reject positions the reference's MCTS is never built on: finished games, malformed boards
+    for (uint32_t i = 0; i < n && !is_device_ptr(my_bb) && !is_device_ptr(op_bb); ++i) {
+        uint64_t my = my_bb[i], op = op_bb[i];
+        if ((my & op) || ((my | op) >> 63)) return fail(SYN_ERR_INVALID_ARGUMENT, "position %u: overlapping or out-of-board stones", i);
+        if ((my | op) == c4::ALL) return fail(SYN_ERR_INVALID_ARGUMENT, "position %u is a full board", i);
+    }
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->h2d = 0; e->d2h = 0; e->launches = 0;
+    CUDA_TRY(e->pos_my.reserve(n)); CUDA_TRY(e->pos_op.reserve(n)); CUDA_TRY(e->pos_seed.reserve(n));
+    CUDA_TRY(e->s_visits.reserve((size_t)n * 9)); CUDA_TRY(e->s_q.reserve((size_t)n * 3)); CUDA_TRY(e->s_csol.reserve((size_t)n * 9));
+    CUDA_TRY(e->s_rsol.reserve(n)); CUDA_TRY(e->s_best.reserve(n)); CUDA_TRY(e->s_nodes.reserve(n));
+    CUDA_TRY(cudaMemcpyAsync(e->pos_my.p, my_bb, n * 8, cudaMemcpyDefault, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->pos_op.p, op_bb, n * 8, cudaMemcpyDefault, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->pos_seed.p, seeds, n * 8, cudaMemcpyDefault, e->stream));
+    e->h2d += (uint64_t)n * 24;
+    KParams kp;
+    fill_common(e, kp, cfg);
+    kp.num_games = n; kp.search_mode = 1;
+    kp.pos_my = e->pos_my.p; kp.pos_op = e->pos_op.p; kp.pos_seed = e->pos_seed.p;
+    kp.s_child_visits = e->s_visits.p; kp.s_child_sol = e->s_csol.p; kp.s_root_q = e->s_q.p; kp.s_root_sol = e->s_rsol.p;
+    kp.s_best = e->s_best.p; kp.s_nodes = e->s_nodes.p;
+    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_N * sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->error.p, 0, sizeof(int), e->stream));
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    rc = launch_selfplay(e, kp);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    rc = check_device_error(e);
+    if (rc) return rc;
+    if ((rc = deliver(e, child_visits, e->s_visits.p, (size_t)n * 36))) return rc;
+    if ((rc = deliver(e, child_solution, e->s_csol.p, (size_t)n * 9))) return rc;
+    if ((rc = deliver(e, root_q, e->s_q.p, (size_t)n * 12))) return rc;
+    if ((rc = deliver(e, root_solution, e->s_rsol.p, n))) return rc;
+    if ((rc = deliver(e, best_action, e->s_best.p, n))) return rc;
+    if ((rc = deliver(e, num_nodes, e->s_nodes.p, (size_t)n * 4))) return rc;
+    return read_stats(e, stats, ms);
+}
+
+int syn_engine_eval(syn_engine* e, const uint64_t* my_bb, const uint64_t* op_bb, uint32_t n, float* logits, float* outcome_probs) {
+    if (!e || !my_bb || !op_bb || !logits || !outcome_probs) return fail(SYN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!e->has_weights) return fail(SYN_ERR_NO_WEIGHTS, "syn_engine_set_weights has not been called");
+    if (n == 0) return SYN_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(e->pos_my.reserve(n)); CUDA_TRY(e->pos_op.reserve(n));
+    CUDA_TRY(e->s_visits.reserve((size_t)n * 9)); CUDA_TRY(e->s_q.reserve((size_t)n * 3));
+    CUDA_TRY(cudaMemcpyAsync(e->pos_my.p, my_bb, n * 8, cudaMemcpyDefault, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->pos_op.p, op_bb, n * 8, cudaMemcpyDefault, e->stream));
+    size_t smem = (size_t)(mlp::WEIGHT_FLOATS + 2 * 32 * mlp::XS) * sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(eval_kernel<NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t blocks = (n + 31) / 32;
+    if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
+    eval_kernel<NN_THREADS><<<blocks, NN_THREADS, smem, e->stream>>>(e->weights.p, e->pos_my.p, e->pos_op.p, n, e->s_visits.p, e->s_q.p);
+    CUDA_TRY(cudaGetLastError());
+    int rc;
+    if ((rc = deliver(e, logits, e->s_visits.p, (size_t)n * 36))) return rc;
+    if ((rc = deliver(e, outcome_probs, e->s_q.p, (size_t)n * 12))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SYN_OK;
+}
+
+int syn_engine_play(syn_engine* e, const uint8_t* moves, const uint32_t* n_moves, uint32_t stride, uint32_t n_games, uint64_t* my_bb,
+                    uint64_t* op_bb, uint8_t* height, uint8_t* legal_mask_lo, uint8_t* legal_mask_hi, uint8_t* status, float* features) {
+    if (!e || !moves || !n_moves || !my_bb || !op_bb || !height || !legal_mask_lo || !legal_mask_hi || !status)
+        return fail(SYN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_games == 0) return SYN_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    size_t mv = (size_t)n_games * stride;
+    size_t off_nm = (mv + 255) / 256 * 256;
+    size_t off_my = (off_nm + (size_t)n_games * 4 + 15) / 16 * 16, off_op = off_my + (size_t)n_games * 8;
+    size_t off_h = off_op + (size_t)n_games * 8, off_lo = off_h + (size_t)n_games * 9, off_hi = off_lo + n_games, off_st = off_hi + n_games;
+    size_t off_f = (off_st + n_games + 15) / 16 * 16, total = off_f + (features ? (size_t)n_games * 63 * 4 : 0);
+    CUDA_TRY(e->staging.reserve(total));
+    uint8_t* b = e->staging.p;
+    CUDA_TRY(cudaMemcpyAsync(b, moves, mv, cudaMemcpyDefault, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(b + off_nm, n_moves, (size_t)n_games * 4, cudaMemcpyDefault, e->stream));
+    uint32_t blocks = (n_games * 32 + 255) / 256;
+    play_kernel<<<blocks, 256, 0, e->stream>>>(b, (const uint32_t*)(b + off_nm), stride, n_games, (uint64_t*)(b + off_my), (uint64_t*)(b + off_op),
+                                               b + off_h, b + off_lo, b + off_hi, b + off_st, features ? (float*)(b + off_f) : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    int rc;
+    if ((rc = deliver(e, my_bb, b + off_my, (size_t)n_games * 8))) return rc;
+    if ((rc = deliver(e, op_bb, b + off_op, (size_t)n_games * 8))) return rc;
+    if ((rc = deliver(e, height, b + off_h, (size_t)n_games * 9))) return rc;
+    if ((rc = deliver(e, legal_mask_lo, b + off_lo, n_games))) return rc;
+    if ((rc = deliver(e, legal_mask_hi, b + off_hi, n_games))) return rc;
+    if ((rc = deliver(e, status, b + off_st, n_games))) return rc;
+    if (features && (rc = deliver(e, features, b + off_f, (size_t)n_games * 63 * 4))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SYN_OK;
+}
+
+} // extern "C"

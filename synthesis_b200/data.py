@@ -1,0 +1,93 @@
+"""`ReplayBuffer`, the experience-buffer output format of the reference
+(synthesis/src/data.rs:106-194), as numpy struct-of-arrays.  Same fields (`game_ids`, `games`
+— split into the four fields of `Connect4` —, `states`, `pis`, `vs`), same counters
+(`game_id`, `steps`) and the same `new_game / add / extend / keep_last_n_games` behaviour.
+"""
+import numpy as np
+
+from .connect4 import Connect4
+
+_FIELDS = (("game_ids", np.uint64, ()), ("my_bb", np.uint64, ()), ("op_bb", np.uint64, ()), ("height", np.uint8, (9,)),
+           ("player", np.uint8, ()), ("states", np.float32, (63,)), ("pis", np.float32, (9,)), ("vs", np.float32, (3,)))
+
+
+class ReplayBuffer:
+    def __init__(self, n: int = 0):  # data.rs:116-126 (n is only a capacity hint there too)
+        self.game_id = 0
+        self.steps = 0
+        for name, dt, shape in _FIELDS:
+            setattr(self, name, np.zeros((0,) + shape, dtype=dt))
+
+    # ---- data.rs:128-149
+    def new_game(self):
+        self.game_id += 1
+
+    def total_games_played(self) -> int:
+        return self.game_id
+
+    def curr_games(self) -> int:
+        if len(self.game_ids) == 0:
+            return 0
+        return int(1 + np.count_nonzero(self.game_ids[1:] != self.game_ids[:-1]))
+
+    def total_steps(self) -> int:
+        return self.steps
+
+    def curr_steps(self) -> int:
+        return len(self.vs)
+
+    @property
+    def games(self):
+        """`Vec<G>` view: rebuilds the Connect4 objects on demand."""
+        return [Connect4(int(m), int(o), [int(x) for x in h], int(p))
+                for m, o, h, p in zip(self.my_bb, self.op_bb, self.height, self.player)]
+
+    # ---- data.rs:151-158
+    def add(self, game: Connect4, pi, v):
+        row = dict(game_ids=self.game_id, my_bb=game.my_bb, op_bb=game.op_bb, height=game.height, player=game.player_,
+                   states=game.features().reshape(63), pis=pi, vs=v)
+        self.steps += 1
+        for name, dt, shape in _FIELDS:
+            arr = np.asarray(row[name], dtype=dt).reshape((1,) + shape)
+            setattr(self, name, np.concatenate([getattr(self, name), arr]))
+
+    # ---- data.rs:160-170
+    def extend(self, other: "ReplayBuffer"):
+        self.steps += other.steps
+        start = self.game_id
+        self.game_ids = np.concatenate([self.game_ids, other.game_ids + np.uint64(start)])
+        self.game_id += other.game_id
+        for name, dt, shape in _FIELDS[1:]:
+            setattr(self, name, np.concatenate([getattr(self, name), getattr(other, name)]))
+            setattr(other, name, np.zeros((0,) + shape, dtype=dt))  # drain(..)
+        # like the reference, other.game_ids is left untouched (only the drained Vecs are emptied)
+
+    # ---- data.rs:172-194
+    def keep_last_n_games(self, n: int):
+        if self.game_id <= n:
+            return
+        min_game_id = self.game_id - n
+        remove = int(np.searchsorted(self.game_ids, np.uint64(min_game_id), side="left")) if self._sorted() else self._prefix(min_game_id)
+        if remove:
+            for name, _, _ in _FIELDS:
+                setattr(self, name, getattr(self, name)[remove:])
+            assert len(self.game_ids) == 0 or self.game_ids[0] >= min_game_id
+
+    def _sorted(self) -> bool:
+        return bool(np.all(self.game_ids[1:] >= self.game_ids[:-1]))
+
+    def _prefix(self, min_game_id: int) -> int:
+        ge = np.nonzero(self.game_ids >= np.uint64(min_game_id))[0]
+        return int(ge[0]) if len(ge) else len(self.game_ids)
+
+    # ---- construction from the C ABI's syn_experience arrays
+    @staticmethod
+    def from_arrays(games_played: int, arrays: dict) -> "ReplayBuffer":
+        """A worker buffer as run_n_games returns it (alpha_zero.rs:181-209): game ids 1..games_played."""
+        b = ReplayBuffer()
+        n = len(arrays["vs"])
+        b.game_id = int(games_played)
+        b.steps = n
+        for name, dt, shape in _FIELDS:
+            setattr(b, name, np.ascontiguousarray(arrays[name], dtype=dt).reshape((n,) + shape))
+        return b

@@ -1,0 +1,155 @@
+"""`Engine`: one B200, one `syn_engine` (include/synthesis_b200.h).  Thin, typed access to the C ABI;
+numpy arrays in and out (or raw device pointers for the multi-GPU path).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .config import RolloutConfig
+from .data import ReplayBuffer
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, device: int = 0, max_games_in_flight: int = 4736, max_explores: int = 1600):
+        self._lib = L.load()
+        h = C.c_void_p()
+        L.check(self._lib.syn_engine_create(int(device), int(max_games_in_flight), int(max_explores), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.max_explores = int(max_explores)
+        self.max_games_in_flight = int(max_games_in_flight)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.syn_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- weights (replaces vs.load(models/<name>.ot), alpha_zero.rs:192-194)
+    def set_weights(self, blob):
+        """blob: numpy float32[30492] (host) or an int device pointer to 30492 floats."""
+        if isinstance(blob, int):
+            L.check(self._lib.syn_engine_set_weights(self._h, C.c_void_p(blob), L.N_WEIGHTS))
+            return
+        b = np.ascontiguousarray(blob, dtype=np.float32).reshape(-1)
+        L.check(self._lib.syn_engine_set_weights(self._h, _ptr(b), b.size))
+
+    def set_group_lanes(self, lanes: int):
+        L.check(self._lib.syn_engine_set_group_lanes(self._h, int(lanes)))
+
+    # ---- gather (replaces gather_experience/run_n_games/run_game, alpha_zero.rs:120-268)
+    @staticmethod
+    def _alloc(rows: int, trace: bool):
+        a = dict(game_ids=np.zeros(rows, np.uint64), my_bb=np.zeros(rows, np.uint64), op_bb=np.zeros(rows, np.uint64),
+                 height=np.zeros((rows, 9), np.uint8), player=np.zeros(rows, np.uint8),
+                 states=np.zeros((rows, 63), np.float32), pis=np.zeros((rows, 9), np.float32), vs=np.zeros((rows, 3), np.float32))
+        t = dict(action=np.zeros(rows, np.uint8), tree_nodes=np.zeros(rows, np.uint32),
+                 child_visits=np.zeros((rows, 9), np.float32)) if trace else None
+        return a, t
+
+    def gather(self, cfg: RolloutConfig, leaf_eval_kind: int, first_game_index: int, num_games: int, seed: int, trace: bool = False):
+        """Plays games [first_game_index, first_game_index+num_games).  Returns (arrays, stats, trace):
+        arrays = dict of the syn_experience fields trimmed to the rows written."""
+        ccfg = cfg.to_c(leaf_eval_kind)
+        rows = L.MAX_TURNS * int(num_games)
+        a, t = self._alloc(rows, trace)
+        exp = L.SynExperience()
+        exp.capacity = rows
+        for k in ("game_ids", "my_bb", "op_bb", "height", "player", "states", "pis", "vs"):
+            setattr(exp, k, a[k].ctypes.data)
+        if trace:
+            L.check(self._lib.syn_engine_set_trace(self._h, _ptr(t["action"]), _ptr(t["tree_nodes"]), _ptr(t["child_visits"])))
+        else:
+            L.check(self._lib.syn_engine_set_trace(self._h, None, None, None))
+        stats = L.SynStats()
+        try:
+            L.check(self._lib.syn_engine_gather(self._h, C.byref(ccfg), int(first_game_index), int(num_games), int(seed),
+                                                C.byref(exp), C.byref(stats)))
+        finally:
+            self._lib.syn_engine_set_trace(self._h, None, None, None)
+        n = int(exp.len)
+        a = {k: v[:n] for k, v in a.items()}
+        if trace:
+            t = {k: v[:n] for k, v in t.items()}
+        return a, stats.as_dict(), t
+
+    def gather_launch(self, cfg: RolloutConfig, leaf_eval_kind: int, first_game_index: int, num_games: int, seed: int):
+        ccfg = cfg.to_c(leaf_eval_kind)
+        L.check(self._lib.syn_engine_gather_launch(self._h, C.byref(ccfg), int(first_game_index), int(num_games), int(seed)))
+
+    def gather_wait(self, exp: "L.SynExperience" = None):
+        """Waits for the launched gather.  exp = None leaves the experience in HBM (bench `value` leg)."""
+        stats = L.SynStats()
+        L.check(self._lib.syn_engine_gather_wait(self._h, C.byref(exp) if exp is not None else None, C.byref(stats)))
+        return stats.as_dict()
+
+    def gather_into(self, cfg: RolloutConfig, leaf_eval_kind: int, first_game_index: int, num_games: int, seed: int, exp: "L.SynExperience"):
+        """gather with caller-owned (host or device) destination arrays already set in `exp`."""
+        ccfg = cfg.to_c(leaf_eval_kind)
+        stats = L.SynStats()
+        L.check(self._lib.syn_engine_gather(self._h, C.byref(ccfg), int(first_game_index), int(num_games), int(seed),
+                                            C.byref(exp), C.byref(stats)))
+        return stats.as_dict()
+
+    # ---- search (replaces MCTS::exploit / FrozenMCTS::exploit on a batch of roots)
+    def search(self, cfg: RolloutConfig, leaf_eval_kind: int, my_bb, op_bb, seeds, tree_kind: int = L.TREE_MCTS):
+        my = np.ascontiguousarray(my_bb, dtype=np.uint64).reshape(-1)
+        op = np.ascontiguousarray(op_bb, dtype=np.uint64).reshape(-1)
+        sd = np.ascontiguousarray(seeds, dtype=np.uint64).reshape(-1)
+        n = my.size
+        if op.size != n or sd.size != n:
+            raise ValueError("my_bb, op_bb and seeds must have the same length")
+        ccfg = cfg.to_c(leaf_eval_kind)
+        out = dict(child_visits=np.zeros((n, 9), np.float32), child_solution=np.zeros((n, 9), np.uint8),
+                   root_q=np.zeros((n, 3), np.float32), root_solution=np.zeros(n, np.uint8),
+                   best_action=np.zeros(n, np.uint8), num_nodes=np.zeros(n, np.uint32))
+        stats = L.SynStats()
+        L.check(self._lib.syn_engine_search(self._h, C.byref(ccfg), int(tree_kind), _ptr(my), _ptr(op), _ptr(sd), n,
+                                            _ptr(out["child_visits"]), _ptr(out["child_solution"]), _ptr(out["root_q"]),
+                                            _ptr(out["root_solution"]), _ptr(out["best_action"]), _ptr(out["num_nodes"]),
+                                            C.byref(stats)))
+        return out, stats.as_dict()
+
+    # ---- Policy::eval for Connect4Net on a batch
+    def eval(self, my_bb, op_bb):
+        my = np.ascontiguousarray(my_bb, dtype=np.uint64).reshape(-1)
+        op = np.ascontiguousarray(op_bb, dtype=np.uint64).reshape(-1)
+        n = my.size
+        logits = np.zeros((n, 9), np.float32)
+        probs = np.zeros((n, 3), np.float32)
+        L.check(self._lib.syn_engine_eval(self._h, _ptr(my), _ptr(op), n, _ptr(logits), _ptr(probs)))
+        return logits, probs
+
+    # ---- Game::step on move lists
+    def play(self, move_lists, features: bool = True):
+        n = len(move_lists)
+        stride = max(1, max((len(m) for m in move_lists), default=1))
+        moves = np.zeros((n, stride), np.uint8)
+        nm = np.zeros(n, np.uint32)
+        for i, m in enumerate(move_lists):
+            nm[i] = len(m)
+            moves[i, :len(m)] = np.asarray(m, dtype=np.uint8)
+        out = dict(my_bb=np.zeros(n, np.uint64), op_bb=np.zeros(n, np.uint64), height=np.zeros((n, 9), np.uint8),
+                   legal_lo=np.zeros(n, np.uint8), legal_hi=np.zeros(n, np.uint8), status=np.zeros(n, np.uint8),
+                   features=np.zeros((n, 63), np.float32) if features else None)
+        L.check(self._lib.syn_engine_play(self._h, _ptr(moves), _ptr(nm), stride, n, _ptr(out["my_bb"]), _ptr(out["op_bb"]),
+                                          _ptr(out["height"]), _ptr(out["legal_lo"]), _ptr(out["legal_hi"]), _ptr(out["status"]),
+                                          _ptr(out["features"])))
+        out["legal_mask"] = out["legal_lo"].astype(np.uint32) | (out["legal_hi"].astype(np.uint32) << 8)
+        return out

@@ -1,0 +1,157 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE (the checker, never the product)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from synthesis_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FLAG_LEGACY, FLAG_LIBM, FLAG_NO_CACHE = 1, 2, 4
+EVAL_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        l = self.lib
+        l.orc_expf.restype = C.c_float
+        l.orc_expf.argtypes = [C.c_float]
+        l.orc_logf.restype = C.c_float
+        l.orc_logf.argtypes = [C.c_float]
+        l.orc_stream_seed.restype = C.c_uint64
+        l.orc_stream_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_uint]
+        l.orc_outcome_value.restype = C.c_float
+        l.orc_outcome_from_f32.argtypes = [C.c_float]
+        l.orc_outcome_from_f32.restype = C.c_uint8
+        l.orc_outcome_reversed.restype = C.c_uint8
+        l.orc_keep_last_n_games_prefix.restype = C.c_size_t
+        l.orc_keep_last_n_games_prefix.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64]
+        l.orc_search.argtypes = [C.POINTER(L.SynRolloutCfg), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.POINTER(L.SynStats)]
+        l.orc_gather.argtypes = [C.POINTER(L.SynRolloutCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                 C.c_int, C.c_uint32, C.POINTER(L.SynExperience), C.POINTER(L.SynStats), C.c_void_p, C.c_void_p, C.c_void_p]
+        l.orc_gather_reference.argtypes = [C.POINTER(L.SynRolloutCfg), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                           C.POINTER(L.SynExperience), C.POINTER(L.SynStats), C.c_void_p, C.c_void_p]
+        l.orc_mlp_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        l.orc_c4_play.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8
+        l.orc_c4_won.argtypes = [C.c_uint64]
+        l.orc_ttt_kat.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.orc_stdrng_words.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
+        l.orc_gen_range_u8.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
+        l.orc_weighted_index.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
+        l.orc_dirichlet.argtypes = [C.c_uint64, C.c_float, C.c_int, C.c_uint32, C.c_void_p]
+        l.orc_normal.argtypes = [C.c_uint64, C.c_float, C.c_float, C.c_uint32, C.c_void_p]
+        l.orc_chacha_block.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        l.orc_seed_key.argtypes = [C.c_uint64, C.c_void_p]
+        l.orc_outcome_cmp.argtypes = [C.c_uint8, C.c_uint8]
+        l.orc_outcome_reversed.argtypes = [C.c_uint8]
+        l.orc_outcome_value.argtypes = [C.c_uint8]
+        l.orc_c4_player.argtypes = [C.c_uint64, C.c_uint64]
+
+    # ---- streams
+    def stdrng_words(self, seed, n):
+        out = np.zeros(n, np.uint32)
+        self.lib.orc_stdrng_words(seed, n, _p(out))
+        return out
+
+    def gen_range_u8(self, seed, n, count):
+        out = np.zeros(count, np.uint8)
+        self.lib.orc_gen_range_u8(seed, n, count, _p(out))
+        return out
+
+    def weighted_index(self, seed, w, count):
+        w = np.ascontiguousarray(w, np.float32)
+        out = np.zeros(count, np.int32)
+        self.lib.orc_weighted_index(seed, _p(w), len(w), count, _p(out))
+        return out
+
+    def dirichlet(self, seed, alpha, k, count):
+        out = np.zeros((count, k), np.float32)
+        self.lib.orc_dirichlet(seed, alpha, k, count, _p(out))
+        return out
+
+    def normal(self, seed, mean, std, count):
+        out = np.zeros(count, np.float32)
+        self.lib.orc_normal(seed, mean, std, count, _p(out))
+        return out
+
+    # ---- Connect4
+    def c4_play(self, moves):
+        m = np.ascontiguousarray(moves, np.uint8)
+        my, op = C.c_uint64(), C.c_uint64()
+        h = np.zeros(9, np.uint8)
+        lm, st = C.c_uint32(), C.c_uint8()
+        f = np.zeros(63, np.float32)
+        rw = C.c_float()
+        so = np.zeros(max(1, len(m)), np.uint8)
+        rc = self.lib.orc_c4_play(_p(m), len(m), C.byref(my), C.byref(op), _p(h), C.byref(lm), C.byref(st), _p(f), C.byref(rw), _p(so))
+        if rc:
+            return None
+        return dict(my_bb=my.value, op_bb=op.value, height=h, legal_mask=lm.value, status=st.value, features=f,
+                    reward_to_move=rw.value, step_over=so[:len(m)])
+
+    # ---- trees
+    def search(self, ccfg, my_bb, op_bb, seed, tree_kind=0, weights=None, callback=None, flags=0):
+        cv, cs, rq = np.zeros(9, np.float32), np.zeros(9, np.uint8), np.zeros(3, np.float32)
+        rs, ba, nn = C.c_uint8(), C.c_uint8(), C.c_uint32()
+        st = L.SynStats()
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        cb = EVAL_FN(callback) if callback else None
+        rc = self.lib.orc_search(C.byref(ccfg), tree_kind, int(my_bb), int(op_bb), int(seed), _p(w), C.cast(cb, C.c_void_p) if cb else None,
+                                 None, flags, _p(cv), _p(cs), _p(rq), C.cast(C.byref(rs), C.c_void_p), C.cast(C.byref(ba), C.c_void_p),
+                                 C.cast(C.byref(nn), C.c_void_p), C.byref(st))
+        assert rc == 0, rc
+        return dict(child_visits=cv, child_solution=cs, root_q=rq, root_solution=rs.value, best_action=ba.value, num_nodes=nn.value), st.as_dict()
+
+    def gather(self, ccfg, seed, first_game, num_games, weights=None, callback=None, threads=1, flags=0, trace=True):
+        rows = 63 * num_games
+        a = dict(game_ids=np.zeros(rows, np.uint64), my_bb=np.zeros(rows, np.uint64), op_bb=np.zeros(rows, np.uint64),
+                 height=np.zeros((rows, 9), np.uint8), player=np.zeros(rows, np.uint8), states=np.zeros((rows, 63), np.float32),
+                 pis=np.zeros((rows, 9), np.float32), vs=np.zeros((rows, 3), np.float32))
+        t = dict(action=np.zeros(rows, np.uint8), tree_nodes=np.zeros(rows, np.uint32), child_visits=np.zeros((rows, 9), np.float32))
+        exp = L.SynExperience()
+        exp.capacity = rows
+        for k in a:
+            setattr(exp, k, a[k].ctypes.data)
+        st = L.SynStats()
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        cb = EVAL_FN(callback) if callback else None
+        rc = self.lib.orc_gather(C.byref(ccfg), _p(w), C.cast(cb, C.c_void_p) if cb else None, None, int(seed), int(first_game),
+                                 int(num_games), int(threads), flags, C.byref(exp), C.byref(st),
+                                 _p(t["action"]) if trace else None, _p(t["tree_nodes"]) if trace else None,
+                                 _p(t["child_visits"]) if trace else None)
+        assert rc == 0, rc
+        n = int(exp.len)
+        return {k: v[:n] for k, v in a.items()}, st.as_dict(), {k: v[:n] for k, v in t.items()}
+
+    def gather_reference(self, ccfg, weights, num_workers, games_per_train, seed, flags=0, want_rows=False):
+        st = L.SynStats()
+        w = np.ascontiguousarray(weights, np.float32)
+        hits, misses = C.c_uint64(), C.c_uint64()
+        rc = self.lib.orc_gather_reference(C.byref(ccfg), _p(w), num_workers, games_per_train, int(seed), flags, None, C.byref(st),
+                                           C.cast(C.byref(hits), C.c_void_p), C.cast(C.byref(misses), C.c_void_p))
+        assert rc == 0, rc
+        d = st.as_dict()
+        d["cache_hits"], d["cache_misses"] = hits.value, misses.value
+        return d
+
+    def mlp_eval(self, weights, my_bb, op_bb, flags=0):
+        w = np.ascontiguousarray(weights, np.float32)
+        my = np.ascontiguousarray(my_bb, np.uint64)
+        op = np.ascontiguousarray(op_bb, np.uint64)
+        n = my.size
+        lg, pr = np.zeros((n, 9), np.float32), np.zeros((n, 3), np.float32)
+        self.lib.orc_mlp_eval(_p(w), _p(my), _p(op), n, flags, _p(lg), _p(pr))
+        return lg, pr
+
+    def ttt_kat(self, which, flags):
+        nodes, best, rs = C.c_uint32(), C.c_int(), C.c_uint8()
+        cs = np.zeros(9, np.uint8)
+        self.lib.orc_ttt_kat(which, flags, C.cast(C.byref(nodes), C.c_void_p), C.cast(C.byref(best), C.c_void_p), _p(cs),
+                             C.cast(C.byref(rs), C.c_void_p))
+        return nodes.value, best.value, cs, rs.value

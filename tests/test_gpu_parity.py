@@ -1,0 +1,321 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Integer / index / visit-count work must be bit-exact; network outputs within 1e-3.
+"""
+import numpy as np
+import pytest
+
+import synthesis_b200 as s
+from synthesis_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+EXP_FIELDS = ("game_ids", "my_bb", "op_bb", "height", "player", "states", "pis", "vs")
+
+
+def assert_rows_equal(a, b, what):
+    for k in a:
+        assert a[k].shape == b[k].shape, f"{what}: {k} shape {a[k].shape} vs {b[k].shape}"
+        if a[k].dtype.kind == "f":
+            same = a[k].view(np.uint32) == b[k].view(np.uint32)
+        else:
+            same = a[k] == b[k]
+        if not np.all(same):
+            bad = np.argwhere(~same)[0]
+            raise AssertionError(f"{what}: {k} differs first at {tuple(bad)}: gpu={a[k][tuple(bad)]!r} oracle={b[k][tuple(bad)]!r}")
+
+
+def random_positions(rng, n, max_plies=40):
+    """Non-terminal positions reached by random legal play (host mirror of Game::step)."""
+    out = []
+    while len(out) < n:
+        g = s.Connect4.new()
+        k = int(rng.integers(0, max_plies))
+        ok = True
+        for _ in range(k):
+            acts = list(g.iter_actions())
+            if g.step(acts[int(rng.integers(0, len(acts)))]):
+                ok = False
+                break
+        if ok:
+            out.append(g)
+    return out
+
+
+# ---------------------------------------------------------------- A1/A2: the game kernel
+def test_game_kernel_matches_oracle_on_random_playouts(engine, oracle):
+    rng = np.random.default_rng(7)
+    lists = []
+    for _ in range(4000):
+        g = s.Connect4.new()
+        ms = []
+        for _ in range(int(rng.integers(0, 64))):
+            acts = list(g.iter_actions())
+            a = acts[int(rng.integers(0, len(acts)))]
+            ms.append(a)
+            if g.step(a):
+                break
+        lists.append(ms)
+    lists.append([])  # the empty board
+    out = engine.play(lists)
+    for i, ms in enumerate(lists):
+        ref = oracle.c4_play(ms)
+        assert int(out["my_bb"][i]) == ref["my_bb"] and int(out["op_bb"][i]) == ref["op_bb"], (i, ms)
+        assert np.array_equal(out["height"][i], ref["height"])
+        assert int(out["legal_mask"][i]) == ref["legal_mask"]
+        assert int(out["status"][i]) == ref["status"], (i, ms, out["status"][i], ref["status"])
+        assert np.array_equal(out["features"][i].view(np.uint32), ref["features"].view(np.uint32))
+
+
+def test_game_kernel_reference_unit_tests(engine):
+    # connect4.rs:300-334 (first/second player wins) and :337-447 (the 63-ply draw)
+    first = [0, 1, 0, 1, 0, 1, 0]
+    second = [0, 1, 2, 1, 2, 1, 2, 1]
+    draw = []
+    for pair in range(4):
+        a, b = 2 * pair, 2 * pair + 1
+        draw += [a, b, a, b, b, a, b, a, a, b, a, b, a, b]
+    draw += [8] * 7
+    out = engine.play([first, first[:-1], second, second[:-1], draw, draw[:-1], [0] * 8])
+    assert list(out["status"]) == [3, 0, 3, 0, 1, 0, 255]
+    assert int(out["legal_mask"][4]) == 0 and int(out["legal_mask"][5]) == 1 << 8
+    assert list(out["height"][4]) == [7] * 9
+
+
+# ---------------------------------------------------------------- A4-A10: one tree, rollout leaves
+@pytest.mark.parametrize("explores", [1, 50, 800])
+def test_search_rollout_bit_exact(engine, oracle, explores):
+    rng = np.random.default_rng(explores)
+    games = [s.Connect4.new()] + random_positions(rng, 47)
+    # the survey's solved-root positions
+    for ms in ([4, 4, 3, 3], [4, 3, 4, 3, 4, 3]):
+        g = s.Connect4.new()
+        for m in ms:
+            g.step(m)
+        games.append(g)
+    cfg = s.study_connect4_rollout_cfg(num_explores=explores)
+    seeds = np.arange(len(games), dtype=np.uint64) * 3 + 1
+    seeds[0] = 0
+    out, stats = engine.search(cfg, L.LEAF_ROLLOUT, [g.my_bb for g in games], [g.op_bb for g in games], seeds)
+    ccfg = cfg.to_c(L.LEAF_ROLLOUT)
+    tot = dict(explores=0, nodes=0, select_levels=0, children_scanned=0, expansions=0, leaf_evals=0, rollout_plies=0, backprop_levels=0)
+    for i, g in enumerate(games):
+        ref, st = oracle.search(ccfg, g.my_bb, g.op_bb, int(seeds[i]))
+        for k in tot:
+            tot[k] += st[k]
+        assert np.array_equal(out["child_visits"][i], ref["child_visits"]), (i, out["child_visits"][i], ref["child_visits"])
+        assert np.array_equal(out["child_solution"][i], ref["child_solution"]), i
+        assert np.array_equal(out["root_q"][i].view(np.uint32), ref["root_q"].view(np.uint32)), i
+        assert int(out["root_solution"][i]) == ref["root_solution"], i
+        assert int(out["best_action"][i]) == ref["best_action"], i
+        assert int(out["num_nodes"][i]) == ref["num_nodes"], i
+    for k in tot:
+        assert stats[k] == tot[k], (k, stats[k], tot[k])
+    if explores == 800:  # SURVEY.md §8(c) vector for the empty board, seed 0
+        assert list(out["child_visits"][0]) == [47, 38, 87, 76, 41, 343, 24, 125, 19]
+        assert int(out["num_nodes"][0]) == 7210
+
+
+def test_search_uct_config_bit_exact(engine, oracle):
+    """The evaluator's rollout-baseline config (UCT c=2, FPU=+inf, no auto-extend): exercises ln(),
+    inf/NaN comparisons and ActionSelection::Q."""
+    rng = np.random.default_rng(5)
+    games = [s.Connect4.new()] + random_positions(rng, 31)
+    cfg = s.study_connect4_rollout_cfg(num_explores=300, mcts_cfg=s.study_connect4_rollout_mcts_cfg())
+    cfg.action = s.ActionSelection.Q
+    seeds = np.arange(len(games), dtype=np.uint64) + 100
+    out, _ = engine.search(cfg, L.LEAF_ROLLOUT, [g.my_bb for g in games], [g.op_bb for g in games], seeds)
+    ccfg = cfg.to_c(L.LEAF_ROLLOUT)
+    for i, g in enumerate(games):
+        ref, _ = oracle.search(ccfg, g.my_bb, g.op_bb, int(seeds[i]))
+        assert np.array_equal(out["child_visits"][i], ref["child_visits"]), (i, out["child_visits"][i], ref["child_visits"])
+        assert int(out["best_action"][i]) == ref["best_action"], i
+        assert int(out["num_nodes"][i]) == ref["num_nodes"], i
+
+
+@pytest.mark.parametrize("variant", ["no_solve", "no_correct", "no_select_solved", "parent_q", "equal_noise", "dirichlet", "fpu_normal"])
+def test_search_config_variants_bit_exact(engine, oracle, variant):
+    rng = np.random.default_rng(11)
+    games = [s.Connect4.new()] + random_positions(rng, 23, max_plies=30)
+    m = s.study_connect4_mcts_cfg()
+    if variant == "no_solve":
+        m.solve = False
+    elif variant == "no_correct":
+        m.correct_values_on_solve = False
+    elif variant == "no_select_solved":
+        m.select_solved_nodes = False
+    elif variant == "parent_q":
+        m.fpu = s.Fpu.ParentQ()
+    elif variant == "equal_noise":
+        m.root_policy_noise = s.PolicyNoise.Equal(0.25)
+    elif variant == "dirichlet":
+        m.root_policy_noise = s.PolicyNoise.Dirichlet(1.0, 0.25)
+    elif variant == "fpu_normal":
+        m.fpu = s.Fpu.Normal(1.0, 0.1)
+    cfg = s.study_connect4_rollout_cfg(num_explores=200, mcts_cfg=m)
+    seeds = np.arange(len(games), dtype=np.uint64) + 9
+    out, _ = engine.search(cfg, L.LEAF_ROLLOUT, [g.my_bb for g in games], [g.op_bb for g in games], seeds)
+    ccfg = cfg.to_c(L.LEAF_ROLLOUT)
+    for i, g in enumerate(games):
+        ref, _ = oracle.search(ccfg, g.my_bb, g.op_bb, int(seeds[i]))
+        assert np.array_equal(out["child_visits"][i], ref["child_visits"]), (variant, i, out["child_visits"][i], ref["child_visits"])
+        assert np.array_equal(out["child_solution"][i], ref["child_solution"]), (variant, i)
+        assert np.array_equal(out["root_q"][i].view(np.uint32), ref["root_q"].view(np.uint32)), (variant, i)
+        assert int(out["num_nodes"][i]) == ref["num_nodes"], (variant, i)
+
+
+# ---------------------------------------------------------------- A11/A12: whole games, rollout leaves
+@pytest.mark.parametrize("explores,games,sample_until,vt", [(50, 64, 0, "Q"), (200, 24, 30, "Z"), (800, 8, 30, "QtoZ"), (100, 16, 10, "QZ")])
+def test_gather_rollout_bit_exact(engine, oracle, explores, games, sample_until, vt):
+    cfg = s.study_connect4_rollout_cfg(num_explores=explores, sample_actions_until=sample_until)
+    cfg.value_target = {"Q": s.ValueTarget.Q(), "Z": s.ValueTarget.Z(), "QtoZ": s.ValueTarget.QtoZ(0.25, 0.75),
+                        "QZ": s.ValueTarget.QZaverage(0.3)}[vt]
+    a, st, tr = engine.gather(cfg, L.LEAF_ROLLOUT, first_game_index=3, num_games=games, seed=0, trace=True)
+    ra, rst, rtr = oracle.gather(cfg.to_c(L.LEAF_ROLLOUT), 0, 3, games, threads=8)
+    assert_rows_equal(tr, rtr, "trace")
+    assert_rows_equal(a, ra, "experience")
+    for k in ("explores", "leaf_evals", "rows", "games", "trees", "nodes", "select_levels", "children_scanned", "expansions",
+              "children_created", "backprop_levels", "rollout_plies"):
+        assert st[k] == rst[k], (k, st[k], rst[k])
+
+
+def test_gather_survey_vectors(engine):
+    """g=0..2 at E=50 with random_actions_until=1, sample_actions_until=0."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=50, sample_actions_until=0)
+    a, st, tr = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 3, 0, trace=True)
+    moves = ["743641716112556277605", "542042434480676008355502302", "15462382653550447302"]
+    sums = [8130, 10374, 8021]
+    off = 0
+    for g in range(3):
+        n = len(moves[g])
+        assert "".join(str(int(x)) for x in tr["action"][off:off + n]) == moves[g]
+        assert int(tr["tree_nodes"][off:off + n].sum()) == sums[g]
+        assert np.all(a["game_ids"][off:off + n] == g + 1)
+        off += n
+    assert off == len(a["vs"])
+    assert a["vs"][0].tolist() == [np.float32(15) / np.float32(51), 0.0, np.float32(36) / np.float32(51)]
+
+
+def test_gather_stop_games_when_solved(engine, oracle):
+    cfg = s.study_connect4_rollout_cfg(num_explores=400, sample_actions_until=8)
+    cfg.stop_games_when_solved = True
+    cfg.value_target = s.ValueTarget.Z()
+    a, st, tr = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 24, 5, trace=True)
+    ra, rst, rtr = oracle.gather(cfg.to_c(L.LEAF_ROLLOUT), 5, 0, 24, threads=8)
+    assert_rows_equal(tr, rtr, "trace")
+    assert_rows_equal(a, ra, "experience")
+
+
+def test_group_lanes_do_not_change_results(engine):
+    cfg = s.study_connect4_rollout_cfg(num_explores=100)
+    engine.set_group_lanes(32)
+    a32, _, t32 = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 40, 1, trace=True)
+    engine.set_group_lanes(16)
+    try:
+        a16, _, t16 = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 40, 1, trace=True)
+    finally:
+        engine.set_group_lanes(32)
+    assert_rows_equal(a16, a32, "GL16 vs GL32 experience")
+    assert_rows_equal(t16, t32, "GL16 vs GL32 trace")
+
+
+def test_sharding_is_invisible(engine):
+    """Games are seeded by their global index: two shards concatenated == one call."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=60)
+    whole, _, _ = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 48, 2)
+    lo, _, _ = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 20, 2)
+    hi, _, _ = engine.gather(cfg, L.LEAF_ROLLOUT, 20, 28, 2)
+    cat = {k: np.concatenate([lo[k], hi[k]]) for k in whole}
+    assert_rows_equal(cat, whole, "shards vs whole")
+
+
+# ---------------------------------------------------------------- A9: the network
+def test_nn_eval_within_tolerance(engine, oracle):
+    net = s.Connect4Net.new(0)
+    engine.set_weights(net.blob())
+    rng = np.random.default_rng(3)
+    games = [s.Connect4.new()] + random_positions(rng, 999, max_plies=60)
+    my = [g.my_bb for g in games]
+    op = [g.op_bb for g in games]
+    lg, pr = engine.eval(my, op)
+    rl, rp = oracle.mlp_eval(net.blob(), my, op)
+    # BASELINE.json north_star: within 1e-3 abs/rel of the fp32 forward
+    np.testing.assert_allclose(lg, rl, rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(pr, rp, rtol=1e-3, atol=1e-3)
+    assert np.allclose(pr.sum(1), 1.0, atol=1e-5)
+
+
+def _gpu_leaf_callback(engine):
+    def cb(ctx, my, op, logits, probs):
+        lg, pr = engine.eval([my], [op])
+        for i in range(9):
+            logits[i] = float(lg[0, i])
+        for i in range(3):
+            probs[i] = float(pr[0, i])
+    return cb
+
+
+def test_search_nn_tree_bit_exact_given_gpu_leaf_outputs(engine, oracle):
+    """Tree logic is bit-exact when the oracle is fed the GPU's (logits, value) per leaf."""
+    net = s.Connect4Net.new(1)
+    engine.set_weights(net.blob())
+    rng = np.random.default_rng(13)
+    games = [s.Connect4.new()] + random_positions(rng, 5, max_plies=30)
+    cfg = s.study_connect4_rollout_cfg(num_explores=150)
+    seeds = np.zeros(len(games), np.uint64)
+    out, _ = engine.search(cfg, L.LEAF_NN, [g.my_bb for g in games], [g.op_bb for g in games], seeds)
+    ccfg = cfg.to_c(L.LEAF_NN)
+    cb = _gpu_leaf_callback(engine)
+    for i, g in enumerate(games):
+        ref, _ = oracle.search(ccfg, g.my_bb, g.op_bb, 0, callback=cb)
+        assert np.array_equal(out["child_visits"][i], ref["child_visits"]), (i, out["child_visits"][i], ref["child_visits"])
+        assert np.array_equal(out["child_solution"][i], ref["child_solution"]), i
+        assert np.array_equal(out["root_q"][i].view(np.uint32), ref["root_q"].view(np.uint32)), i
+        assert int(out["num_nodes"][i]) == ref["num_nodes"], i
+
+
+def test_gather_nn_bit_exact_given_gpu_leaf_outputs(engine, oracle):
+    net = s.Connect4Net.new(2)
+    engine.set_weights(net.blob())
+    cfg = s.study_connect4_rollout_cfg(num_explores=60, sample_actions_until=12)
+    a, st, tr = engine.gather(cfg, L.LEAF_NN, 0, 6, 4, trace=True)
+    ra, rst, rtr = oracle.gather(cfg.to_c(L.LEAF_NN), 4, 0, 6, callback=_gpu_leaf_callback(engine), threads=1)
+    assert_rows_equal(tr, rtr, "trace")
+    assert_rows_equal(a, ra, "experience")
+
+
+def test_gather_nn_close_to_fp32_oracle(engine, oracle):
+    """Against the oracle's OWN fp32 forward the trees may differ after a near-tie, but Q values of
+    the first ply (identical position, 800 explores) must agree to 1e-3-ish and games must be legal."""
+    net = s.Connect4Net.new(0)
+    engine.set_weights(net.blob())
+    cfg = s.study_connect4_rollout_cfg(num_explores=200)
+    a, st, tr = engine.gather(cfg, L.LEAF_NN, 0, 32, 0, trace=True)
+    ra, rst, rtr = oracle.gather(cfg.to_c(L.LEAF_NN), 0, 0, 32, weights=net.blob(), threads=8)
+    first_gpu = a["vs"][np.r_[True, a["game_ids"][1:] != a["game_ids"][:-1]]]
+    first_ref = ra["vs"][np.r_[True, ra["game_ids"][1:] != ra["game_ids"][:-1]]]
+    np.testing.assert_allclose(first_gpu, first_ref, rtol=1e-3, atol=1e-3)
+    # fraction of rows that are bit-identical is reported, not asserted (near-ties may flip)
+    n = min(len(a["vs"]), len(ra["vs"]))
+    same = np.mean(np.all(a["pis"][:n] == ra["pis"][:n], axis=1))
+    print(f"rows identical to the fp32-oracle run: {same:.3f}")
+    assert np.allclose(a["pis"].sum(1), 1.0, atol=1e-5)
+
+
+# ---------------------------------------------------------------- errors
+def test_error_behaviour(engine):
+    cfg = s.study_connect4_rollout_cfg(num_explores=10)
+    cfg.mcts_cfg.fpu = s.Fpu.Func(lambda: 1.0)
+    with pytest.raises(L.EngineError) as e:
+        engine.gather(cfg, L.LEAF_ROLLOUT, 0, 4, 0)
+    assert e.value.code == L.SYN_ERR_UNSUPPORTED
+    cfg = s.study_connect4_rollout_cfg(num_explores=100000)
+    with pytest.raises(L.EngineError) as e:
+        engine.gather(cfg, L.LEAF_ROLLOUT, 0, 4, 0)
+    assert e.value.code == L.SYN_ERR_CAPACITY
+    fresh = s.Engine(0, 64, 50)
+    try:
+        with pytest.raises(L.EngineError) as e:
+            fresh.gather(s.study_connect4_rollout_cfg(num_explores=10), L.LEAF_NN, 0, 4, 0)
+        assert e.value.code == L.SYN_ERR_NO_WEIGHTS
+    finally:
+        fresh.close()
