@@ -212,6 +212,11 @@ int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, f
  * the SYN_GROUP_LANES environment variable at syn_engine_create.  Results do not depend on it. */
 int syn_engine_set_group_lanes(syn_engine* e, int lanes);
 
+/* Which kernel evaluates Connect4Net: 1 (default) = fp16-operand / fp32-accumulate GEMM chain on the
+ * tcgen05 tensor cores; 0 = fp32 CUDA-core kernel (kept as the device-side numerical reference).
+ * The SYN_MLP=fp32 environment variable selects 0 at syn_engine_create. */
+int syn_engine_set_mlp_mode(syn_engine* e, int tensor_cores);
+
 /* Packed Option<Outcome> (synthesis/src/game.rs:9-14): 0 = None, else kind<<6 | turns with
  * kind 1 = Lose, 2 = Draw, 3 = Win; turns <= 63. */
 #define SYN_OUTCOME_NONE 0u

@@ -64,7 +64,9 @@ struct syn_engine {
     DevBuf<float4> stat;
     DevBuf<uint4> meta;
     DevBuf<float> weights;
+    DevBuf<uint8_t> weight_image; // mlptc layout (fp16 weights + fp32 biases)
     bool has_weights = false;
+    bool use_tc = true;           // Connect4Net on tcgen05 tensor cores (false: fp32 CUDA-core kernel)
     DevBuf<unsigned int> next_game;
     DevBuf<unsigned long long> counters;
     DevBuf<int> error;
@@ -120,6 +122,7 @@ static int validate_cfg(const syn_rollout_cfg* cfg, const syn_engine* e) {
     return SYN_OK;
 }
 
+static size_t nn_tc_smem_bytes(int gpb) { return sizeof(mlptc::Smem) + (size_t)gpb * 64 * sizeof(uint32_t); }
 static size_t nn_smem_bytes(int gpb) { return (size_t)(mlp::WEIGHT_FLOATS + 2 * gpb * mlp::XS + gpb * 64) * sizeof(float); }
 
 constexpr int ROLLOUT_THREADS = 256;
@@ -141,7 +144,16 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
     }
     if (blocks == 0) blocks = 1;
     CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-    if (nn) {
+    if (nn && e->use_tc) {
+        size_t smem = nn_tc_smem_bytes(gpb);
+        if (gl == 32) {
+            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tc_kernel<32, NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            selfplay_nn_tc_kernel<32, NN_THREADS><<<blocks, threads, smem, e->stream>>>(kp);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tc_kernel<16, NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            selfplay_nn_tc_kernel<16, NN_THREADS><<<blocks, threads, smem, e->stream>>>(kp);
+        }
+    } else if (nn) {
         size_t smem = nn_smem_bytes(gpb);
         if (gl == 32) {
             CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_kernel<32, NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -169,6 +181,7 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.counters = e->counters.p;
     kp.error = e->error.p;
     kp.weights = e->weights.p;
+    kp.weight_image = e->weight_image.p;
 }
 
 static int read_stats(syn_engine* e, syn_stats* stats, float ms) {
@@ -229,6 +242,8 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     syn_engine* e = new syn_engine();
     e->device = cuda_device;
     e->sm_count = prop.multiProcessorCount;
+    const char* mlpenv = std::getenv("SYN_MLP");
+    e->use_tc = !(mlpenv && std::strcmp(mlpenv, "fp32") == 0);
     const char* glenv = std::getenv("SYN_GROUP_LANES");
     e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : 32;
     // round the in-flight game count up to whole CTAs of either kernel
@@ -243,7 +258,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
         (ce = e->stat.reserve(total)) != cudaSuccess || (ce = e->meta.reserve(total)) != cudaSuccess ||
-        (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
+        (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->weight_image.reserve(mlptc::IMG_BYTES)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
         (ce = e->counters.reserve(CNT_N)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
         int rc = fail(SYN_ERR_CUDA, "engine allocation failed (%zu arena nodes = %.1f MiB): %s", total,
                       (double)total * 32.0 / 1048576.0, cudaGetErrorString(ce));
@@ -258,7 +273,7 @@ void syn_engine_destroy(syn_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->stat.release(); e->meta.release(); e->weights.release(); e->next_game.release(); e->counters.release(); e->error.release();
+    e->stat.release(); e->meta.release(); e->weights.release(); e->weight_image.release(); e->next_game.release(); e->counters.release(); e->error.release();
     e->row_my.release(); e->row_op.release(); e->row_off.release(); e->row_pi.release(); e->row_v.release(); e->row_visits.release();
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();
@@ -275,12 +290,20 @@ int syn_engine_set_group_lanes(syn_engine* e, int lanes) {
     return SYN_OK;
 }
 
+int syn_engine_set_mlp_mode(syn_engine* e, int tensor_cores) {
+    if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    e->use_tc = tensor_cores != 0;
+    return SYN_OK;
+}
+
 int syn_engine_set_weights(syn_engine* e, const float* blob, size_t n_floats) {
     if (!e || !blob) return fail(SYN_ERR_INVALID_ARGUMENT, "engine or blob is NULL");
     if (n_floats != SYN_N_WEIGHTS) return fail(SYN_ERR_INVALID_ARGUMENT, "expected %d floats (63-128-96-64-48-12 MLP), got %zu", SYN_N_WEIGHTS, n_floats);
     CUDA_TRY(cudaSetDevice(e->device));
     bool dev = is_device_ptr(blob);
     CUDA_TRY(cudaMemcpyAsync(e->weights.p, blob, n_floats * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p);
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (!dev) e->h2d += n_floats * sizeof(float);
     e->has_weights = true;
@@ -464,11 +487,19 @@ int syn_engine_eval(syn_engine* e, const uint64_t* my_bb, const uint64_t* op_bb,
     CUDA_TRY(e->s_visits.reserve((size_t)n * 9)); CUDA_TRY(e->s_q.reserve((size_t)n * 3));
     CUDA_TRY(cudaMemcpyAsync(e->pos_my.p, my_bb, n * 8, cudaMemcpyDefault, e->stream));
     CUDA_TRY(cudaMemcpyAsync(e->pos_op.p, op_bb, n * 8, cudaMemcpyDefault, e->stream));
-    size_t smem = (size_t)(mlp::WEIGHT_FLOATS + 2 * 32 * mlp::XS) * sizeof(float);
-    CUDA_TRY(cudaFuncSetAttribute(eval_kernel<NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t blocks = (n + 31) / 32;
-    if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
-    eval_kernel<NN_THREADS><<<blocks, NN_THREADS, smem, e->stream>>>(e->weights.p, e->pos_my.p, e->pos_op.p, n, e->s_visits.p, e->s_q.p);
+    if (e->use_tc) {
+        size_t smem = sizeof(mlptc::Smem);
+        CUDA_TRY(cudaFuncSetAttribute(eval_tc_kernel<NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uint32_t blocks = (n + 127) / 128;
+        if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
+        eval_tc_kernel<NN_THREADS><<<blocks, NN_THREADS, smem, e->stream>>>(e->weight_image.p, e->pos_my.p, e->pos_op.p, n, e->s_visits.p, e->s_q.p);
+    } else {
+        size_t smem = (size_t)(mlp::WEIGHT_FLOATS + 2 * 32 * mlp::XS) * sizeof(float);
+        CUDA_TRY(cudaFuncSetAttribute(eval_kernel<NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uint32_t blocks = (n + 31) / 32;
+        if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
+        eval_kernel<NN_THREADS><<<blocks, NN_THREADS, smem, e->stream>>>(e->weights.p, e->pos_my.p, e->pos_op.p, n, e->s_visits.p, e->s_q.p);
+    }
     CUDA_TRY(cudaGetLastError());
     int rc;
     if ((rc = deliver(e, logits, e->s_visits.p, (size_t)n * 36))) return rc;

@@ -17,6 +17,7 @@
 //                  semantics stay strictly sequential (no virtual loss).
 #pragma once
 #include "mlp.cuh"
+#include "mlp_tc.cuh"
 #include "tree.cuh"
 
 namespace eng {
@@ -52,6 +53,7 @@ struct KParams {
     unsigned long long* counters; // [CNT_N]
     int* error;
     const float* weights; // device blob, NN mode
+    const uint8_t* weight_image; // mlptc image (fp16 UMMA layout), NN mode on tensor cores
 };
 
 enum Phase { PH_NEED_GAME = 0, PH_NEW_TREE = 1, PH_EXPLORE = 2, PH_DONE = 3 };
@@ -386,6 +388,117 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_kernel(const __grid_co
         __syncthreads(); // xb is overwritten by the next forward's first layer
     }
     flush_counters(g, p, t);
+}
+
+// ------------------------------------------------------------------ NN-mode kernel, tensor-core MLP (tcgen05 + TMEM)
+// Shared memory: mlptc::Smem (weight image, two activation tiles, outputs, barriers) | paths.
+// Group i of the CTA owns tile row mlptc::row_of_slot(i); the whole CTA runs one five-GEMM chain per
+// round for all of its groups' leaves.
+template <int GL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) selfplay_nn_tc_kernel(const __grid_constant__ KParams p) {
+    constexpr int GPB = THREADS / GL;
+    static_assert(GPB <= 128 && GPB % 4 == 0, "one tile row per group");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    mlptc::Smem& ms = *reinterpret_cast<mlptc::Smem*>(smem_raw);
+    uint32_t* s_path = reinterpret_cast<uint32_t*>(smem_raw + sizeof(mlptc::Smem));
+    mlptc::setup(ms, p.weight_image);
+
+    Grp<GL> g;
+    const int grp = threadIdx.x / GL;
+    const int row = mlptc::row_of_slot(grp);
+    const size_t slot = (size_t)blockIdx.x * GPB + grp;
+    Tree<GL> t;
+    t.stat = p.stat + slot * p.arena_nodes;
+    t.meta = p.meta + slot * p.arena_nodes;
+    t.path = s_path + grp * 64;
+    t.cap = p.arena_nodes;
+    t.cfg = &p.cfg.mcts;
+    t.err = 0;
+    t.nn = 1;
+#pragma unroll
+    for (int i = 0; i < CNT_N; ++i) t.cnt[i] = 0u;
+    GroupState<GL, true> st;
+    st.phase = PH_NEED_GAME;
+    st.is_init = false;
+    RolloutRng<GL> rr;
+    rr.buf = nullptr; rr.kA = rr.kB = 0; rr.pos = 0;
+    Pending pend;
+    uint32_t mma_phase = 0;
+    for (;;) {
+        bool need = advance<GL, true>(g, p, t, st, rr, nullptr, pend);
+        if (need) { // Game::features of the leaf, fp16, straight into the A tile (K-major UMMA layout)
+            constexpr int CPL = 64 / GL; // columns per lane
+            float f[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                int i = g.gl * CPL + j;
+                f[j] = i < 63 ? c4::feature(pend.my, pend.op, i) : 0.0f;
+            }
+            uint8_t* dst = ms.a0 + mlptc::a_off(row, g.gl * CPL);
+            if (CPL == 2) {
+                *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(f[0], f[1]);
+            } else {
+                __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2 % CPL], f[3 % CPL]);
+                *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            }
+        }
+        if (!__syncthreads_or(need ? 1 : 0)) break;
+        mlptc::forward<THREADS / 32>(ms, mma_phase, GPB / 4);
+        if (need) {
+            const float* y = ms.y[row];
+            float logit = g.gl < 9 ? y[g.gl] : 0.0f;
+            float y0 = y[9], y1 = y[10], y2 = y[11];
+            float m = fmaxf(y0, fmaxf(y1, y2));
+            float e0 = syn_expf(__fsub_rn(y0, m)), e1 = syn_expf(__fsub_rn(y1, m)), e2 = syn_expf(__fsub_rn(y2, m));
+            float tot = __fadd_rn(__fadd_rn(e0, e1), e2);
+            explore_finish(g, t, pend, false, logit, __fdiv_rn(e0, tot), __fdiv_rn(e1, tot), __fdiv_rn(e2, tot));
+            after_eval(g, t, st);
+        }
+        // no trailing barrier needed: the next forward() starts with a CTA barrier before any MMA, and
+        // y / a0 are only rewritten after that barrier (a0 by this thread's own group, y by the epilogue)
+    }
+    flush_counters(g, p, t);
+    mlptc::teardown(ms);
+}
+
+// Batched Policy::eval on tensor cores: 128 positions per tile, row = position.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) eval_tc_kernel(const uint8_t* __restrict__ weight_image, const uint64_t* __restrict__ my_bb,
+                                                              const uint64_t* __restrict__ op_bb, uint32_t n, float* __restrict__ logits,
+                                                              float* __restrict__ probs) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    mlptc::Smem& ms = *reinterpret_cast<mlptc::Smem*>(smem_raw);
+    mlptc::setup(ms, weight_image);
+    uint32_t mma_phase = 0;
+    for (uint32_t base = blockIdx.x * 128u; base < n; base += gridDim.x * 128u) {
+        for (int e = threadIdx.x; e < 128 * 32; e += THREADS) { // two features per thread
+            int r = e >> 5, c = (e & 31) * 2;
+            uint32_t idx = base + r;
+            float f0 = 0.0f, f1 = 0.0f;
+            if (idx < n) {
+                uint64_t my = my_bb[idx], op = op_bb[idx];
+                f0 = c4::feature(my, op, c);
+                f1 = c + 1 < 63 ? c4::feature(my, op, c + 1) : 0.0f;
+            }
+            *reinterpret_cast<__half2*>(ms.a0 + mlptc::a_off(r, c)) = __floats2half2_rn(f0, f1);
+        }
+        mlptc::forward<THREADS / 32>(ms, mma_phase, 32);
+        if (threadIdx.x < 128) {
+            uint32_t idx = base + threadIdx.x;
+            if (idx < n) {
+                const float* y = ms.y[threadIdx.x];
+                for (int k = 0; k < 9; ++k) logits[(size_t)idx * 9 + k] = y[k];
+                float m = fmaxf(y[9], fmaxf(y[10], y[11]));
+                float e0 = syn_expf(__fsub_rn(y[9], m)), e1 = syn_expf(__fsub_rn(y[10], m)), e2 = syn_expf(__fsub_rn(y[11], m));
+                float tot = __fadd_rn(__fadd_rn(e0, e1), e2);
+                probs[(size_t)idx * 3 + 0] = __fdiv_rn(e0, tot);
+                probs[(size_t)idx * 3 + 1] = __fdiv_rn(e1, tot);
+                probs[(size_t)idx * 3 + 2] = __fdiv_rn(e2, tot);
+            }
+        }
+        __syncthreads();
+    }
+    mlptc::teardown(ms);
 }
 
 // ------------------------------------------------------------------ batched Policy::eval (syn_engine_eval)

@@ -1,0 +1,100 @@
+"""Multi-GPU self-play: games shard across ranks, one process per GPU.
+
+The reference fans games out over `num_workers + 1` OS threads and joins their buffers in worker
+order (alpha_zero.rs:132-168); weights reach the workers through `models/model_{i}.ot`
+(alpha_zero.rs:192-194).  Here a rank is a worker: contiguous ranges of the global game index
+(seeds derive from the index, so the result is independent of the rank count), ONE broadcast of the
+weight blob from the trainer rank and ONE gather of experience to it per iteration — both outside
+the search, which needs no collective at all.
+"""
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .data import ReplayBuffer
+
+FIELDS = (("game_ids", np.uint64, ()), ("my_bb", np.uint64, ()), ("op_bb", np.uint64, ()), ("height", np.uint8, (9,)),
+          ("player", np.uint8, ()), ("states", np.float32, (63,)), ("pis", np.float32, (9,)), ("vs", np.float32, (3,)))
+
+
+def split_games(num_games: int, world_size: int) -> List[Tuple[int, int]]:
+    """(first, count) per rank with the reference's rule `remaining / workers_left`
+    (alpha_zero.rs:138,152-153): 1000 games over 7 workers -> 142, 143 x 6."""
+    out, first, remaining, left = [], 0, int(num_games), int(world_size)
+    for _ in range(world_size):
+        n = remaining // left
+        out.append((first, n))
+        first += n
+        remaining -= n
+        left -= 1
+    assert remaining == 0
+    return out
+
+
+def _torch_dtype(torch, dt):
+    # torch has no uint64 arithmetic but can carry the bits as int64
+    return {np.uint64: torch.int64, np.uint8: torch.uint8, np.float32: torch.float32}[dt]
+
+
+def gather_experience_distributed(play_fn: Callable[[int, int], Dict[str, np.ndarray]], num_games: int, buffer: Optional[ReplayBuffer],
+                                  games_to_keep: int, *, group=None, device=None, dst: int = 0, first_game_index: int = 0):
+    """Shard `num_games` over the process group, play each shard with `play_fn(first, count)` (which
+    returns the syn_experience arrays of that shard with GLOBAL 1-based game ids), gather all rows to
+    rank `dst` in rank order and fold them into `buffer` exactly like gather_experience
+    (keep_last_n_games then extend).  Returns the merged arrays on `dst`, None elsewhere.
+
+    Works with any torch.distributed backend: NCCL on GPUs (tensors on `device`), gloo on CPU.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    first, count = split_games(num_games, world)[rank]
+    arrays = play_fn(first_game_index + first, count) if count > 0 else {n: np.zeros((0,) + sh, dt) for n, dt, sh in FIELDS}
+    rows = len(arrays["vs"])
+    dev = device if device is not None else torch.device("cpu")
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([rows], dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts_h = counts.cpu().numpy()
+    cap = int(counts_h.max())
+    merged = {}
+    for name, dt, shape in FIELDS:
+        a = np.ascontiguousarray(arrays[name], dtype=dt).reshape((rows,) + shape)
+        if dt == np.uint64:
+            a = a.view(np.int64)
+        t = torch.zeros((cap,) + shape, dtype=_torch_dtype(torch, dt), device=dev)
+        if rows:
+            t[:rows] = torch.from_numpy(a).to(dev)
+        if rank == dst:
+            recv = [torch.zeros_like(t) for _ in range(world)]
+            dist.gather(t, recv, dst=dst, group=group)
+            parts = [recv[r][: int(counts_h[r])].cpu().numpy() for r in range(world)]
+            m = np.concatenate(parts) if parts else a
+            merged[name] = m.view(np.uint64) if dt == np.uint64 else m
+        else:
+            dist.gather(t, None, dst=dst, group=group)
+    if rank != dst:
+        return None
+    if buffer is not None:
+        worker_arrays = dict(merged)
+        worker_arrays["game_ids"] = merged["game_ids"] - np.uint64(first_game_index)
+        worker = ReplayBuffer.from_arrays(num_games, worker_arrays)
+        buffer.keep_last_n_games(games_to_keep - num_games)
+        buffer.extend(worker)
+    return merged
+
+
+def broadcast_weights(blob_or_none, *, group=None, device=None, src: int = 0):
+    """One broadcast of the 30,492-float weight blob from the trainer rank (replaces every worker's
+    `vs.load(model_{i}.ot)`).  Returns a torch tensor on `device`."""
+    import torch
+    import torch.distributed as dist
+
+    from ._lib import N_WEIGHTS
+    dev = device if device is not None else torch.device("cpu")
+    t = torch.zeros(N_WEIGHTS, dtype=torch.float32, device=dev)
+    if dist.get_rank(group) == src:
+        t.copy_(torch.from_numpy(np.ascontiguousarray(blob_or_none, dtype=np.float32).reshape(-1)))
+    dist.broadcast(t, src=src, group=group)
+    return t

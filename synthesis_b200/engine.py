@@ -50,6 +50,10 @@ class Engine:
         b = np.ascontiguousarray(blob, dtype=np.float32).reshape(-1)
         L.check(self._lib.syn_engine_set_weights(self._h, _ptr(b), b.size))
 
+    def set_mlp_mode(self, tensor_cores: bool):
+        """True (default): Connect4Net on the tcgen05 tensor cores; False: the fp32 CUDA-core kernel."""
+        L.check(self._lib.syn_engine_set_mlp_mode(self._h, int(bool(tensor_cores))))
+
     def set_group_lanes(self, lanes: int):
         L.check(self._lib.syn_engine_set_group_lanes(self._h, int(lanes)))
 

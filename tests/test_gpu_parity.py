@@ -205,13 +205,17 @@ def test_gather_stop_games_when_solved(engine, oracle):
     assert_rows_equal(a, ra, "experience")
 
 
-def test_group_lanes_do_not_change_results(engine):
+@pytest.mark.parametrize("leaf", ["rollout", "nn"])
+def test_group_lanes_do_not_change_results(engine, leaf):
     cfg = s.study_connect4_rollout_cfg(num_explores=100)
+    kind = L.LEAF_ROLLOUT if leaf == "rollout" else L.LEAF_NN
+    if leaf == "nn":
+        engine.set_weights(s.Connect4Net.new(3).blob())
     engine.set_group_lanes(32)
-    a32, _, t32 = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 40, 1, trace=True)
+    a32, _, t32 = engine.gather(cfg, kind, 0, 40, 1, trace=True)
     engine.set_group_lanes(16)
     try:
-        a16, _, t16 = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 40, 1, trace=True)
+        a16, _, t16 = engine.gather(cfg, kind, 0, 40, 1, trace=True)
     finally:
         engine.set_group_lanes(32)
     assert_rows_equal(a16, a32, "GL16 vs GL32 experience")
@@ -229,7 +233,14 @@ def test_sharding_is_invisible(engine):
 
 
 # ---------------------------------------------------------------- A9: the network
-def test_nn_eval_within_tolerance(engine, oracle):
+@pytest.fixture(params=["tensor_cores", "fp32_cuda_cores"])
+def mlp_mode(request, engine):
+    engine.set_mlp_mode(request.param == "tensor_cores")
+    yield request.param
+    engine.set_mlp_mode(True)
+
+
+def test_nn_eval_within_tolerance(engine, oracle, mlp_mode):
     net = s.Connect4Net.new(0)
     engine.set_weights(net.blob())
     rng = np.random.default_rng(3)
@@ -242,6 +253,27 @@ def test_nn_eval_within_tolerance(engine, oracle):
     np.testing.assert_allclose(lg, rl, rtol=1e-3, atol=1e-3)
     np.testing.assert_allclose(pr, rp, rtol=1e-3, atol=1e-3)
     assert np.allclose(pr.sum(1), 1.0, atol=1e-5)
+    print(f"{mlp_mode}: max |logit err| = {np.abs(lg - rl).max():.3e}, max |prob err| = {np.abs(pr - rp).max():.3e}")
+
+
+def test_nn_eval_large_weights_and_batch_independence(engine, oracle):
+    """Trained-scale weights (10x the init range) and: a position's output must not depend on which
+    tile row / batch it is evaluated in (that is what lets the oracle replay the GPU's leaf outputs)."""
+    rng = np.random.default_rng(21)
+    blob = (s.Connect4Net.new(5).blob() * rng.uniform(0.5, 4.0, size=L.N_WEIGHTS)).astype(np.float32)
+    engine.set_weights(blob)
+    games = random_positions(rng, 300, max_plies=60)
+    my = np.array([g.my_bb for g in games], np.uint64)
+    op = np.array([g.op_bb for g in games], np.uint64)
+    lg, pr = engine.eval(my, op)
+    rl, rp = oracle.mlp_eval(blob, my, op)
+    np.testing.assert_allclose(lg, rl, rtol=2e-3, atol=2e-3 * max(1.0, float(np.abs(rl).max())))
+    perm = rng.permutation(len(games))
+    lg2, pr2 = engine.eval(my[perm], op[perm])
+    assert np.array_equal(lg2.view(np.uint32), lg[perm].view(np.uint32))
+    assert np.array_equal(pr2.view(np.uint32), pr[perm].view(np.uint32))
+    one_l, one_p = engine.eval(my[:1], op[:1])
+    assert np.array_equal(one_l.view(np.uint32), lg[:1].view(np.uint32))
 
 
 def _gpu_leaf_callback(engine):
@@ -254,7 +286,7 @@ def _gpu_leaf_callback(engine):
     return cb
 
 
-def test_search_nn_tree_bit_exact_given_gpu_leaf_outputs(engine, oracle):
+def test_search_nn_tree_bit_exact_given_gpu_leaf_outputs(engine, oracle, mlp_mode):
     """Tree logic is bit-exact when the oracle is fed the GPU's (logits, value) per leaf."""
     net = s.Connect4Net.new(1)
     engine.set_weights(net.blob())
@@ -273,7 +305,7 @@ def test_search_nn_tree_bit_exact_given_gpu_leaf_outputs(engine, oracle):
         assert int(out["num_nodes"][i]) == ref["num_nodes"], i
 
 
-def test_gather_nn_bit_exact_given_gpu_leaf_outputs(engine, oracle):
+def test_gather_nn_bit_exact_given_gpu_leaf_outputs(engine, oracle, mlp_mode):
     net = s.Connect4Net.new(2)
     engine.set_weights(net.blob())
     cfg = s.study_connect4_rollout_cfg(num_explores=60, sample_actions_until=12)
@@ -283,7 +315,7 @@ def test_gather_nn_bit_exact_given_gpu_leaf_outputs(engine, oracle):
     assert_rows_equal(a, ra, "experience")
 
 
-def test_gather_nn_close_to_fp32_oracle(engine, oracle):
+def test_gather_nn_close_to_fp32_oracle(engine, oracle, mlp_mode):
     """Against the oracle's OWN fp32 forward the trees may differ after a near-tie, but Q values of
     the first ply (identical position, 800 explores) must agree to 1e-3-ish and games must be legal."""
     net = s.Connect4Net.new(0)
