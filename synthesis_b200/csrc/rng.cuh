@@ -3,7 +3,7 @@
 // rand 0.8 `StdRng` = ChaCha12 (rand_chacha 0.3), seeded by rand_core 0.6 `seed_from_u64`
 // (PCG32 expansion), consumed as consecutive little-endian u32 words of consecutive blocks.
 // Call sites replaced: policies/rollout.rs:16 (one u32 per rollout ply), alpha_zero.rs:281,
-// 286-287 (action sampling).  See oracle/rng.hpp for the CPU restatement these must equal.
+// 286-287 (action sampling).  The CPU checker restates the same streams (tests compare them word for word).
 #pragma once
 #include <stdint.h>
 

@@ -351,3 +351,24 @@ def test_error_behaviour(engine):
         assert e.value.code == L.SYN_ERR_NO_WEIGHTS
     finally:
         fresh.close()
+
+
+# ---------------------------------------------------------------- committed golden fixtures (tests/golden/)
+def test_engine_matches_committed_search_fixtures(engine):
+    import golden_fixtures as G
+
+    def run(cfg, kind, g, seed, tree_kind):
+        out, _ = engine.search(cfg, kind, [g.my_bb], [g.op_bb], [seed], tree_kind=tree_kind)
+        return {k: v[0] for k, v in out.items()}
+
+    assert G.check_search_fixture(run, kinds=(L.TREE_MCTS,)) >= 90
+
+
+def test_engine_matches_committed_gather_fixtures(engine):
+    import golden_fixtures as G
+
+    def run(cfg, kind, first, n, seed):
+        a, _, t = engine.gather(cfg, kind, first, n, seed, trace=True)
+        return a, t
+
+    G.check_gather_fixture(run)

@@ -1,0 +1,203 @@
+"""CPU suite, part 2: host-side mirror of the reference interface, and the C-ABI library.
+
+No compute call is made here (there is no GPU in the authoring container): the library must load,
+export every symbol include/synthesis_b200.h declares, and FAIL LOUDLY without a B200 — there is
+no CPU fallback behind any entry point.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import synthesis_b200 as s
+from synthesis_b200 import _lib as L
+from synthesis_b200 import distributed as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+# ------------------------------------------------------------------ the C ABI
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "synthesis_b200.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(syn_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
+    lib = L.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.syn_abi_version() == int(re.search(r"#define SYN_ABI_VERSION (\d+)", header).group(1))
+    assert b"sm_100a" in lib.syn_build_info()
+
+
+def test_struct_layouts_match_the_header():
+    # sizes as laid out by the C compiler for include/synthesis_b200.h (checked by a static_assert-like test)
+    assert C.sizeof(L.SynMctsCfg) == 36
+    assert C.sizeof(L.SynRolloutCfg) == 72
+    assert C.sizeof(L.SynExperience) == 3 * C.sizeof(C.c_size_t) + 8 * C.sizeof(C.c_void_p)
+    assert C.sizeof(L.SynStats) == 8 * len(L.SynStats._fields_)
+    src = r'''
+#include "synthesis_b200.h"
+#include <stdio.h>
+int main(void) { printf("%zu %zu %zu %zu\n", sizeof(syn_mcts_cfg), sizeof(syn_rollout_cfg), sizeof(syn_experience), sizeof(syn_stats)); return 0; }
+'''
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "sz.c")
+        with open(p, "w") as f:
+            f.write(src)
+        exe = os.path.join(d, "sz")
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), p, "-o", exe])  # the header is plain C
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(L.SynMctsCfg), C.sizeof(L.SynRolloutCfg), C.sizeof(L.SynExperience), C.sizeof(L.SynStats)]
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_engine_creation_fails_loudly():
+    with pytest.raises(L.EngineError) as e:
+        s.Engine(0, 64, 100)
+    assert e.value.code == L.SYN_ERR_NO_DEVICE
+    assert "no CPU path" in str(e.value) or "sm_100a" in str(e.value)
+    lib = L.load()
+    h = C.c_void_p()
+    assert lib.syn_engine_create(0, 0, 0, C.byref(h)) != 0 and not h.value
+    assert lib.syn_engine_create(0, 64, 100, None) == L.SYN_ERR_INVALID_ARGUMENT
+    # NULL engines are rejected, not dereferenced
+    assert lib.syn_engine_set_weights(None, None, 0) == L.SYN_ERR_INVALID_ARGUMENT
+    assert lib.syn_engine_gather_wait(None, None, None) == L.SYN_ERR_INVALID_ARGUMENT
+    lib.syn_engine_destroy(None)
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "synthesis_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    txt = f.read()
+                for needle in ("liboracle", "oracle_binding", "import oracle", "from oracle", '"oracle"', "oracle/", "orc_"):
+                    assert needle not in txt, f"{fn} mentions {needle!r}: the product must not reach into oracle/"
+
+
+# ------------------------------------------------------------------ config.rs mirror
+def test_config_maps_to_the_c_structs():
+    cfg = s.study_connect4_rollout_cfg(num_explores=800, sample_actions_until=30)
+    c = cfg.to_c(L.LEAF_NN)
+    assert (c.num_explores, c.random_actions_until, c.sample_actions_until, c.stop_games_when_solved) == (800, 1, 30, 0)
+    assert c.value_target_kind == L.VALUE_Q and c.action_selection == L.ACTION_NUM_VISITS and c.leaf_eval_kind == L.LEAF_NN
+    m = c.mcts
+    assert (m.exploration_kind, m.c) == (L.EXPLORATION_POLYNOMIAL_UCT, 3.0)
+    assert (m.solve, m.correct_values_on_solve, m.select_solved_nodes, m.auto_extend) == (1, 1, 1, 1)
+    assert (m.fpu_kind, m.fpu_a, m.noise_kind) == (L.FPU_CONST, 1.0, L.NOISE_NONE)
+    r = s.study_connect4_rollout_mcts_cfg().to_c()
+    assert (r.exploration_kind, r.c, r.auto_extend, r.fpu_kind) == (L.EXPLORATION_UCT, 2.0, 0, L.FPU_CONST) and np.isinf(r.fpu_a)
+    cfg.value_target = s.ValueTarget.QtoZ(0.25, 0.75)
+    cfg.mcts_cfg.root_policy_noise = s.PolicyNoise.Dirichlet(1.0, 0.25)
+    cfg.mcts_cfg.fpu = s.Fpu.Normal(1.0, 0.1)
+    c = cfg.to_c(L.LEAF_ROLLOUT)
+    assert (c.value_target_kind, c.vt_a, c.vt_b) == (L.VALUE_Q_TO_Z, 0.25, 0.75)
+    assert (c.mcts.noise_kind, c.mcts.noise_alpha, c.mcts.noise_weight) == (L.NOISE_DIRICHLET, 1.0, 0.25)
+    assert (c.mcts.fpu_kind, c.mcts.fpu_a) == (L.FPU_NORMAL, 1.0) and abs(c.mcts.fpu_b - 0.1) < 1e-7
+    cfg.mcts_cfg.fpu = s.Fpu.Func(lambda: 1.0)  # carried to the engine, which rejects it (SYN_ERR_UNSUPPORTED)
+    assert cfg.to_c(L.LEAF_NN).mcts.fpu_kind == L.FPU_FUNC
+    cfg.mcts_cfg.fpu = "nonsense"
+    with pytest.raises(TypeError):
+        cfg.to_c(L.LEAF_NN)
+
+
+def test_connect4net_blob_round_trip():
+    net = s.Connect4Net.new(0)
+    blob = net.blob()
+    assert blob.shape == (L.N_WEIGHTS,) and blob.dtype == np.float32
+    assert L.N_WEIGHTS == 63 * 128 + 128 + 128 * 96 + 96 + 96 * 64 + 64 + 64 * 48 + 48 + 48 * 12 + 12
+    again = s.Connect4Net.from_blob(blob)
+    for k, v in net.params.items():
+        assert np.array_equal(v, again.params[k])
+    assert np.abs(net.params["l_1.weight"]).max() <= 1 / np.sqrt(63) and np.abs(net.params["l_5.bias"]).max() <= 1 / np.sqrt(48)
+    with pytest.raises(ValueError):
+        s.Connect4Net.from_blob(blob[:-1])
+
+
+def test_host_connect4_mirror_against_the_oracle(oracle):
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        g, ms = s.Connect4.new(), []
+        for _ in range(int(rng.integers(0, 64))):
+            acts = list(g.iter_actions())
+            a = acts[int(rng.integers(0, len(acts)))]
+            ms.append(a)
+            if g.step(a):
+                break
+        r = oracle.c4_play(ms)
+        assert (g.my_bb, g.op_bb, list(g.height)) == (r["my_bb"], r["op_bb"], list(r["height"]))
+        assert g.is_over() == bool(r["status"] & 1)
+        assert g.reward(g.player()) == r["reward_to_move"]
+        assert sum(1 << c for c in g.iter_actions()) == r["legal_mask"]
+        assert np.array_equal(g.features().reshape(63).view(np.uint32), r["features"].view(np.uint32))
+        assert s.Connect4.from_bitboards(g.my_bb, g.op_bb) == g
+    with pytest.raises(ValueError):
+        g = s.Connect4.new()
+        for _ in range(8):
+            g.step(0)
+
+
+# ------------------------------------------------------------------ data.rs mirror
+def _rows(ids):
+    n = len(ids)
+    return dict(game_ids=np.asarray(ids, np.uint64), my_bb=np.arange(n, dtype=np.uint64), op_bb=np.zeros(n, np.uint64),
+                height=np.zeros((n, 9), np.uint8), player=np.zeros(n, np.uint8), states=np.zeros((n, 63), np.float32),
+                pis=np.zeros((n, 9), np.float32), vs=np.zeros((n, 3), np.float32))
+
+
+def test_replay_buffer_extend_and_keep_last_n_games(oracle):
+    buf = s.ReplayBuffer()
+    w1 = s.ReplayBuffer.from_arrays(3, _rows([1, 1, 2, 3, 3, 3]))
+    buf.keep_last_n_games(10 - 3)
+    buf.extend(w1)
+    assert buf.total_games_played() == 3 and buf.curr_steps() == 6 and buf.total_steps() == 6 and buf.curr_games() == 3
+    assert len(w1.vs) == 0  # drained like Vec::drain(..) (data.rs:165-169)
+    w2 = s.ReplayBuffer.from_arrays(2, _rows([1, 2, 2]))
+    buf.extend(w2)  # ids are re-based by the running game counter (data.rs:162-163)
+    assert list(buf.game_ids) == [1, 1, 2, 3, 3, 3, 4, 5, 5] and buf.game_id == 5
+    # keep_last_n_games(n): drop every row whose id < game_id - n (data.rs:172-194), checked against the oracle's restatement
+    for n in (0, 1, 2, 3, 4, 5, 9):
+        b = s.ReplayBuffer.from_arrays(5, _rows([1, 1, 2, 3, 3, 3, 4, 5, 5]))
+        ids = b.game_ids.copy()
+        want = oracle.lib.orc_keep_last_n_games_prefix(ids.ctypes.data, len(ids), 5, n)
+        b.keep_last_n_games(n)
+        assert len(ids) - len(b.game_ids) == want, n
+        assert b.total_games_played() == 5
+    g = s.Connect4.new()
+    g.step(4)
+    buf.new_game()
+    buf.add(g, np.full(9, 1 / 9, np.float32), np.zeros(3, np.float32))
+    assert buf.game_ids[-1] == 6 and buf.curr_steps() == 10 and buf.games[-1] == g
+
+
+def test_split_games_follows_the_reference_schedule():
+    # alpha_zero.rs:132-154: num_games = remaining / workers_left; 1000 games over 7 workers -> 142, 143 x 6
+    parts = D.split_games(1000, 7)
+    assert [n for _, n in parts] == [142] + [143] * 6
+    assert parts[0][0] == 0 and all(parts[i + 1][0] == parts[i][0] + parts[i][1] for i in range(6))
+    assert D.split_games(3, 8) == [(0, 0)] * 5 + [(0, 1), (1, 1), (2, 1)]
+    assert sum(n for _, n in D.split_games(32768, 8)) == 32768 and {n for _, n in D.split_games(32768, 8)} == {4096}
+
+
+def test_stream_seeds(oracle):
+    """include/syn_streams.h: seed 0 gives rollout stream 2g and action stream 2g+1 (SURVEY §8c convention)."""
+    for g in (0, 1, 5, 4095):
+        assert oracle.lib.orc_stream_seed(0, g, 0) == 2 * g and oracle.lib.orc_stream_seed(0, g, 1) == 2 * g + 1
+    seen = {oracle.lib.orc_stream_seed(sd, g, k) for sd in range(3) for g in range(50) for k in range(4)}
+    assert len(seen) == 3 * 50 * 4
