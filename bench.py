@@ -39,7 +39,8 @@ def parse_args():
     p.add_argument("--games", type=int, default=4096, help="self-play games per GPU per step")
     p.add_argument("--explores", type=int, default=800)
     p.add_argument("--leaf", default="nn", choices=["nn", "rollout"])
-    p.add_argument("--group-lanes", type=int, default=int(os.environ.get("SYN_GROUP_LANES", "16")))
+    p.add_argument("--group-lanes", type=int, default=int(os.environ.get("SYN_GROUP_LANES", "1")),
+                   help="lanes per game: 1 = thread per game (default), 16 / 32 = lane group per game")
     p.add_argument("--cpu-games", type=int, default=0, help="games in the CPU sample (default 8 per host thread)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
@@ -219,7 +220,12 @@ def run_ours(args):
 
     leaf = L.LEAF_NN if args.leaf == "nn" else L.LEAF_ROLLOUT
     cfg = workload_cfg(args)
-    in_flight = 148 * (512 // args.group_lanes) if args.leaf == "nn" else 148 * 8 * (256 // args.group_lanes)
+    if args.leaf == "nn" and args.group_lanes == 1:
+        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "4"))  # one CTA per SM, teams of 128 games
+    elif args.leaf == "nn":
+        in_flight = 148 * (512 // args.group_lanes)
+    else:
+        in_flight = 148 * 8 * (256 // (16 if args.group_lanes == 1 else args.group_lanes))
     eng = s.Engine(local_rank, in_flight, args.explores)
     eng.set_group_lanes(args.group_lanes)
     games = args.games

@@ -208,8 +208,10 @@ int syn_engine_play(syn_engine* e, const uint8_t* moves, const uint32_t* n_moves
  * it is what the parity tests compare ("bit-exact visit counts"). */
 int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, float* child_visits /*[cap][9]*/);
 
-/* Lanes per game: 32 (a warp per game) or 16 (two games per warp).  Default 32, or the value of
- * the SYN_GROUP_LANES environment variable at syn_engine_create.  Results do not depend on it. */
+/* Lanes per game: 1 (default; a thread per game, 128 games = one tensor-core tile of leaves), 32 (a
+ * warp per game) or 16 (two games per warp).  The SYN_GROUP_LANES environment variable overrides the
+ * default at syn_engine_create.  Rollout leaves use lane groups (1 means 16 there).  Results do not
+ * depend on it. */
 int syn_engine_set_group_lanes(syn_engine* e, int lanes);
 
 /* Which kernel evaluates Connect4Net: 1 (default) = fp16-operand / fp32-accumulate GEMM chain on the

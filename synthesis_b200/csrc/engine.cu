@@ -60,9 +60,9 @@ struct syn_engine {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
-    int group_lanes = 32;
-    DevBuf<float4> stat;
-    DevBuf<uint4> meta;
+    int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
+    int tpg_teams = 4;     // teams of 128 threads per CTA in thread-per-game mode
+    DevBuf<uint4> nodes; // 2 x uint4 = one 32-byte record per tree node
     DevBuf<float> weights;
     DevBuf<uint8_t> weight_image; // mlptc layout (fp16 weights + fp32 biases)
     bool has_weights = false;
@@ -122,6 +122,14 @@ static int validate_cfg(const syn_rollout_cfg* cfg, const syn_engine* e) {
     return SYN_OK;
 }
 
+template <int TEAMS>
+static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
+    size_t smem = sizeof(mlpteam::Smem<TEAMS>);
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg_kernel<TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_nn_tpg_kernel<TEAMS><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+    return SYN_OK;
+}
+
 static size_t nn_tc_smem_bytes(int gpb) { return sizeof(mlptc::Smem) + (size_t)gpb * 64 * sizeof(uint32_t); }
 static size_t nn_smem_bytes(int gpb) { return (size_t)(mlp::WEIGHT_FLOATS + 2 * gpb * mlp::XS + gpb * 64) * sizeof(float); }
 
@@ -130,8 +138,24 @@ constexpr int NN_THREADS = 512;
 
 // Launches the self-play kernel for `n` games/positions.  Rows/search buffers must be set in kp.
 static int launch_selfplay(syn_engine* e, KParams& kp) {
-    const int gl = e->group_lanes;
     const bool nn = kp.cfg.leaf_eval_kind == SYN_LEAF_NN;
+    if (nn && e->group_lanes == 1 && e->use_tc) { // thread per game: one persistent CTA per SM
+        const uint32_t gpb = 128u * (uint32_t)e->tpg_teams;
+        uint32_t max_blocks = e->max_games / gpb;
+        if (max_blocks == 0) return fail(SYN_ERR_CAPACITY, "max_games_in_flight %u is smaller than one CTA's %u games", e->max_games, gpb);
+        // spread the games over the SMs first (whole teams), then fill the CTAs
+        uint32_t want_teams = (kp.num_games + 127u) / 128u;
+        uint32_t blocks = want_teams < (uint32_t)e->sm_count ? want_teams : (uint32_t)e->sm_count;
+        if (blocks > max_blocks) blocks = max_blocks;
+        if (blocks == 0) blocks = 1;
+        CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
+        int rc = e->tpg_teams == 4 ? launch_tpg<4>(e, kp, blocks) : (e->tpg_teams == 2 ? launch_tpg<2>(e, kp, blocks) : launch_tpg<1>(e, kp, blocks));
+        if (rc) return rc;
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        return SYN_OK;
+    }
+    const int gl = e->group_lanes == 1 ? 16 : e->group_lanes; // rollout leaves: lane groups
     const int threads = nn ? NN_THREADS : ROLLOUT_THREADS;
     const int gpb = threads / gl;
     uint32_t max_blocks = e->max_games / gpb;
@@ -175,8 +199,7 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     std::memset(&kp, 0, sizeof(kp));
     kp.cfg = *cfg;
     kp.arena_nodes = e->arena_nodes;
-    kp.stat = e->stat.p;
-    kp.meta = e->meta.p;
+    kp.nodes = e->nodes.p;
     kp.next_game = e->next_game.p;
     kp.counters = e->counters.p;
     kp.error = e->error.p;
@@ -245,9 +268,11 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     const char* mlpenv = std::getenv("SYN_MLP");
     e->use_tc = !(mlpenv && std::strcmp(mlpenv, "fp32") == 0);
     const char* glenv = std::getenv("SYN_GROUP_LANES");
-    e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : 32;
-    // round the in-flight game count up to whole CTAs of either kernel
-    uint32_t unit = NN_THREADS / 16;
+    e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : ((glenv && std::atoi(glenv) == 32) ? 32 : 1);
+    const char* tenv = std::getenv("SYN_TPG_TEAMS");
+    if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4)) e->tpg_teams = std::atoi(tenv);
+    // round the in-flight game count up to whole CTAs of every kernel
+    uint32_t unit = 512;
     e->max_games = ((max_games_in_flight + unit - 1) / unit) * unit;
     e->max_explores = max_explores;
     // nodes.len() <= 1 + 9 * (explores + 1): every visit pushes at most 9 nodes (mcts.rs:384-397)
@@ -257,7 +282,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     size_t total = (size_t)e->max_games * e->arena_nodes;
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
-        (ce = e->stat.reserve(total)) != cudaSuccess || (ce = e->meta.reserve(total)) != cudaSuccess ||
+        (ce = e->nodes.reserve(2 * total)) != cudaSuccess ||
         (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->weight_image.reserve(mlptc::IMG_BYTES)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
         (ce = e->counters.reserve(CNT_N)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
         int rc = fail(SYN_ERR_CUDA, "engine allocation failed (%zu arena nodes = %.1f MiB): %s", total,
@@ -273,7 +298,7 @@ void syn_engine_destroy(syn_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->stat.release(); e->meta.release(); e->weights.release(); e->weight_image.release(); e->next_game.release(); e->counters.release(); e->error.release();
+    e->nodes.release(); e->weights.release(); e->weight_image.release(); e->next_game.release(); e->counters.release(); e->error.release();
     e->row_my.release(); e->row_op.release(); e->row_off.release(); e->row_pi.release(); e->row_v.release(); e->row_visits.release();
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();
@@ -285,7 +310,7 @@ void syn_engine_destroy(syn_engine* e) {
 }
 
 int syn_engine_set_group_lanes(syn_engine* e, int lanes) {
-    if (!e || (lanes != 16 && lanes != 32)) return fail(SYN_ERR_INVALID_ARGUMENT, "group lanes must be 16 or 32");
+    if (!e || (lanes != 1 && lanes != 16 && lanes != 32)) return fail(SYN_ERR_INVALID_ARGUMENT, "group lanes must be 1, 16 or 32");
     e->group_lanes = lanes;
     return SYN_OK;
 }

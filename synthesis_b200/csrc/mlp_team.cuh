@@ -1,0 +1,172 @@
+// mlp_team.cuh — Connect4Net forward for a TEAM of 128 threads = 128 leaves = one UMMA M-tile.
+//
+// Replaces study-connect4/src/policies.rs:28-59 (five nn::Linear + ReLU through libtorch, batch 1
+// per leaf).  Same GEMM chain, operand layout and numerics as mlp_tc.cuh (fp16 operands, fp32
+// accumulate in TMEM, bias + ReLU in registers), re-cut for the thread-per-game kernels:
+//
+//   * thread r of the team owns tile row r end to end: it writes its leaf's 64 fp16 features into
+//     the A tile, and after every layer reads ITS row of the accumulator back from TMEM lane r
+//     (tcgen05.ld 32x32b: warp w of the team covers lanes 32w..32w+31), applies bias + ReLU, and
+//     writes the row of the next layer's A tile.  The final 12 outputs arrive in the registers of
+//     the thread whose tree needs them — no staging of results through shared memory.
+//   * one A tile per team: a layer's MMAs have completed (mbarrier) before any thread writes the
+//     next activations, so layer l+1's A overwrites layer l's in place.
+//   * several teams per CTA share ONE resident fp16 weight image (bulk-async copy, once per
+//     kernel) and run their chains independently: team barriers are named barriers over 128
+//     threads, completion is one mbarrier per team, accumulators are disjoint TMEM column ranges.
+#pragma once
+#include "mlp_tc.cuh"
+
+namespace mlpteam {
+
+using namespace mlptc;
+
+constexpr int A_BYTES = (128 / 8) * M_TILE * 16; // K up to 128 -> 32768 B per team
+constexpr int TEAM = 128;
+
+template <int TEAMS>
+struct __align__(128) Smem {
+    uint8_t img[IMG_BYTES];      // fp16 weights of the five layers + fp32 biases (bulk-copied image)
+    uint8_t a[TEAMS][A_BYTES];   // one activation tile per team
+    uint64_t bar_w;              // weights landed
+    uint64_t bar_mma[TEAMS];     // a team's layer completed
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void team_sync(int team) { // named barrier 1 + team over the team's 128 threads
+    asm volatile("barrier.sync %0, %1;" ::"r"(team + 1), "n"(TEAM) : "memory");
+}
+__device__ __forceinline__ bool team_any(int team, bool p) {
+    uint32_t out;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\tbarrier.red.or.pred q, %1, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(out) : "r"(team + 1), "r"((uint32_t)p), "n"(TEAM) : "memory");
+    return out != 0u;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+
+// Prologue: all threads of the CTA call.
+template <int TEAMS>
+__device__ __forceinline__ void setup(Smem<TEAMS>& s, const uint8_t* __restrict__ weight_image) {
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&s.bar_w, 1);
+#pragma unroll
+        for (int t = 0; t < TEAMS; ++t) mbar_init(&s.bar_mma[t], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&s.tmem_base, 128 * TEAMS);
+    for (int i = threadIdx.x; i < TEAMS * A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(&s.a[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s.bar_w, IMG_BYTES);
+        bulk_g2s(s.img, weight_image, IMG_BYTES, &s.bar_w);
+    }
+    mbar_wait(&s.bar_w, 0);
+    fence_proxy_async();
+    __syncthreads();
+}
+
+template <int TEAMS>
+__device__ __forceinline__ void teardown(Smem<TEAMS>& s) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(s.tmem_base, 128 * TEAMS);
+}
+
+// Game::features (connect4.rs:237-258) of one position as 64 fp16 values (the 64th is padding),
+// written as row `r` of the team's A tile in the K-major UMMA layout.  +1 mine, -1 theirs, +0.1 the
+// next playable cell of a column with room, -0.1 any other empty cell; k = row * 9 + col.
+__device__ __forceinline__ void write_features(uint8_t* a_tile, int r, uint64_t my, uint64_t op) {
+    const uint64_t occ = my | op;
+    const uint64_t play = ((occ << 1) | c4::ROW0) & ~occ & c4::ALL; // empty with support below
+    constexpr uint32_t H_ONE = 0x3C00u, H_MONE = 0xBC00u, H_P01 = 0x2E66u, H_M01 = 0xAE66u; // fp16 bits of +-1, RN(+-0.1)
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t h[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = ch * 8 + j * 2 + e;
+                if (k < 63) {
+                    const int bit = (k / 9) + 7 * (k % 9);
+                    const bool m = (my >> bit) & 1ull, o = (op >> bit) & 1ull, pl = (play >> bit) & 1ull;
+                    h[e] = m ? H_ONE : (o ? H_MONE : (pl ? H_P01 : H_M01));
+                } else {
+                    h[e] = 0u;
+                }
+            }
+            w[j] = h[0] | (h[1] << 16);
+        }
+        *reinterpret_cast<uint4*>(a_tile + ch * (M_TILE * 16) + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// Forward pass of the team's 128 rows.  Every thread of the team calls with its row's features
+// already in the A tile (generic-proxy stores); `phase` is the running parity of the team's
+// mbarrier (start at 0, kept by the caller).  On return y[0..8] are the row's policy logits and
+// y[9..11] its value logits.
+template <int TEAMS>
+__device__ __forceinline__ void forward(Smem<TEAMS>& s, int team, int r, uint32_t& phase, float (&y)[12]) {
+    uint8_t* a_tile = s.a[team];
+    const uint32_t tmem = s.tmem_base + (uint32_t)(team * 128);           // the team's 128 accumulator columns
+    const uint32_t tlane = tmem + ((uint32_t)((r >> 5) * 32) << 16);       // this warp's 32 TMEM lanes
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int K = layer_k(l), N = layer_n(l);
+        fence_proxy_async();  // this thread's A-tile stores -> visible to the tensor core's async proxy
+        tc_fence_before();
+        team_sync(team);
+        if (r == 0) {
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(a_tile), b_base = smem_u32(s.img + w_off(l));
+#pragma unroll
+            for (int kk = 0; kk < K / 16; ++kk) {
+                uint64_t ad = make_desc(a_base + kk * 2 * (M_TILE * 16), M_TILE * 16, 128);
+                uint64_t bd = make_desc(b_base + kk * 2 * (N * 16), N * 16, 128);
+                umma_f16(tmem, ad, bd, make_idesc(N), kk > 0 ? 1u : 0u);
+            }
+            umma_commit(&s.bar_mma[team]);
+        }
+        mbar_wait(&s.bar_mma[team], phase);
+        phase ^= 1u;
+        tc_fence_after();
+        const float* bias = reinterpret_cast<const float*>(s.img + BIAS_OFF) + b_off(l);
+#pragma unroll
+        for (int c16 = 0; c16 < N / 16; ++c16) {
+            uint32_t v[16];
+            tmem_ld16(tlane + (uint32_t)(c16 * 16), v);
+            tmem_ld_wait();
+            if (l < NL - 1) {
+                uint32_t h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float2 b2 = *reinterpret_cast<const float2*>(bias + c16 * 16 + 2 * j);
+                    float x0 = fminf(fmaxf(__uint_as_float(v[2 * j]) + b2.x, 0.0f), 65504.0f);     // bias, ReLU, fp16 range
+                    float x1 = fminf(fmaxf(__uint_as_float(v[2 * j + 1]) + b2.y, 0.0f), 65504.0f);
+                    __half2 hh = __floats2half2_rn(x0, x1);
+                    h[j] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                *reinterpret_cast<uint4*>(a_tile + (2 * c16) * (M_TILE * 16) + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(a_tile + (2 * c16 + 1) * (M_TILE * 16) + r * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) y[j] = __uint_as_float(v[j]) + bias[j];
+            }
+        }
+    }
+    // the next forward()'s first team_sync orders these TMEM reads before the next MMA overwrites D
+    tc_fence_before();
+}
+
+} // namespace mlpteam

@@ -28,8 +28,7 @@ struct KParams {
     uint32_t num_games;
     uint32_t search_mode; // 1: one tree per given position, no game loop (syn_engine_search)
     uint32_t arena_nodes;
-    float4* stat;
-    uint4* meta;
+    uint4* nodes; // tree arenas: arena_nodes 32-byte records per game slot (tree.cuh)
     unsigned int* next_game;
     // experience rows, [num_games][63]
     uint64_t* row_my;
@@ -311,8 +310,7 @@ __global__ void __launch_bounds__(THREADS) selfplay_rollout_kernel(const __grid_
     const int grp = threadIdx.x / GL;
     const size_t slot = (size_t)blockIdx.x * GPB + grp;
     Tree<GL> t;
-    t.stat = p.stat + slot * p.arena_nodes;
-    t.meta = p.meta + slot * p.arena_nodes;
+    t.stat.base = t.meta.base = p.nodes + 2 * slot * p.arena_nodes;
     t.path = s_path[grp];
     t.cap = p.arena_nodes;
     t.cfg = &p.cfg.mcts;
@@ -352,8 +350,7 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_kernel(const __grid_co
     const int grp = threadIdx.x / GL;
     const size_t slot = (size_t)blockIdx.x * GPB + grp;
     Tree<GL> t;
-    t.stat = p.stat + slot * p.arena_nodes;
-    t.meta = p.meta + slot * p.arena_nodes;
+    t.stat.base = t.meta.base = p.nodes + 2 * slot * p.arena_nodes;
     t.path = s_path + grp * 64;
     t.cap = p.arena_nodes;
     t.cfg = &p.cfg.mcts;
@@ -408,8 +405,7 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_tc_kernel(const __grid
     const int row = mlptc::row_of_slot(grp);
     const size_t slot = (size_t)blockIdx.x * GPB + grp;
     Tree<GL> t;
-    t.stat = p.stat + slot * p.arena_nodes;
-    t.meta = p.meta + slot * p.arena_nodes;
+    t.stat.base = t.meta.base = p.nodes + 2 * slot * p.arena_nodes;
     t.path = s_path + grp * 64;
     t.cap = p.arena_nodes;
     t.cfg = &p.cfg.mcts;
@@ -537,6 +533,53 @@ __global__ void __launch_bounds__(THREADS, 1) eval_kernel(const float* __restric
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------ NN-mode kernel, thread per game (tpg.cuh + mlp_team.cuh)
+// One persistent CTA per SM, TEAMS teams of 128 threads.  Every thread plays whole games; each round
+// it advances its tree to the next leaf, the team's <= 128 leaves go through ONE Connect4Net forward
+// on the tensor cores (thread r = tile row r), and the thread finishes its explore with the logits
+// it reads back from TMEM.  Teams are independent of each other (named barriers, one mbarrier and
+// 128 TMEM columns each) and share the resident weight image.
+} // namespace eng
+#include "mlp_team.cuh"
+#include "tpg.cuh"
+namespace eng {
+
+template <int TEAMS>
+__global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    mlpteam::Smem<TEAMS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS>*>(smem_raw);
+    mlpteam::setup<TEAMS>(ms, p.weight_image);
+    const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
+    tpg::Ctx c;
+    c.cfg = &p.cfg.mcts; c.cap = p.arena_nodes; c.seed = p.seed; c.search_mode = p.search_mode != 0;
+    tpg::Game g;
+    tpg::init_game(p, g, (size_t)blockIdx.x * (128 * TEAMS) + threadIdx.x);
+    tpg::Leaf lf;
+    uint64_t my = 0, op = 0;
+    uint32_t mma_phase = 0;
+    for (;;) {
+        bool need = tpg::advance(p, c, g, lf, my, op);
+        if (need) mlpteam::write_features(ms.a[team], r, my, op);
+        __syncwarp();
+        if (!mlpteam::team_any(team, need)) break; // no thread of this team has a game left
+        float y[12];
+        mlpteam::forward<TEAMS>(ms, team, r, mma_phase, y);
+        if (need) {
+            // value.softmax(-1) (study-connect4/src/policies.rs:54-56)
+            float m = fmaxf(y[9], fmaxf(y[10], y[11]));
+            float e0 = syn_expf(__fsub_rn(y[9], m)), e1 = syn_expf(__fsub_rn(y[10], m)), e2 = syn_expf(__fsub_rn(y[11], m));
+            float tot = __fadd_rn(__fadd_rn(e0, e1), e2);
+            float lg[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) lg[k] = y[k];
+            tpg::finish(c, g, lf, false, lg, __fdiv_rn(e0, tot), __fdiv_rn(e1, tot), __fdiv_rn(e2, tot));
+            tpg::after_eval(c, g);
+        }
+    }
+    tpg::flush_counters(p, g);
+    mlpteam::teardown<TEAMS>(ms);
 }
 
 // ------------------------------------------------------------------ game rules on move lists (syn_engine_play)

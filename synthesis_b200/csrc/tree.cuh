@@ -11,11 +11,12 @@
 // stays one here: there is never more than one explore of a tree in flight, which is what keeps
 // visit counts bit-identical; parallelism comes from the thousands of independent games.
 //
-// Node arena (HBM, one slab per group slot, reset every move like the reference's fresh Vec):
-//   stat[i] = float4 { num_visits, outcome_probs[0] (Lose), [1] (Draw), [2] (Win) }
-//   meta[i] = uint4  { action_prob bits, first_child, parent, num_children | solution<<8 | action<<16 }
-// Children of a node are contiguous (mcts.rs:163-166), so one level of selection is two coalesced
-// 16-byte loads per lane over <= 9 consecutive records.
+// Node arena (HBM, one slab per game slot, reset every move like the reference's fresh Vec): one
+// 32-byte record per node = exactly one DRAM/L2 sector,
+//   bytes  0..15  stat = float4 { num_visits, outcome_probs[0] (Lose), [1] (Draw), [2] (Win) }
+//   bytes 16..31  meta = uint4  { action_prob bits, first_child, parent, num_children | solution<<8 | action<<16 }
+// Children of a node are contiguous (mcts.rs:163-166), so one level of selection reads <= 9
+// consecutive records = <= 288 contiguous bytes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -171,11 +172,21 @@ __device__ __forceinline__ int rollout(const Grp<GL>& g, uint64_t my, uint64_t o
     }
 }
 
+// Views of the two halves of the 32-byte node records (see the header comment).
+struct StatView {
+    uint4* base;
+    __device__ __forceinline__ float4& operator[](size_t i) const { return *reinterpret_cast<float4*>(base + 2 * i); }
+};
+struct MetaView {
+    uint4* base;
+    __device__ __forceinline__ uint4& operator[](size_t i) const { return base[2 * i + 1]; }
+};
+
 // ------------------------------------------------------------------ per-group tree context
 template <int GL>
 struct Tree {
-    float4* stat;   // this slot's arena
-    uint4* meta;
+    StatView stat;  // this slot's arena
+    MetaView meta;
     uint32_t* path; // shared, 64 entries: node ids root..current
     uint32_t nn;    // nodes.len()
     uint32_t cap;   // arena capacity in nodes

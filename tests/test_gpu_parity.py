@@ -207,19 +207,24 @@ def test_gather_stop_games_when_solved(engine, oracle):
 
 @pytest.mark.parametrize("leaf", ["rollout", "nn"])
 def test_group_lanes_do_not_change_results(engine, leaf):
+    """Thread-per-game (1), half-warp-per-game (16) and warp-per-game (32) are three schedules of the
+    same serial per-tree algorithm: experience and visit counts must be identical bit for bit."""
     cfg = s.study_connect4_rollout_cfg(num_explores=100)
     kind = L.LEAF_ROLLOUT if leaf == "rollout" else L.LEAF_NN
     if leaf == "nn":
         engine.set_weights(s.Connect4Net.new(3).blob())
-    engine.set_group_lanes(32)
-    a32, _, t32 = engine.gather(cfg, kind, 0, 40, 1, trace=True)
-    engine.set_group_lanes(16)
+    res = {}
     try:
-        a16, _, t16 = engine.gather(cfg, kind, 0, 40, 1, trace=True)
+        for gl in (32, 16, 1):
+            engine.set_group_lanes(gl)
+            res[gl] = engine.gather(cfg, kind, 0, 200, 1, trace=True)
     finally:
-        engine.set_group_lanes(32)
-    assert_rows_equal(a16, a32, "GL16 vs GL32 experience")
-    assert_rows_equal(t16, t32, "GL16 vs GL32 trace")
+        engine.set_group_lanes(1)
+    for gl in (16, 1):
+        assert_rows_equal(res[gl][0], res[32][0], f"GL{gl} vs GL32 experience")
+        assert_rows_equal(res[gl][2], res[32][2], f"GL{gl} vs GL32 trace")
+        for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels"):
+            assert res[gl][1][k] == res[32][1][k], (gl, k)
 
 
 def test_sharding_is_invisible(engine):
