@@ -219,6 +219,11 @@ int syn_engine_set_group_lanes(syn_engine* e, int lanes);
  * The SYN_MLP=fp32 environment variable selects 0 at syn_engine_create. */
 int syn_engine_set_mlp_mode(syn_engine* e, int tensor_cores);
 
+/* Profiling aid, not part of the reference's surface: per-warp clock totals of the last thread-per-game
+ * launch, out[0..7) = cycles in {tree advance, waiting for the team, Connect4Net forward, explore
+ * finish}, rounds, leaves evaluated, total cycles (each summed over warps). */
+int syn_engine_debug_counters(syn_engine* e, uint64_t* out, uint32_t n);
+
 /* Packed Option<Outcome> (synthesis/src/game.rs:9-14): 0 = None, else kind<<6 | turns with
  * kind 1 = Lose, 2 = Draw, 3 = Win; turns <= 63. */
 #define SYN_OUTCOME_NONE 0u

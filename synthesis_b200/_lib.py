@@ -74,7 +74,7 @@ class SynStats(C.Structure):
 EXPORTED_SYMBOLS = (
     "syn_abi_version", "syn_build_info", "syn_last_error", "syn_engine_create", "syn_engine_destroy",
     "syn_engine_set_weights", "syn_engine_gather", "syn_engine_gather_launch", "syn_engine_gather_wait",
-    "syn_engine_search", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode",
+    "syn_engine_search", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode", "syn_engine_debug_counters",
 )
 
 _lib = None
@@ -113,6 +113,7 @@ def load():
     lib.syn_engine_set_trace.argtypes = [vp, vp, vp, vp]
     lib.syn_engine_set_group_lanes.argtypes = [vp, i32]
     lib.syn_engine_set_mlp_mode.argtypes = [vp, i32]
+    lib.syn_engine_debug_counters.argtypes = [vp, vp, u32]
     _lib = lib
     return lib
 

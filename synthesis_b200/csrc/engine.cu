@@ -284,7 +284,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
         (ce = e->nodes.reserve(2 * total)) != cudaSuccess ||
         (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->weight_image.reserve(mlptc::IMG_BYTES)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
-        (ce = e->counters.reserve(CNT_N)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
+        (ce = e->counters.reserve(CNT_ALL)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
         int rc = fail(SYN_ERR_CUDA, "engine allocation failed (%zu arena nodes = %.1f MiB): %s", total,
                       (double)total * 32.0 / 1048576.0, cudaGetErrorString(ce));
         syn_engine_destroy(e);
@@ -312,6 +312,16 @@ void syn_engine_destroy(syn_engine* e) {
 int syn_engine_set_group_lanes(syn_engine* e, int lanes) {
     if (!e || (lanes != 1 && lanes != 16 && lanes != 32)) return fail(SYN_ERR_INVALID_ARGUMENT, "group lanes must be 1, 16 or 32");
     e->group_lanes = lanes;
+    return SYN_OK;
+}
+
+int syn_engine_debug_counters(syn_engine* e, uint64_t* out, uint32_t n) {
+    if (!e || !out) return fail(SYN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is in flight");
+    unsigned long long c[CNT_ALL];
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaMemcpy(c, e->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; ++i) out[i] = i < (uint32_t)(CNT_ALL - CNT_N) ? c[CNT_N + i] : 0;
     return SYN_OK;
 }
 
@@ -352,7 +362,7 @@ int syn_engine_gather_launch(syn_engine* e, const syn_rollout_cfg* cfg, uint64_t
     kp.row_my = e->row_my.p; kp.row_op = e->row_op.p; kp.row_pi = e->row_pi.p; kp.row_v = e->row_v.p;
     kp.row_action = e->row_action.p; kp.row_nodes = e->row_nodes.p; kp.row_visits = e->row_visits.p; kp.game_len = e->game_len.p;
     e->launches = 0;
-    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_N * sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_ALL * sizeof(unsigned long long), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->error.p, 0, sizeof(int), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->game_len.p, 0, num_games * sizeof(uint32_t), e->stream));
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
@@ -483,7 +493,7 @@ int syn_engine_search(syn_engine* e, const syn_rollout_cfg* cfg, uint32_t tree_k
     kp.pos_my = e->pos_my.p; kp.pos_op = e->pos_op.p; kp.pos_seed = e->pos_seed.p;
     kp.s_child_visits = e->s_visits.p; kp.s_child_sol = e->s_csol.p; kp.s_root_q = e->s_q.p; kp.s_root_sol = e->s_rsol.p;
     kp.s_best = e->s_best.p; kp.s_nodes = e->s_nodes.p;
-    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_N * sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_ALL * sizeof(unsigned long long), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->error.p, 0, sizeof(int), e->stream));
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
     rc = launch_selfplay(e, kp);

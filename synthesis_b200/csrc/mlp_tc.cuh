@@ -4,8 +4,12 @@
 // Replaces study-connect4/src/policies.rs:28-59 (five nn::Linear + ReLU through libtorch, batch 1
 // per leaf) with a chain of five UMMA GEMMs per batch:
 //     D[128 x N] (fp32, TMEM) = A[128 x K] (fp16, smem, K-major) * W[N x K]^T (fp16, smem, K-major)
-// with (K, N) = (64,128) (128,96) (96,64) (64,48) (48,16).  PyTorch keeps nn.Linear weights as
-// [out][in] row-major, which IS the K-major B operand, so no transpose is needed.
+// with (K, N) = (80,128) (128,96) (96,64) (64,48) (48,16).  PyTorch keeps nn.Linear weights as
+// [out][in] row-major, which IS the K-major B operand, so no transpose is needed.  Layer 0's K axis is
+// permuted: feature (row, col) of Game::features (index row*9+col) sits at k = col*8 + row, i.e. one
+// 16-byte chunk of 8 fp16 per board column (7 cells + a zero), chunks 0..8, chunk 9 all zero; the
+// weight image carries the same permutation, so the product is unchanged and a column's features
+// can be written with one 16-byte store (mlp_team.cuh looks them up in a 255-entry table).
 //
 //  * weights: converted once (syn_engine_set_weights) to an fp16 image in exactly the shared-memory
 //    layout the UMMA descriptors expect, then brought into shared memory with ONE bulk-async copy
@@ -31,17 +35,19 @@ namespace mlptc {
 
 constexpr int M_TILE = 128;
 constexpr int NL = 5;
-__host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 64 : (l == 1 ? 128 : (l == 2 ? 96 : (l == 3 ? 64 : 48))); }
+__host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 80 : (l == 1 ? 128 : (l == 2 ? 96 : (l == 3 ? 64 : 48))); }
 __host__ __device__ constexpr int layer_n(int l) { return l == 0 ? 128 : (l == 1 ? 96 : (l == 2 ? 64 : (l == 3 ? 48 : 16))); }
 __host__ __device__ constexpr int layer_in(int l) { return l == 0 ? 63 : layer_k(l); }   // real fan-in
+// K index of feature i = row*9+col in layer 0's permuted K axis
+__host__ __device__ constexpr int kperm(int i) { return (i % 9) * 8 + (i / 9); }
 __host__ __device__ constexpr int layer_out(int l) { return l == 4 ? 12 : layer_n(l); }  // real fan-out
 __host__ __device__ constexpr int w_bytes(int l) { return layer_k(l) * layer_n(l) * 2; }
 __host__ __device__ constexpr int w_off(int l) { return l == 0 ? 0 : w_off(l - 1) + w_bytes(l - 1); }
-constexpr int W_TOTAL = w_off(4) + w_bytes(4);          // 60928 B of fp16 weights
+constexpr int W_TOTAL = w_off(4) + w_bytes(4);          // 65024 B of fp16 weights
 constexpr int BIAS_OFF = W_TOTAL;                        // fp32 biases, padded to N
 __host__ __device__ constexpr int b_off(int l) { return l == 0 ? 0 : b_off(l - 1) + layer_n(l - 1); }
 constexpr int BIAS_FLOATS = b_off(4) + layer_n(4);       // 352
-constexpr int IMG_BYTES = W_TOTAL + BIAS_FLOATS * 4;     // 62336 B, multiple of 16
+constexpr int IMG_BYTES = W_TOTAL + BIAS_FLOATS * 4;     // 66432 B, multiple of 16
 static_assert(IMG_BYTES % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
 // activation tiles: even layers read A0, odd layers read A1
 constexpr int A0_BYTES = (96 / 8) * M_TILE * 16;         // K up to 96  -> 24576 B
@@ -62,7 +68,9 @@ __global__ void build_weight_image(const float* __restrict__ blob, uint8_t* __re
         __half* dst = reinterpret_cast<__half*>(img + w_off(l));
         for (int e = tid; e < K * N; e += nt) {
             int n = e / K, k = e - n * K;
-            float v = (n < O && k < I) ? W[n * I + k] : 0.0f;
+            int src = k; // layer 0: k = col*8 + row  <-  blob column row*9 + col
+            if (l == 0) src = ((k & 7) < 7 && (k >> 3) < 9) ? (k & 7) * 9 + (k >> 3) : I;
+            float v = (n < O && src < I) ? W[n * I + src] : 0.0f;
             dst[(k / 8) * (N * 8) + n * 8 + (k % 8)] = __float2half_rn(v);
         }
         float* bd = reinterpret_cast<float*>(img + BIAS_OFF) + b_off(l);
@@ -176,7 +184,7 @@ __device__ __forceinline__ void teardown(Smem& s) {
     if ((threadIdx.x >> 5) == 1) tmem_dealloc(s.tmem_base, TMEM_COLS);
 }
 
-// Forward pass over the rows currently in s.a0 (fp16 features, K = 64).  All NW warps call; every
+// Forward pass over the rows currently in s.a0 (fp16 features, K = 80, permuted: kperm()).  All NW warps call; every
 // thread must have finished writing its part of a0 (generic-proxy stores) before the call — the
 // function issues the proxy fence and the CTA barrier itself.  `phase` is the running parity of
 // bar_mma and must be kept by the caller across calls (start at 0).  nrows_per_quarter = number

@@ -28,6 +28,7 @@ template <int TEAMS>
 struct __align__(128) Smem {
     uint8_t img[IMG_BYTES];      // fp16 weights of the five layers + fp32 biases (bulk-copied image)
     uint8_t a[TEAMS][A_BYTES];   // one activation tile per team
+    uint4 col_lut[256];          // fp16 features of one board column by (stones, owners): see write_features
     uint64_t bar_w;              // weights landed
     uint64_t bar_mma[TEAMS];     // a team's layer completed
     uint32_t tmem_base;
@@ -51,6 +52,45 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "r"(taddr) : "memory");
 }
 
+// {lo, hi} -> fp16x2 with ReLU and saturation to +-65504 (F2FP.SATFINITE.RELU.F16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t cvt_relu_sat_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// Game::features (connect4.rs:237-258) of one position, fp16, written as row `r` of the team's A tile
+// in the K-major UMMA layout with layer 0's permuted K axis (mlp_tc.cuh): chunk c = board column c =
+// 7 cells bottom-up + a zero.  +1 mine, -1 theirs, +0.1 the next playable cell, -0.1 any other empty
+// cell.  A column with h stones whose owners are the low h bits of my_col is entry
+// (2^h - 1) + my_col = occ_col + my_col of a 255-entry table, so a column costs one 16-byte
+// table read and one 16-byte store.
+__device__ __forceinline__ uint4 col_lut_entry(int idx) {
+    int h = 31 - __clz(idx + 1);
+    uint32_t mine = (uint32_t)(idx + 1) - (1u << h);
+    uint32_t hv[8];
+#pragma unroll
+    for (int row = 0; row < 8; ++row) {
+        uint32_t v;
+        if (row == 7) v = 0u;
+        else if (row < h) v = ((mine >> row) & 1u) ? 0x3C00u : 0xBC00u; // fp16 +1 / -1
+        else if (row == h) v = 0x2E66u;                                  // fp16 RN(+0.1)
+        else v = 0xAE66u;                                                // fp16 RN(-0.1)
+        hv[row] = v;
+    }
+    return make_uint4(hv[0] | (hv[1] << 16), hv[2] | (hv[3] << 16), hv[4] | (hv[5] << 16), hv[6] | (hv[7] << 16));
+}
+
+__device__ __forceinline__ void write_features(uint8_t* a_tile, const uint4* lut, int r, uint64_t my, uint64_t op) {
+    const uint64_t occ = my | op;
+#pragma unroll
+    for (int col = 0; col < 9; ++col) {
+        uint32_t oc = (uint32_t)(occ >> (7 * col)) & 0x7fu, mc = (uint32_t)(my >> (7 * col)) & 0x7fu;
+        *reinterpret_cast<uint4*>(a_tile + col * (M_TILE * 16) + r * 16) = lut[oc + mc];
+    }
+    *reinterpret_cast<uint4*>(a_tile + 9 * (M_TILE * 16) + r * 16) = make_uint4(0u, 0u, 0u, 0u); // K 72..79
+}
+
 // Prologue: all threads of the CTA call.
 template <int TEAMS>
 __device__ __forceinline__ void setup(Smem<TEAMS>& s, const uint8_t* __restrict__ weight_image) {
@@ -63,6 +103,7 @@ __device__ __forceinline__ void setup(Smem<TEAMS>& s, const uint8_t* __restrict_
     }
     if (warp == 0) tmem_alloc(&s.tmem_base, 128 * TEAMS);
     for (int i = threadIdx.x; i < TEAMS * A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(&s.a[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s.col_lut[i] = col_lut_entry(i < 255 ? i : 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -80,36 +121,6 @@ __device__ __forceinline__ void teardown(Smem<TEAMS>& s) {
     tc_fence_before();
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) tmem_dealloc(s.tmem_base, 128 * TEAMS);
-}
-
-// Game::features (connect4.rs:237-258) of one position as 64 fp16 values (the 64th is padding),
-// written as row `r` of the team's A tile in the K-major UMMA layout.  +1 mine, -1 theirs, +0.1 the
-// next playable cell of a column with room, -0.1 any other empty cell; k = row * 9 + col.
-__device__ __forceinline__ void write_features(uint8_t* a_tile, int r, uint64_t my, uint64_t op) {
-    const uint64_t occ = my | op;
-    const uint64_t play = ((occ << 1) | c4::ROW0) & ~occ & c4::ALL; // empty with support below
-    constexpr uint32_t H_ONE = 0x3C00u, H_MONE = 0xBC00u, H_P01 = 0x2E66u, H_M01 = 0xAE66u; // fp16 bits of +-1, RN(+-0.1)
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t h[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int k = ch * 8 + j * 2 + e;
-                if (k < 63) {
-                    const int bit = (k / 9) + 7 * (k % 9);
-                    const bool m = (my >> bit) & 1ull, o = (op >> bit) & 1ull, pl = (play >> bit) & 1ull;
-                    h[e] = m ? H_ONE : (o ? H_MONE : (pl ? H_P01 : H_M01));
-                } else {
-                    h[e] = 0u;
-                }
-            }
-            w[j] = h[0] | (h[1] << 16);
-        }
-        *reinterpret_cast<uint4*>(a_tile + ch * (M_TILE * 16) + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
 }
 
 // Forward pass of the team's 128 rows.  Every thread of the team calls with its row's features
@@ -150,12 +161,11 @@ __device__ __forceinline__ void forward(Smem<TEAMS>& s, int team, int r, uint32_
             if (l < NL - 1) {
                 uint32_t h[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float2 b2 = *reinterpret_cast<const float2*>(bias + c16 * 16 + 2 * j);
-                    float x0 = fminf(fmaxf(__uint_as_float(v[2 * j]) + b2.x, 0.0f), 65504.0f);     // bias, ReLU, fp16 range
-                    float x1 = fminf(fmaxf(__uint_as_float(v[2 * j + 1]) + b2.y, 0.0f), 65504.0f);
-                    __half2 hh = __floats2half2_rn(x0, x1);
-                    h[j] = *reinterpret_cast<uint32_t*>(&hh);
+                for (int j = 0; j < 4; ++j) {
+                    float4 b4 = *reinterpret_cast<const float4*>(bias + c16 * 16 + 4 * j);
+                    // bias, then ReLU + saturate to the fp16 range + round + pack in ONE instruction
+                    h[2 * j] = cvt_relu_sat_f16x2(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y);
+                    h[2 * j + 1] = cvt_relu_sat_f16x2(__uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
                 }
                 *reinterpret_cast<uint4*>(a_tile + (2 * c16) * (M_TILE * 16) + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(a_tile + (2 * c16 + 1) * (M_TILE * 16) + r * 16) = make_uint4(h[4], h[5], h[6], h[7]);

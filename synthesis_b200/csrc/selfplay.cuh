@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_tc_kernel(const __grid
     Grp<GL> g;
     const int grp = threadIdx.x / GL;
     const int row = mlptc::row_of_slot(grp);
+    const int row_of_grp = row;
     const size_t slot = (size_t)blockIdx.x * GPB + grp;
     Tree<GL> t;
     t.stat.base = t.meta.base = p.nodes + 2 * slot * p.arena_nodes;
@@ -422,20 +423,11 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_tc_kernel(const __grid
     uint32_t mma_phase = 0;
     for (;;) {
         bool need = advance<GL, true>(g, p, t, st, rr, nullptr, pend);
-        if (need) { // Game::features of the leaf, fp16, straight into the A tile (K-major UMMA layout)
-            constexpr int CPL = 64 / GL; // columns per lane
-            float f[CPL];
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                int i = g.gl * CPL + j;
-                f[j] = i < 63 ? c4::feature(pend.my, pend.op, i) : 0.0f;
-            }
-            uint8_t* dst = ms.a0 + mlptc::a_off(row, g.gl * CPL);
-            if (CPL == 2) {
-                *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(f[0], f[1]);
-            } else {
-                __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2 % CPL], f[3 % CPL]);
-                *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        if (need) { // Game::features of the leaf, fp16, straight into the A tile (K-major UMMA layout, permuted K)
+            for (int k = g.gl; k < 80; k += GL) {
+                int col = k >> 3, row = k & 7;
+                float f = (row < 7 && col < 9) ? c4::feature(pend.my, pend.op, row * 9 + col) : 0.0f;
+                *reinterpret_cast<__half*>(ms.a0 + mlptc::a_off(row_of_grp, k)) = __float2half_rn(f);
             }
         }
         if (!__syncthreads_or(need ? 1 : 0)) break;
@@ -467,16 +459,13 @@ __global__ void __launch_bounds__(THREADS, 1) eval_tc_kernel(const uint8_t* __re
     mlptc::setup(ms, weight_image);
     uint32_t mma_phase = 0;
     for (uint32_t base = blockIdx.x * 128u; base < n; base += gridDim.x * 128u) {
-        for (int e = threadIdx.x; e < 128 * 32; e += THREADS) { // two features per thread
-            int r = e >> 5, c = (e & 31) * 2;
+        for (int e = threadIdx.x; e < 128 * 80; e += THREADS) {
+            int r = e / 80, k = e - r * 80;
+            int col = k >> 3, row = k & 7;
             uint32_t idx = base + r;
-            float f0 = 0.0f, f1 = 0.0f;
-            if (idx < n) {
-                uint64_t my = my_bb[idx], op = op_bb[idx];
-                f0 = c4::feature(my, op, c);
-                f1 = c + 1 < 63 ? c4::feature(my, op, c + 1) : 0.0f;
-            }
-            *reinterpret_cast<__half2*>(ms.a0 + mlptc::a_off(r, c)) = __floats2half2_rn(f0, f1);
+            float f = 0.0f;
+            if (idx < n && row < 7 && col < 9) f = c4::feature(my_bb[idx], op_bb[idx], row * 9 + col);
+            *reinterpret_cast<__half*>(ms.a0 + mlptc::a_off(r, k)) = __float2half_rn(f);
         }
         mlptc::forward<THREADS / 32>(ms, mma_phase, 32);
         if (threadIdx.x < 128) {
@@ -559,13 +548,20 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg_kernel(const _
     tpg::Leaf lf;
     uint64_t my = 0, op = 0;
     uint32_t mma_phase = 0;
+    long long t_adv = 0, t_wait = 0, t_mlp = 0, t_fin = 0, t_start = clock64();
+    uint32_t rounds = 0, leaves = 0;
     for (;;) {
+        long long t0 = clock64();
         bool need = tpg::advance(p, c, g, lf, my, op);
-        if (need) mlpteam::write_features(ms.a[team], r, my, op);
+        if (need) mlpteam::write_features(ms.a[team], ms.col_lut, r, my, op);
         __syncwarp();
+        long long t1 = clock64();
+        leaves += (uint32_t)__popc(__ballot_sync(0xffffffffu, need));
         if (!mlpteam::team_any(team, need)) break; // no thread of this team has a game left
+        long long t2 = clock64();
         float y[12];
         mlpteam::forward<TEAMS>(ms, team, r, mma_phase, y);
+        long long t3 = clock64();
         if (need) {
             // value.softmax(-1) (study-connect4/src/policies.rs:54-56)
             float m = fmaxf(y[9], fmaxf(y[10], y[11]));
@@ -577,6 +573,18 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg_kernel(const _
             tpg::finish(c, g, lf, false, lg, __fdiv_rn(e0, tot), __fdiv_rn(e1, tot), __fdiv_rn(e2, tot));
             tpg::after_eval(c, g);
         }
+        __syncwarp();
+        long long t4 = clock64();
+        t_adv += t1 - t0; t_wait += t2 - t1; t_mlp += t3 - t2; t_fin += t4 - t3; ++rounds;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(p.counters + DBG_T_ADVANCE, (unsigned long long)t_adv);
+        atomicAdd(p.counters + DBG_T_TEAMWAIT, (unsigned long long)t_wait);
+        atomicAdd(p.counters + DBG_T_MLP, (unsigned long long)t_mlp);
+        atomicAdd(p.counters + DBG_T_FINISH, (unsigned long long)t_fin);
+        atomicAdd(p.counters + DBG_ROUNDS, (unsigned long long)rounds);
+        atomicAdd(p.counters + DBG_LEAVES, (unsigned long long)leaves);
+        atomicAdd(p.counters + DBG_T_TOTAL, (unsigned long long)(clock64() - t_start));
     }
     tpg::flush_counters(p, g);
     mlpteam::teardown<TEAMS>(ms);

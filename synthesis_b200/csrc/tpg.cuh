@@ -22,11 +22,13 @@ struct Rec { // one node record in registers
     uint32_t prior, fc, parent, pk; // pk = num_children | solution << 8 | action << 16
 };
 
-__device__ __forceinline__ Rec load_rec(const uint4* nodes, uint32_t i) {
-    uint4 a = nodes[2 * (size_t)i], b = nodes[2 * (size_t)i + 1];
+__device__ __forceinline__ Rec load_rec(const uint4* nodes, uint32_t i) { // one 256-bit load (LDG.E.256) = one sector
     Rec r;
-    r.vis = __uint_as_float(a.x); r.o0 = __uint_as_float(a.y); r.o1 = __uint_as_float(a.z); r.o2 = __uint_as_float(a.w);
-    r.prior = b.x; r.fc = b.y; r.parent = b.z; r.pk = b.w;
+    unsigned long long q0, q1, q2, q3;
+    asm volatile("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(nodes + 2 * (size_t)i) : "memory");
+    r.vis = __uint_as_float((uint32_t)q0); r.o0 = __uint_as_float((uint32_t)(q0 >> 32));
+    r.o1 = __uint_as_float((uint32_t)q1); r.o2 = __uint_as_float((uint32_t)(q1 >> 32));
+    r.prior = (uint32_t)q2; r.fc = (uint32_t)(q2 >> 32); r.parent = (uint32_t)q3; r.pk = (uint32_t)(q3 >> 32);
     return r;
 }
 __device__ __forceinline__ void store_stat(uint4* nodes, uint32_t i, float vis, float o0, float o1, float o2) {
@@ -151,22 +153,33 @@ __device__ __forceinline__ bool descend(const Ctx& c, Game& g, uint64_t& my, uin
         const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
         uint32_t b = 0u, bfc = 0u, bpk = 0u;
         float bval = 0.0f, bvis = 0.0f, bo0 = 0.0f, bo2 = 0.0f;
-        for (uint32_t k = 0; k < nch; ++k) {
-            Rec ch = load_rec(nodes, cfc + k);
-            uint32_t csol = (ch.pk >> 8) & 0xffu, cn = ch.pk & 0xffu;
-            float q;
-            if (csol) {
-                uint32_t kd = sol_kind(csol);
-                q = cfg.select_solved_nodes ? (kd == SYN_KIND_WIN ? -1.0f : (kd == SYN_KIND_LOSE ? 1.0f : 0.0f)) : __uint_as_float(0xff800000u);
-            } else if (cn == 0u) {
-                q = cfg.fpu_kind == SYN_FPU_CONST ? cfg.fpu_a : (cfg.fpu_kind == SYN_FPU_PARENT_Q ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : fpu_normal_draw(c, g));
-            } else {
-                q = -__fdiv_rn(__fsub_rn(ch.o2, ch.o0), ch.vis);
+        // three children per trip: their records are requested together, so a level costs
+        // ceil(nch / 3) memory round trips instead of nch
+        for (uint32_t k0 = 0; k0 < nch; k0 += 3u) {
+            Rec chs[3];
+#pragma unroll
+            for (uint32_t j = 0; j < 3u; ++j) chs[j] = load_rec(nodes, cfc + (k0 + j < nch ? k0 + j : nch - 1u));
+#pragma unroll
+            for (uint32_t j = 0; j < 3u; ++j) {
+                const uint32_t k = k0 + j;
+                if (k < nch) {
+                    const Rec& ch = chs[j];
+                    uint32_t csol = (ch.pk >> 8) & 0xffu, cn = ch.pk & 0xffu;
+                    float q;
+                    if (csol) {
+                        uint32_t kd = sol_kind(csol);
+                        q = cfg.select_solved_nodes ? (kd == SYN_KIND_WIN ? -1.0f : (kd == SYN_KIND_LOSE ? 1.0f : 0.0f)) : __uint_as_float(0xff800000u);
+                    } else if (cn == 0u) {
+                        q = cfg.fpu_kind == SYN_FPU_CONST ? cfg.fpu_a : (cfg.fpu_kind == SYN_FPU_PARENT_Q ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : fpu_normal_draw(c, g));
+                    } else {
+                        q = -__fdiv_rn(__fsub_rn(ch.o2, ch.o0), ch.vis);
+                    }
+                    float u = puct ? __fdiv_rn(__fmul_rn(__fmul_rn(cfg.c, __uint_as_float(ch.prior)), pterm), __fadd_rn(1.0f, ch.vis))
+                                   : __fdiv_rn(pterm, __fsqrt_rn(ch.vis));
+                    float value = __fadd_rn(q, u);
+                    if (k == 0u || value > bval) { b = k; bval = value; bvis = ch.vis; bo0 = ch.o0; bo2 = ch.o2; bfc = ch.fc; bpk = ch.pk; }
+                }
             }
-            float u = puct ? __fdiv_rn(__fmul_rn(__fmul_rn(cfg.c, __uint_as_float(ch.prior)), pterm), __fadd_rn(1.0f, ch.vis))
-                           : __fdiv_rn(pterm, __fsqrt_rn(ch.vis));
-            float value = __fadd_rn(q, u);
-            if (k == 0u || value > bval) { b = k; bval = value; bvis = ch.vis; bo0 = ch.o0; bo2 = ch.o2; bfc = ch.fc; bpk = ch.pk; }
         }
         g.cnt[CNT_SELECT_LEVELS] += 1u;
         g.cnt[CNT_CHILDREN_SCANNED] += nch;

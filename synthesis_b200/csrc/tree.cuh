@@ -32,7 +32,9 @@ namespace eng {
 
 enum Counter {
     CNT_EXPLORES = 0, CNT_LEAF_EVALS, CNT_ROWS, CNT_GAMES, CNT_TREES, CNT_NODES, CNT_SELECT_LEVELS,
-    CNT_CHILDREN_SCANNED, CNT_EXPANSIONS, CNT_CHILDREN_CREATED, CNT_BACKPROP_LEVELS, CNT_ROLLOUT_PLIES, CNT_N
+    CNT_CHILDREN_SCANNED, CNT_EXPANSIONS, CNT_CHILDREN_CREATED, CNT_BACKPROP_LEVELS, CNT_ROLLOUT_PLIES, CNT_N,
+    // per-warp phase clocks of the thread-per-game kernels (lane 0 of every warp; syn_engine_debug_counters)
+    DBG_T_ADVANCE = CNT_N, DBG_T_TEAMWAIT, DBG_T_MLP, DBG_T_FINISH, DBG_ROUNDS, DBG_LEAVES, DBG_T_TOTAL, CNT_ALL
 };
 
 enum DeviceError { DERR_NONE = 0, DERR_ARENA_OVERFLOW = 1, DERR_DEPTH_OVERFLOW = 2, DERR_BAD_WEIGHTS = 3 };

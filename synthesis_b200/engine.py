@@ -54,6 +54,13 @@ class Engine:
         """True (default): Connect4Net on the tcgen05 tensor cores; False: the fp32 CUDA-core kernel."""
         L.check(self._lib.syn_engine_set_mlp_mode(self._h, int(bool(tensor_cores))))
 
+    def debug_counters(self):
+        """Per-warp phase clocks of the last thread-per-game launch (profiling aid)."""
+        out = np.zeros(7, np.uint64)
+        L.check(self._lib.syn_engine_debug_counters(self._h, _ptr(out), 7))
+        names = ("t_advance", "t_teamwait", "t_mlp", "t_finish", "rounds", "leaves", "t_total")
+        return {k: int(v) for k, v in zip(names, out)}
+
     def set_group_lanes(self, lanes: int):
         L.check(self._lib.syn_engine_set_group_lanes(self._h, int(lanes)))
 
