@@ -221,7 +221,7 @@ def run_ours(args):
     leaf = L.LEAF_NN if args.leaf == "nn" else L.LEAF_ROLLOUT
     cfg = workload_cfg(args)
     if args.leaf == "nn" and args.group_lanes == 1:
-        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "4"))  # one CTA per SM, teams of 128 games
+        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "8"))  # one CTA per SM, teams of 128 games
     elif args.leaf == "nn":
         in_flight = 148 * (512 // args.group_lanes)
     else:

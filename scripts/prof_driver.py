@@ -8,7 +8,7 @@ explores = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 gl = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 modes = sys.argv[4].split(",") if len(sys.argv) > 4 else ["rollout", "nn"]
 cfg = s.study_connect4_rollout_cfg(num_explores=explores)
-eng = s.Engine(0, max(148 * 32, min(games, 148 * 512)), explores)
+eng = s.Engine(0, max(148 * 32, min(games, 148 * 1024)), explores)
 eng.set_group_lanes(gl)
 eng.set_weights(s.Connect4Net.new(0).blob())
 for m in modes:
@@ -21,4 +21,4 @@ for m in modes:
         tot = max(1, d["t_total"])
         print("   phase share of warp time: advance %.1f%% teamwait %.1f%% mlp %.1f%% finish %.1f%% | rounds/warp %.0f leaves/round/warp %.1f | cycles/round %.0f"
               % (100 * d["t_advance"] / tot, 100 * d["t_teamwait"] / tot, 100 * d["t_mlp"] / tot, 100 * d["t_finish"] / tot,
-                 d["rounds"] / (148 * 16), d["leaves"] / max(1, d["rounds"]), (d["t_advance"] + d["t_teamwait"] + d["t_mlp"] + d["t_finish"]) / max(1, d["rounds"])))
+                 d["rounds"] / (148 * 4 * int(os.environ.get("SYN_TPG_TEAMS", "8"))), d["leaves"] / max(1, d["rounds"]), (d["t_advance"] + d["t_teamwait"] + d["t_mlp"] + d["t_finish"]) / max(1, d["rounds"])))

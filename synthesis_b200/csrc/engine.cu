@@ -61,7 +61,7 @@ struct syn_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
     int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
-    int tpg_teams = 4;     // teams of 128 threads per CTA in thread-per-game mode
+    int tpg_teams = 8;     // teams of 128 threads per CTA in thread-per-game mode (8 teams share 4 MLP slots)
     DevBuf<uint4> nodes; // 2 x uint4 = one 32-byte record per tree node
     DevBuf<float> weights;
     DevBuf<uint8_t> weight_image; // mlptc layout (fp16 weights + fp32 biases)
@@ -122,11 +122,11 @@ static int validate_cfg(const syn_rollout_cfg* cfg, const syn_engine* e) {
     return SYN_OK;
 }
 
-template <int TEAMS>
+template <int TEAMS, int SLOTS>
 static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
-    size_t smem = sizeof(mlpteam::Smem<TEAMS>);
-    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg_kernel<TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    selfplay_nn_tpg_kernel<TEAMS><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+    size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>);
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg_kernel<TEAMS, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_nn_tpg_kernel<TEAMS, SLOTS><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
     return SYN_OK;
 }
 
@@ -149,7 +149,9 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         if (blocks > max_blocks) blocks = max_blocks;
         if (blocks == 0) blocks = 1;
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-        int rc = e->tpg_teams == 4 ? launch_tpg<4>(e, kp, blocks) : (e->tpg_teams == 2 ? launch_tpg<2>(e, kp, blocks) : launch_tpg<1>(e, kp, blocks));
+        int rc = e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
+                 : e->tpg_teams == 4 ? launch_tpg<4, 4>(e, kp, blocks)
+                 : e->tpg_teams == 2 ? launch_tpg<2, 2>(e, kp, blocks) : launch_tpg<1, 1>(e, kp, blocks);
         if (rc) return rc;
         CUDA_TRY(cudaGetLastError());
         e->launches += 1;
@@ -270,9 +272,9 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     const char* glenv = std::getenv("SYN_GROUP_LANES");
     e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : ((glenv && std::atoi(glenv) == 32) ? 32 : 1);
     const char* tenv = std::getenv("SYN_TPG_TEAMS");
-    if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4)) e->tpg_teams = std::atoi(tenv);
+    if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
     // round the in-flight game count up to whole CTAs of every kernel
-    uint32_t unit = 512;
+    uint32_t unit = 1024;
     e->max_games = ((max_games_in_flight + unit - 1) / unit) * unit;
     e->max_explores = max_explores;
     // nodes.len() <= 1 + 9 * (explores + 1): every visit pushes at most 9 nodes (mcts.rs:384-397)

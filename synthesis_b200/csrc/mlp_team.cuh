@@ -13,7 +13,11 @@
 //     next activations, so layer l+1's A overwrites layer l's in place.
 //   * several teams per CTA share ONE resident fp16 weight image (bulk-async copy, once per
 //     kernel) and run their chains independently: team barriers are named barriers over 128
-//     threads, completion is one mbarrier per team, accumulators are disjoint TMEM column ranges.
+//     threads; a forward runs in one of SLOTS "MLP slots" = {A tile, 128 TMEM columns, mbarrier}.
+//     With SLOTS == TEAMS every team owns a slot; with more teams than slots (8 teams, 4 slots:
+//     1024 threads per SM at 64 registers) a team takes any free slot for the ~15 % of a round
+//     it spends in the forward and gives it back, so shared memory and TMEM hold four tiles
+//     while twice as many warps hide the tree phase's memory latency.
 #pragma once
 #include "mlp_tc.cuh"
 
@@ -24,13 +28,16 @@ using namespace mlptc;
 constexpr int A_BYTES = (128 / 8) * M_TILE * 16; // K up to 128 -> 32768 B per team
 constexpr int TEAM = 128;
 
-template <int TEAMS>
+template <int TEAMS, int SLOTS>
 struct __align__(128) Smem {
     uint8_t img[IMG_BYTES];      // fp16 weights of the five layers + fp32 biases (bulk-copied image)
-    uint8_t a[TEAMS][A_BYTES];   // one activation tile per team
+    uint8_t a[SLOTS][A_BYTES];   // one activation tile per MLP slot
     uint4 col_lut[256];          // fp16 features of one board column by (stones, owners): see write_features
     uint64_t bar_w;              // weights landed
-    uint64_t bar_mma[TEAMS];     // a team's layer completed
+    uint64_t bar_mma[SLOTS];     // a slot's layer completed
+    uint32_t slot_busy[SLOTS];   // 0 free / 1 taken (only used when SLOTS < TEAMS)
+    uint32_t slot_phase[SLOTS];  // running parity of bar_mma[slot], handed from owner to owner
+    uint32_t team_slot[TEAMS];   // the slot a team's leader just took (broadcast to the team)
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -92,17 +99,17 @@ __device__ __forceinline__ void write_features(uint8_t* a_tile, const uint4* lut
 }
 
 // Prologue: all threads of the CTA call.
-template <int TEAMS>
-__device__ __forceinline__ void setup(Smem<TEAMS>& s, const uint8_t* __restrict__ weight_image) {
+template <int TEAMS, int SLOTS>
+__device__ __forceinline__ void setup(Smem<TEAMS, SLOTS>& s, const uint8_t* __restrict__ weight_image) {
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         mbar_init(&s.bar_w, 1);
 #pragma unroll
-        for (int t = 0; t < TEAMS; ++t) mbar_init(&s.bar_mma[t], 1);
+        for (int t = 0; t < SLOTS; ++t) { mbar_init(&s.bar_mma[t], 1); s.slot_busy[t] = 0u; s.slot_phase[t] = 0u; }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&s.tmem_base, 128 * TEAMS);
-    for (int i = threadIdx.x; i < TEAMS * A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(&s.a[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) tmem_alloc(&s.tmem_base, 128 * SLOTS);
+    for (int i = threadIdx.x; i < SLOTS * A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(&s.a[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s.col_lut[i] = col_lut_entry(i < 255 ? i : 0);
     tc_fence_before();
     __syncthreads();
@@ -116,21 +123,54 @@ __device__ __forceinline__ void setup(Smem<TEAMS>& s, const uint8_t* __restrict_
     __syncthreads();
 }
 
-template <int TEAMS>
-__device__ __forceinline__ void teardown(Smem<TEAMS>& s) {
+template <int TEAMS, int SLOTS>
+__device__ __forceinline__ void teardown(Smem<TEAMS, SLOTS>& s) {
     tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tmem_dealloc(s.tmem_base, 128 * TEAMS);
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(s.tmem_base, 128 * SLOTS);
+}
+
+// Takes an MLP slot for the team (all 128 threads call; returns the slot and the parity of its mbarrier).
+template <int TEAMS, int SLOTS>
+__device__ __forceinline__ int acquire_slot(Smem<TEAMS, SLOTS>& s, int team, int r, uint32_t& phase) {
+    if (SLOTS == TEAMS) { phase = s.slot_phase[team]; return team; }
+    if (r == 0) {
+        int got = -1;
+        for (int k = team; got < 0; ++k) {
+            int cand = k % SLOTS;
+            if (atomicCAS(&s.slot_busy[cand], 0u, 1u) == 0u) got = cand;
+            else if (cand == SLOTS - 1) __nanosleep(64);
+        }
+        __threadfence_block();
+        s.team_slot[team] = (uint32_t)got;
+    }
+    team_sync(team);
+    int slot = (int)s.team_slot[team];
+    phase = s.slot_phase[slot];
+    return slot;
+}
+
+// Gives the slot back: every thread has finished reading the slot's TMEM columns and A tile.
+template <int TEAMS, int SLOTS>
+__device__ __forceinline__ void release_slot(Smem<TEAMS, SLOTS>& s, int team, int r, int slot, uint32_t phase) {
+    if (SLOTS == TEAMS) { if (r == 0) s.slot_phase[slot] = phase; return; }
+    tc_fence_before();
+    team_sync(team);
+    if (r == 0) {
+        s.slot_phase[slot] = phase;
+        __threadfence_block();
+        atomicExch(&s.slot_busy[slot], 0u);
+    }
 }
 
 // Forward pass of the team's 128 rows.  Every thread of the team calls with its row's features
-// already in the A tile (generic-proxy stores); `phase` is the running parity of the team's
-// mbarrier (start at 0, kept by the caller).  On return y[0..8] are the row's policy logits and
+// already in the slot's A tile (generic-proxy stores); `phase` is the running parity of the slot's
+// mbarrier (acquire_slot / release_slot carry it).  On return y[0..8] are the row's policy logits and
 // y[9..11] its value logits.
-template <int TEAMS>
-__device__ __forceinline__ void forward(Smem<TEAMS>& s, int team, int r, uint32_t& phase, float (&y)[12]) {
-    uint8_t* a_tile = s.a[team];
-    const uint32_t tmem = s.tmem_base + (uint32_t)(team * 128);           // the team's 128 accumulator columns
+template <int TEAMS, int SLOTS>
+__device__ __forceinline__ void forward(Smem<TEAMS, SLOTS>& s, int team, int slot, int r, uint32_t& phase, float (&y)[12]) {
+    uint8_t* a_tile = s.a[slot];
+    const uint32_t tmem = s.tmem_base + (uint32_t)(slot * 128);           // the slot's 128 accumulator columns
     const uint32_t tlane = tmem + ((uint32_t)((r >> 5) * 32) << 16);       // this warp's 32 TMEM lanes
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -147,9 +187,9 @@ __device__ __forceinline__ void forward(Smem<TEAMS>& s, int team, int r, uint32_
                 uint64_t bd = make_desc(b_base + kk * 2 * (N * 16), N * 16, 128);
                 umma_f16(tmem, ad, bd, make_idesc(N), kk > 0 ? 1u : 0u);
             }
-            umma_commit(&s.bar_mma[team]);
+            umma_commit(&s.bar_mma[slot]);
         }
-        mbar_wait(&s.bar_mma[team], phase);
+        mbar_wait(&s.bar_mma[slot], phase);
         phase ^= 1u;
         tc_fence_after();
         const float* bias = reinterpret_cast<const float*>(s.img + BIAS_OFF) + b_off(l);

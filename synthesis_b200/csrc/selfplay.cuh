@@ -535,11 +535,11 @@ __global__ void __launch_bounds__(THREADS, 1) eval_kernel(const float* __restric
 #include "tpg.cuh"
 namespace eng {
 
-template <int TEAMS>
+template <int TEAMS, int SLOTS>
 __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    mlpteam::Smem<TEAMS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS>*>(smem_raw);
-    mlpteam::setup<TEAMS>(ms, p.weight_image);
+    mlpteam::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS, SLOTS>*>(smem_raw);
+    mlpteam::setup<TEAMS, SLOTS>(ms, p.weight_image);
     const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
     tpg::Ctx c;
     c.cfg = &p.cfg.mcts; c.cap = p.arena_nodes; c.seed = p.seed; c.search_mode = p.search_mode != 0;
@@ -547,20 +547,22 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg_kernel(const _
     tpg::init_game(p, g, (size_t)blockIdx.x * (128 * TEAMS) + threadIdx.x);
     tpg::Leaf lf;
     uint64_t my = 0, op = 0;
-    uint32_t mma_phase = 0;
     long long t_adv = 0, t_wait = 0, t_mlp = 0, t_fin = 0, t_start = clock64();
     uint32_t rounds = 0, leaves = 0;
     for (;;) {
         long long t0 = clock64();
         bool need = tpg::advance(p, c, g, lf, my, op);
-        if (need) mlpteam::write_features(ms.a[team], ms.col_lut, r, my, op);
         __syncwarp();
         long long t1 = clock64();
         leaves += (uint32_t)__popc(__ballot_sync(0xffffffffu, need));
         if (!mlpteam::team_any(team, need)) break; // no thread of this team has a game left
+        uint32_t mma_phase;
+        const int slot = mlpteam::acquire_slot<TEAMS, SLOTS>(ms, team, r, mma_phase);
         long long t2 = clock64();
+        if (need) mlpteam::write_features(ms.a[slot], ms.col_lut, r, my, op);
         float y[12];
-        mlpteam::forward<TEAMS>(ms, team, r, mma_phase, y);
+        mlpteam::forward<TEAMS, SLOTS>(ms, team, slot, r, mma_phase, y);
+        mlpteam::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
         long long t3 = clock64();
         if (need) {
             // value.softmax(-1) (study-connect4/src/policies.rs:54-56)
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg_kernel(const _
         atomicAdd(p.counters + DBG_T_TOTAL, (unsigned long long)(clock64() - t_start));
     }
     tpg::flush_counters(p, g);
-    mlpteam::teardown<TEAMS>(ms);
+    mlpteam::teardown<TEAMS, SLOTS>(ms);
 }
 
 // ------------------------------------------------------------------ game rules on move lists (syn_engine_play)
