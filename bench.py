@@ -33,17 +33,32 @@ UNIT = "explores/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--steps", type=int, default=2)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--games", type=int, default=4096, help="self-play games per GPU per step")
+    p.add_argument("--games", type=int, default=0, help="self-play games per GPU per step (default: --games-mult x games in flight)")
+    p.add_argument("--games-mult", type=int, default=3,
+                   help="games per step as a multiple of the games one GPU holds in flight (amortises the end-of-step tail)")
     p.add_argument("--explores", type=int, default=800)
     p.add_argument("--leaf", default="nn", choices=["nn", "rollout"])
     p.add_argument("--group-lanes", type=int, default=int(os.environ.get("SYN_GROUP_LANES", "1")),
                    help="lanes per game: 1 = thread per game (default), 16 / 32 = lane group per game")
-    p.add_argument("--cpu-games", type=int, default=0, help="games in the CPU sample (default 8 per host thread)")
+    p.add_argument("--cpu-games", type=int, default=0, help="games in the CPU sample (default 96 per host thread, ~10-20 s)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
+
+
+def size_workload(args):
+    """Games one GPU holds in flight and games per step; identical for both arms so their `config` matches."""
+    if args.leaf == "nn" and args.group_lanes == 1:
+        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "8"))  # one CTA per SM, teams of 128 games
+    elif args.leaf == "nn":
+        in_flight = 148 * (512 // args.group_lanes)
+    else:
+        in_flight = 148 * 8 * (256 // (16 if args.group_lanes == 1 else args.group_lanes))
+    args.in_flight = in_flight
+    args.games = args.games or args.games_mult * in_flight
+    return in_flight, args.games
 
 
 def workload_cfg(args):
@@ -63,7 +78,8 @@ def config_dict(args, n_gpus):
         "mcts": "PUCT c=3, Fpu::Const(1.0), solve+correct_values+select_solved+auto_extend, no root noise (study-connect4/src/main.rs:58-66)",
         "driver": "random_actions_until=1, sample_actions_until=30, ValueTarget::Q, ActionSelection::NumVisits (main.rs:31-35)",
         "parallelism": "game-sharded x%d (no data-path collective)" % n_gpus,
-        "l2": "inputs larger than L2: tree arenas of the games in flight are ~0.23 MB/game (~1 GB/GPU) vs 126 MB L2; a new seed per step",
+        "games_in_flight_per_gpu": getattr(args, "in_flight", None),
+        "l2": "inputs larger than L2: the tree arenas of the games in flight (0.23 MB/game at 800 explores) total ~35 GB per GPU vs 126 MB L2; a new seed per step",
     }
 
 
@@ -125,6 +141,19 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def ncu_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for ONE launch of this configuration, from the
+    committed ncu capture (profiles/traffic.json, written by scripts/ncu_traffic.py); None if no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            for rec in json.load(f):
+                if (rec["leaf"], rec["explores"], rec["games"], rec["group_lanes"]) == (args.leaf, args.explores, args.games, args.group_lanes):
+                    return rec["dram_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 def algorithmic_bytes_per_explore(st):
     """B = d*(20 + 18*C) + x*C*47 + (d+1)*36 with d = select levels per explore, C = children
     per selected parent, x = expansions per explore, all measured in this run."""
@@ -171,7 +200,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    games = args.cpu_games or 8 * cores
+    cpu_games = args.cpu_games or 96 * cores
+    size_workload(args)  # the same `config` as our arm; every step times a bounded sample of that workload
+    games = cpu_games
     for w in range(args.warmup):
         cpu_reference_run(args, max(cores, games // 8), 1000 + w)
     tot_e = tot_rows = 0
@@ -220,15 +251,9 @@ def run_ours(args):
 
     leaf = L.LEAF_NN if args.leaf == "nn" else L.LEAF_ROLLOUT
     cfg = workload_cfg(args)
-    if args.leaf == "nn" and args.group_lanes == 1:
-        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "8"))  # one CTA per SM, teams of 128 games
-    elif args.leaf == "nn":
-        in_flight = 148 * (512 // args.group_lanes)
-    else:
-        in_flight = 148 * 8 * (256 // (16 if args.group_lanes == 1 else args.group_lanes))
+    in_flight, games = size_workload(args)
     eng = s.Engine(local_rank, in_flight, args.explores)
     eng.set_group_lanes(args.group_lanes)
-    games = args.games
     first = rank * games  # weak scaling: every rank plays `games` games of the global index space
 
     # weights: rank 0 owns them (the trainer); ONE broadcast per iteration when N > 1
@@ -295,7 +320,9 @@ def run_ours(args):
     # N = 1: weights pinned-host -> HBM, experience HBM -> pinned host.  N > 1 adds the two collectives the
     # path has per iteration: ONE broadcast of the weights from rank 0 and ONE gather of the rows to rank 0
     # (NCCL over NVLink), rank 0 then copies everything to its pinned host buffers.
-    cap = L.MAX_TURNS * games
+    # rows per game: 63 always suffices (synthesis_b200.h); this workload's games last ~28 plies, so 44 per game bounds
+    # the pinned buffers (the engine reports SYN_ERR_CAPACITY instead of overrunning if that were ever too small)
+    cap = min(L.MAX_TURNS, 44) * games
     host = {n: torch.zeros((cap * (world if rank == 0 else 1),) + sh, dtype=D._torch_dtype(torch, dt)).pin_memory() for n, dt, sh in D.FIELDS}
     dev_out = None
     if dist is not None:
@@ -347,15 +374,15 @@ def run_ours(args):
         peak, peak_src = measured_peak_hbm()
         kernel_s = dev_ns * 1e-9 / max(1, args.steps)  # rank 0's kernel, average launch duration
         achieved = bpe * (acc["explores"] / max(1, args.steps)) / kernel_s / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "selfplay_nn_kernel" if args.leaf == "nn" else "selfplay_rollout_kernel",
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args),
+                    "kernel": ("selfplay_nn_tpg_kernel" if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn" else "selfplay_rollout_kernel",
                     "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": acc["explores"] / max(1, args.steps),
                     "launch_ms": 1e3 * kernel_s, "peak_source": peak_src, **shape,
                     "note": "latency-bound pointer chasing over per-game trees; see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cgames = args.cpu_games or 8 * cores
+            cgames = args.cpu_games or 96 * cores
             cst, cdt, cores = cpu_reference_run(args, cgames, 0)
             cpu = {"value": cst["explores"] / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d games (%d explores, %.1f s), reference schedule: %d worker threads, per-worker memo cache"

@@ -1,0 +1,124 @@
+//! Raw bindings of `include/synthesis_b200.h` — mechanical, one item per C declaration.
+//! (Source only; not compiled in the build image, which has no Rust toolchain.)
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int};
+
+pub const SYN_N_ACTIONS: usize = 9;
+pub const SYN_MAX_TURNS: usize = 63;
+pub const SYN_N_FEATURES: usize = 63;
+pub const SYN_N_WEIGHTS: usize = 30492;
+
+pub const SYN_OK: c_int = 0;
+pub const SYN_ERR_UNSUPPORTED: c_int = -4;
+
+pub const SYN_EXPLORATION_UCT: u32 = 0;
+pub const SYN_EXPLORATION_POLYNOMIAL_UCT: u32 = 1;
+pub const SYN_FPU_CONST: u32 = 0;
+pub const SYN_FPU_PARENT_Q: u32 = 1;
+pub const SYN_FPU_NORMAL: u32 = 2;
+pub const SYN_FPU_FUNC: u32 = 3;
+pub const SYN_NOISE_NONE: u32 = 0;
+pub const SYN_NOISE_EQUAL: u32 = 1;
+pub const SYN_NOISE_DIRICHLET: u32 = 2;
+pub const SYN_VALUE_Z: u32 = 0;
+pub const SYN_VALUE_Q: u32 = 1;
+pub const SYN_VALUE_QZ_AVERAGE: u32 = 2;
+pub const SYN_VALUE_Q_TO_Z: u32 = 3;
+pub const SYN_ACTION_Q: u32 = 0;
+pub const SYN_ACTION_NUM_VISITS: u32 = 1;
+pub const SYN_LEAF_NN: u32 = 0;
+pub const SYN_LEAF_ROLLOUT: u32 = 1;
+pub const SYN_TREE_MCTS: u32 = 0;
+pub const SYN_TREE_FROZEN: u32 = 1;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct syn_mcts_cfg {
+    pub exploration_kind: u32,
+    pub c: f32,
+    pub solve: u8,
+    pub correct_values_on_solve: u8,
+    pub select_solved_nodes: u8,
+    pub auto_extend: u8,
+    pub fpu_kind: u32,
+    pub fpu_a: f32,
+    pub fpu_b: f32,
+    pub noise_kind: u32,
+    pub noise_alpha: f32,
+    pub noise_weight: f32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct syn_rollout_cfg {
+    pub num_explores: u32,
+    pub random_actions_until: u32,
+    pub sample_actions_until: u32,
+    pub stop_games_when_solved: u8,
+    pub _pad: [u8; 3],
+    pub value_target_kind: u32,
+    pub vt_a: f32,
+    pub vt_b: f32,
+    pub action_selection: u32,
+    pub mcts: syn_mcts_cfg,
+    pub leaf_eval_kind: u32,
+}
+
+#[repr(C)]
+pub struct syn_experience {
+    pub capacity: usize,
+    pub len: usize,
+    pub games: usize,
+    pub game_ids: *mut u64,
+    pub my_bb: *mut u64,
+    pub op_bb: *mut u64,
+    pub height: *mut u8,   // [cap][9]
+    pub player: *mut u8,
+    pub states: *mut f32,  // [cap][63]
+    pub pis: *mut f32,     // [cap][9]
+    pub vs: *mut f32,      // [cap][3]
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct syn_stats {
+    pub explores: u64,
+    pub leaf_evals: u64,
+    pub rows: u64,
+    pub games: u64,
+    pub trees: u64,
+    pub nodes: u64,
+    pub select_levels: u64,
+    pub children_scanned: u64,
+    pub expansions: u64,
+    pub children_created: u64,
+    pub backprop_levels: u64,
+    pub rollout_plies: u64,
+    pub device_ns: u64,
+    pub kernel_launches: u64,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
+}
+
+#[repr(C)]
+pub struct syn_engine {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn syn_abi_version() -> c_int;
+    pub fn syn_build_info() -> *const c_char;
+    pub fn syn_last_error() -> *const c_char;
+    pub fn syn_engine_create(cuda_device: c_int, max_games_in_flight: u32, max_explores: u32, out: *mut *mut syn_engine) -> c_int;
+    pub fn syn_engine_destroy(e: *mut syn_engine);
+    pub fn syn_engine_set_weights(e: *mut syn_engine, blob: *const f32, n_floats: usize) -> c_int;
+    pub fn syn_engine_gather(e: *mut syn_engine, cfg: *const syn_rollout_cfg, first_game_index: u64, num_games: u32, seed: u64,
+                             out: *mut syn_experience, stats: *mut syn_stats) -> c_int;
+    pub fn syn_engine_gather_launch(e: *mut syn_engine, cfg: *const syn_rollout_cfg, first_game_index: u64, num_games: u32, seed: u64) -> c_int;
+    pub fn syn_engine_gather_wait(e: *mut syn_engine, out: *mut syn_experience, stats: *mut syn_stats) -> c_int;
+    pub fn syn_engine_search(e: *mut syn_engine, cfg: *const syn_rollout_cfg, tree_kind: u32, my_bb: *const u64, op_bb: *const u64,
+                             seeds: *const u64, n_positions: u32, child_visits: *mut f32, child_solution: *mut u8, root_q: *mut f32,
+                             root_solution: *mut u8, best_action: *mut u8, num_nodes: *mut u32, stats: *mut syn_stats) -> c_int;
+    pub fn syn_engine_eval(e: *mut syn_engine, my_bb: *const u64, op_bb: *const u64, n_positions: u32, logits: *mut f32,
+                           outcome_probs: *mut f32) -> c_int;
+}

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+nproc; free -g | head -2
+( time timeout 1500 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err ) 2>&1 | grep real; cat gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
+( time timeout 900 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err ) 2>&1 | grep real; cat gpurun_out/bench_reference.json; tail -3 gpurun_out/bench_reference.err
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:selfplay -c 1 --csv --log-file gpurun_out/traffic_nn_e800_g454656.csv python scripts/prof_driver.py 454656 800 1 nn > gpurun_out/traffic.log 2>&1; tail -2 gpurun_out/traffic.log
