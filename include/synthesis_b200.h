@@ -188,6 +188,34 @@ int syn_engine_search(syn_engine* e, const syn_rollout_cfg* cfg, uint32_t tree_k
                       uint8_t* child_solution, float* root_q, uint8_t* root_solution, uint8_t* best_action,
                       uint32_t* num_nodes, syn_stats* stats);
 
+/* One player of an evaluation match: which tree (MCTS, mcts.rs, or the evaluator's FrozenMCTS,
+ * evaluator.rs:299-534), which Policy evaluates its leaves, how many explores per move and how the
+ * move is read from the finished tree.  Mirrors the argument lists of MCTS::exploit (mcts.rs:111-121)
+ * and FrozenMCTS::exploit (evaluator.rs:308-318) and the pairs (policy_*, rollout_*) of
+ * EvaluationConfig (config.rs:58-74). */
+typedef struct {
+    uint32_t tree_kind;        /* syn_tree_kind */
+    uint32_t leaf_eval_kind;   /* syn_leaf_eval_kind */
+    uint32_t num_explores;
+    uint32_t action_selection; /* syn_action_selection */
+    syn_mcts_cfg mcts;
+} syn_player_cfg;
+
+/* Replaces the evaluator's game loops eval_against_rollout_mcts (evaluator.rs:163-198), mcts_vs_mcts
+ * (:200-228) and eval_against_old (:129-160, one network) on a batch of independent matches: match i
+ * starts from Connect4::new(), players[0] moves first, every move is `exploit` of the mover's player
+ * (a fresh tree per move), and the game ends when Game::step reports is_over.  All RolloutPolicy
+ * draws of match i — by either player — come from ONE stream StdRng::seed_from_u64(seeds[i]), as in
+ * the reference where both FrozenMCTS players share `rollout_policy` (evaluator.rs:208-209).
+ * explores (optional, [n][2]) overrides players[k].num_explores per match (the evaluator sweeps the
+ * opponent's explores, evaluator.rs:65-82); every value must be <= the engine's max_explores.
+ * Outputs (any may be NULL): result[n] = game.reward(first_player) in {+1, 0, -1};
+ * n_moves[n]; moves[n][63] (columns played); per-move trace tree_nodes[n][63] = nodes.len() and
+ * child_visits[n][63][9] = the root's child visit counts by column (0 for illegal columns). */
+int syn_engine_match(syn_engine* e, const syn_player_cfg players[2], const uint64_t* seeds, const uint32_t* explores,
+                     uint32_t n_matches, float* result, uint8_t* n_moves, uint8_t* moves, uint32_t* tree_nodes,
+                     float* child_visits, syn_stats* stats);
+
 /* Replaces Policy::eval for Connect4Net (study-connect4/src/policies.rs:47-59) on a batch:
  * logits[n][9] are the raw policy logits, outcome_probs[n][3] = softmax of the value head,
  * [Lose, Draw, Win] for the player to move. */

@@ -213,6 +213,64 @@ int orc_search(const syn_rollout_cfg* cfg, uint32_t tree_kind, uint64_t my_bb, u
     return 0;
 }
 
+// ---- one evaluation match (evaluator.rs:129-228): players[0] moves first; every move is
+// MCTS::exploit (mcts.rs:111-121) or FrozenMCTS::exploit (evaluator.rs:308-318) of the mover's
+// player on a clone of the game; all RolloutPolicy draws of the match come from ONE
+// StdRng::seed_from_u64(seed) (evaluator.rs:172-173, 207-208).  Returns game.reward(first_player).
+// Trace per move: the column played, nodes.len() and the root's child visit counts by column.
+int orc_match(const syn_player_cfg* players, uint64_t seed, const uint32_t* explores2, const float* weights, orc_eval_fn callback,
+              void* ctx, uint32_t flags, float* result, uint8_t* n_moves, uint8_t* moves63, uint32_t* tree_nodes63,
+              float* child_visits63x9, syn_stats* stats) {
+    TreeOptions opt = opts_from(flags);
+    Counters cnt;
+    StdRng rng = StdRng::seed_from_u64(seed);
+    StdRng noise_rng = StdRng::seed_from_u64(seed ^ (1ull << 63));
+    StdRng fpu_rng = StdRng::seed_from_u64((seed ^ (1ull << 63)) + 1);
+    RolloutPolicy<Connect4> rp(&rng, &cnt);
+    Connect4Net net(weights, opt.libm);
+    CallbackPolicy cb(callback, ctx);
+    Connect4 game;
+    int first_player = game.player();
+    uint32_t ply = 0;
+    if (child_visits63x9) std::memset(child_visits63x9, 0, 63 * 36);
+    for (;;) {
+        const syn_player_cfg& pl = players[ply & 1u];
+        uint32_t E = explores2 ? explores2[ply & 1u] : pl.num_explores;
+        Policy<Connect4>* p = pl.leaf_eval_kind == SYN_LEAF_ROLLOUT ? (Policy<Connect4>*)&rp
+                              : (callback ? (Policy<Connect4>*)&cb : (Policy<Connect4>*)&net);
+        if (pl.leaf_eval_kind == SYN_LEAF_NN && !weights && !callback) return SYN_ERR_NO_WEIGHTS;
+        int action;
+        if (pl.tree_kind == SYN_TREE_MCTS) {
+            MCTS<Connect4> m(E + 1, pl.mcts, p, game, opt, &noise_rng, &fpu_rng, &cnt);
+            m.explore_n(E);
+            m.finish();
+            action = m.best_action(pl.action_selection);
+            const auto& r = m.nodes[m.root];
+            if (tree_nodes63) tree_nodes63[ply] = (uint32_t)m.nodes.size();
+            if (child_visits63x9)
+                for (uint32_t c = r.first_child; c < r.last_child(); ++c) child_visits63x9[9 * ply + m.nodes[c].action] = m.nodes[c].num_visits;
+        } else {
+            FrozenMCTS<Connect4> m(E + 1, pl.mcts, p, game, opt, &cnt);
+            m.explore_n(E);
+            m.finish();
+            if (m.unsupported) return SYN_ERR_UNSUPPORTED;
+            action = m.best_action(pl.action_selection);
+            if (action < 0) return SYN_ERR_DEVICE_FAULT; // the reference's unwrap() panics
+            const auto& r = m.nodes[m.root];
+            if (tree_nodes63) tree_nodes63[ply] = (uint32_t)m.nodes.size();
+            if (child_visits63x9)
+                for (uint32_t c = r.first_child; c < r.last_child(); ++c) child_visits63x9[9 * ply + m.nodes[c].action] = m.nodes[c].num_visits;
+        }
+        if (moves63) moves63[ply] = (uint8_t)action;
+        ++ply;
+        if (game.step(action)) break;
+    }
+    if (result) *result = game.reward(first_player);
+    if (n_moves) *n_moves = (uint8_t)ply;
+    fill_stats(stats, cnt, ply, 1, 0);
+    return 0;
+}
+
 // ---- gather with the engine's per-game streams.  trace_* (optional, one entry per row):
 // the action played, nodes.len() of that ply's tree, and the root's child visit counts.
 int orc_gather(const syn_rollout_cfg* cfg, const float* weights, orc_eval_fn callback, void* ctx, uint64_t seed,

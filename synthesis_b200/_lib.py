@@ -52,6 +52,13 @@ class SynRolloutCfg(C.Structure):
     ]
 
 
+class SynPlayerCfg(C.Structure):
+    _fields_ = [
+        ("tree_kind", C.c_uint32), ("leaf_eval_kind", C.c_uint32), ("num_explores", C.c_uint32),
+        ("action_selection", C.c_uint32), ("mcts", SynMctsCfg),
+    ]
+
+
 class SynExperience(C.Structure):
     _fields_ = [
         ("capacity", C.c_size_t), ("len", C.c_size_t), ("games", C.c_size_t),
@@ -74,7 +81,7 @@ class SynStats(C.Structure):
 EXPORTED_SYMBOLS = (
     "syn_abi_version", "syn_build_info", "syn_last_error", "syn_engine_create", "syn_engine_destroy",
     "syn_engine_set_weights", "syn_engine_gather", "syn_engine_gather_launch", "syn_engine_gather_wait",
-    "syn_engine_search", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode", "syn_engine_debug_counters",
+    "syn_engine_search", "syn_engine_match", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode", "syn_engine_debug_counters",
 )
 
 _lib = None
@@ -108,6 +115,7 @@ def load():
     lib.syn_engine_gather_launch.argtypes = [vp, C.POINTER(SynRolloutCfg), u64, u32, u64]
     lib.syn_engine_gather_wait.argtypes = [vp, C.POINTER(SynExperience), C.POINTER(SynStats)]
     lib.syn_engine_search.argtypes = [vp, C.POINTER(SynRolloutCfg), u32, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, C.POINTER(SynStats)]
+    lib.syn_engine_match.argtypes = [vp, C.POINTER(SynPlayerCfg), vp, vp, u32, vp, vp, vp, vp, vp, C.POINTER(SynStats)]
     lib.syn_engine_eval.argtypes = [vp, vp, vp, u32, vp, vp]
     lib.syn_engine_play.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp, vp]
     lib.syn_engine_set_trace.argtypes = [vp, vp, vp, vp]

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "selfplay.cuh"
+#include "match.cuh"
 
 using namespace eng;
 
@@ -235,7 +236,58 @@ static int check_device_error(syn_engine* e) {
     if (derr == DERR_ARENA_OVERFLOW) return fail(SYN_ERR_CAPACITY, "a tree outgrew its arena of %u nodes", e->arena_nodes);
     if (derr == DERR_DEPTH_OVERFLOW) return fail(SYN_ERR_DEVICE_FAULT, "a tree path exceeded 64 levels");
     if (derr == DERR_BAD_WEIGHTS) return fail(SYN_ERR_DEVICE_FAULT, "WeightedIndex met an all-zero or non-finite search policy (the reference would panic)");
+    if (derr == DERR_NO_BEST_ACTION) return fail(SYN_ERR_DEVICE_FAULT, "FrozenMCTS::best_action met a root whose children are all unvisited (the reference would panic)");
     if (derr) return fail(SYN_ERR_DEVICE_FAULT, "device error %d", derr);
+    return SYN_OK;
+}
+
+static int validate_mcts_cfg(const syn_mcts_cfg& m) {
+    if (m.exploration_kind > SYN_EXPLORATION_POLYNOMIAL_UCT) return fail(SYN_ERR_INVALID_ARGUMENT, "bad exploration_kind %u", m.exploration_kind);
+    if (m.fpu_kind == SYN_FPU_FUNC)
+        return fail(SYN_ERR_UNSUPPORTED, "Fpu::Func carries host code and cannot run on the device; use SYN_FPU_NORMAL{mean,std} for the shipped closure");
+    if (m.fpu_kind > SYN_FPU_FUNC) return fail(SYN_ERR_INVALID_ARGUMENT, "bad fpu_kind %u", m.fpu_kind);
+    if (m.noise_kind > SYN_NOISE_DIRICHLET) return fail(SYN_ERR_INVALID_ARGUMENT, "bad noise_kind %u", m.noise_kind);
+    if (m.noise_kind == SYN_NOISE_DIRICHLET && !(m.noise_alpha > 0.0f)) return fail(SYN_ERR_INVALID_ARGUMENT, "Dirichlet alpha must be > 0");
+    return SYN_OK;
+}
+
+// FrozenMCTS panics on anything but Fpu::Const and Exploration::Uct (evaluator.rs:410, 424)
+static int validate_frozen_cfg(const syn_mcts_cfg& m) {
+    if (m.fpu_kind != SYN_FPU_CONST) return fail(SYN_ERR_UNSUPPORTED, "FrozenMCTS supports Fpu::Const only (evaluator.rs:410 panics otherwise)");
+    if (m.exploration_kind != SYN_EXPLORATION_UCT) return fail(SYN_ERR_UNSUPPORTED, "FrozenMCTS supports Exploration::Uct only (evaluator.rs:424 panics otherwise)");
+    return SYN_OK;
+}
+
+static int validate_player(const syn_player_cfg& pl, const syn_engine* e, int k) {
+    if (pl.tree_kind > SYN_TREE_FROZEN) return fail(SYN_ERR_INVALID_ARGUMENT, "players[%d]: bad tree_kind %u", k, pl.tree_kind);
+    if (pl.leaf_eval_kind > SYN_LEAF_ROLLOUT) return fail(SYN_ERR_INVALID_ARGUMENT, "players[%d]: bad leaf_eval_kind %u", k, pl.leaf_eval_kind);
+    if (pl.action_selection > SYN_ACTION_NUM_VISITS) return fail(SYN_ERR_INVALID_ARGUMENT, "players[%d]: bad action_selection %u", k, pl.action_selection);
+    if (pl.num_explores > e->max_explores)
+        return fail(SYN_ERR_CAPACITY, "players[%d]: num_explores %u exceeds the engine's max_explores %u", k, pl.num_explores, e->max_explores);
+    if (pl.leaf_eval_kind == SYN_LEAF_NN && !e->has_weights)
+        return fail(SYN_ERR_NO_WEIGHTS, "players[%d]: leaf_eval_kind = NN but syn_engine_set_weights has not been called", k);
+    int rc = validate_mcts_cfg(pl.mcts);
+    if (rc) return rc;
+    if (pl.tree_kind == SYN_TREE_FROZEN) return validate_frozen_cfg(pl.mcts);
+    return SYN_OK;
+}
+
+// Launches the thread-per-match kernel (match.cuh) over kp.num_games matches or search roots.
+constexpr int MATCH_TEAMS = 4;
+static int launch_match(syn_engine* e, KParams& kp, mtc::MParams& mp) {
+    const uint32_t per_cta = 128u * MATCH_TEAMS;
+    uint32_t blocks = kp.num_games < (uint32_t)e->sm_count ? kp.num_games : (uint32_t)e->sm_count;
+    if (blocks == 0) blocks = 1;
+    uint32_t active = (kp.num_games + blocks - 1) / blocks;
+    if (active > per_cta) active = per_cta;
+    if ((uint64_t)blocks * active > e->max_games) active = e->max_games / blocks;
+    if (active == 0) { blocks = e->max_games; active = 1; }
+    mp.active_per_block = active;
+    size_t smem = sizeof(mlpteam::Smem<MATCH_TEAMS, MATCH_TEAMS>);
+    CUDA_TRY(cudaFuncSetAttribute(match_tpg_kernel<MATCH_TEAMS, MATCH_TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    match_tpg_kernel<MATCH_TEAMS, MATCH_TEAMS><<<blocks, per_cta, smem, e->stream>>>(kp, mp);
+    CUDA_TRY(cudaGetLastError());
+    e->launches += 1;
     return SYN_OK;
 }
 
@@ -471,9 +523,10 @@ int syn_engine_search(syn_engine* e, const syn_rollout_cfg* cfg, uint32_t tree_k
     if (!e || !my_bb || !op_bb || !seeds) return fail(SYN_ERR_INVALID_ARGUMENT, "engine, bitboards and seeds must not be NULL");
     if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is in flight");
     if (n == 0) return fail(SYN_ERR_INVALID_ARGUMENT, "n_positions must be > 0");
-    if (tree_kind != SYN_TREE_MCTS) return fail(SYN_ERR_UNSUPPORTED, "tree_kind %u: FrozenMCTS is not implemented on the device yet", tree_kind);
+    if (tree_kind > SYN_TREE_FROZEN) return fail(SYN_ERR_INVALID_ARGUMENT, "bad tree_kind %u", tree_kind);
     int rc = validate_cfg(cfg, e);
     if (rc) return rc;
+    if (tree_kind == SYN_TREE_FROZEN && (rc = validate_frozen_cfg(cfg->mcts))) return rc;
     // reject positions the reference's MCTS is never built on: finished games, malformed boards
     for (uint32_t i = 0; i < n && !is_device_ptr(my_bb) && !is_device_ptr(op_bb); ++i) {
         uint64_t my = my_bb[i], op = op_bb[i];
@@ -498,7 +551,18 @@ int syn_engine_search(syn_engine* e, const syn_rollout_cfg* cfg, uint32_t tree_k
     CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_ALL * sizeof(unsigned long long), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->error.p, 0, sizeof(int), e->stream));
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
-    rc = launch_selfplay(e, kp);
+    if (tree_kind == SYN_TREE_FROZEN) { // thread per root (match.cuh), the same player on every root
+        mtc::MParams mp;
+        std::memset(&mp, 0, sizeof(mp));
+        for (int k = 0; k < 2; ++k) {
+            mp.players[k].tree_kind = SYN_TREE_FROZEN; mp.players[k].leaf_eval_kind = cfg->leaf_eval_kind;
+            mp.players[k].num_explores = cfg->num_explores; mp.players[k].action_selection = cfg->action_selection;
+            mp.players[k].mcts = cfg->mcts;
+        }
+        rc = launch_match(e, kp, mp);
+    } else {
+        rc = launch_selfplay(e, kp);
+    }
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -512,6 +576,61 @@ int syn_engine_search(syn_engine* e, const syn_rollout_cfg* cfg, uint32_t tree_k
     if ((rc = deliver(e, root_solution, e->s_rsol.p, n))) return rc;
     if ((rc = deliver(e, best_action, e->s_best.p, n))) return rc;
     if ((rc = deliver(e, num_nodes, e->s_nodes.p, (size_t)n * 4))) return rc;
+    return read_stats(e, stats, ms);
+}
+
+int syn_engine_match(syn_engine* e, const syn_player_cfg players[2], const uint64_t* seeds, const uint32_t* explores, uint32_t n,
+                     float* result, uint8_t* n_moves, uint8_t* moves, uint32_t* tree_nodes, float* child_visits, syn_stats* stats) {
+    if (!e || !players || !seeds) return fail(SYN_ERR_INVALID_ARGUMENT, "engine, players and seeds must not be NULL");
+    if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is in flight");
+    if (n == 0) return fail(SYN_ERR_INVALID_ARGUMENT, "n_matches must be > 0");
+    int rc;
+    for (int k = 0; k < 2; ++k)
+        if ((rc = validate_player(players[k], e, k))) return rc;
+    if (explores && !is_device_ptr(explores))
+        for (size_t i = 0; i < 2 * (size_t)n; ++i)
+            if (explores[i] > e->max_explores)
+                return fail(SYN_ERR_CAPACITY, "explores[%zu][%zu] = %u exceeds the engine's max_explores %u", i / 2, i % 2, explores[i], e->max_explores);
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->h2d = 0; e->d2h = 0; e->launches = 0;
+    size_t rows = (size_t)n * 63;
+    CUDA_TRY(e->pos_seed.reserve(n)); CUDA_TRY(e->row_visits.reserve(rows * 9)); CUDA_TRY(e->row_action.reserve(rows));
+    CUDA_TRY(e->row_nodes.reserve(rows)); CUDA_TRY(e->s_q.reserve(n)); CUDA_TRY(e->s_rsol.reserve(n));
+    if (explores) CUDA_TRY(e->s_nodes.reserve(2 * (size_t)n));
+    CUDA_TRY(cudaMemcpyAsync(e->pos_seed.p, seeds, (size_t)n * 8, cudaMemcpyDefault, e->stream));
+    e->h2d += (uint64_t)n * 8;
+    if (explores) {
+        CUDA_TRY(cudaMemcpyAsync(e->s_nodes.p, explores, (size_t)n * 8, cudaMemcpyDefault, e->stream));
+        e->h2d += (uint64_t)n * 8;
+    }
+    CUDA_TRY(cudaMemsetAsync(e->row_action.p, 0, rows, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->row_nodes.p, 0, rows * 4, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->row_visits.p, 0, rows * 36, e->stream));
+    syn_rollout_cfg dummy;
+    std::memset(&dummy, 0, sizeof(dummy));
+    KParams kp;
+    fill_common(e, kp, &dummy);
+    kp.num_games = n; kp.search_mode = 0; kp.pos_seed = e->pos_seed.p;
+    kp.row_visits = e->row_visits.p; kp.row_action = e->row_action.p; kp.row_nodes = e->row_nodes.p;
+    mtc::MParams mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.players[0] = players[0]; mp.players[1] = players[1];
+    mp.explores = explores ? e->s_nodes.p : nullptr;
+    mp.result = e->s_q.p; mp.n_moves = e->s_rsol.p;
+    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_ALL * sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->error.p, 0, sizeof(int), e->stream));
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    if ((rc = launch_match(e, kp, mp))) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    if ((rc = check_device_error(e))) return rc;
+    if ((rc = deliver(e, result, e->s_q.p, (size_t)n * 4))) return rc;
+    if ((rc = deliver(e, n_moves, e->s_rsol.p, n))) return rc;
+    if ((rc = deliver(e, moves, e->row_action.p, rows))) return rc;
+    if ((rc = deliver(e, tree_nodes, e->row_nodes.p, rows * 4))) return rc;
+    if ((rc = deliver(e, child_visits, e->row_visits.p, rows * 36))) return rc;
     return read_stats(e, stats, ms);
 }
 

@@ -37,7 +37,7 @@ enum Counter {
     DBG_T_ADVANCE = CNT_N, DBG_T_TEAMWAIT, DBG_T_MLP, DBG_T_FINISH, DBG_ROUNDS, DBG_LEAVES, DBG_T_TOTAL, CNT_ALL
 };
 
-enum DeviceError { DERR_NONE = 0, DERR_ARENA_OVERFLOW = 1, DERR_DEPTH_OVERFLOW = 2, DERR_BAD_WEIGHTS = 3 };
+enum DeviceError { DERR_NONE = 0, DERR_ARENA_OVERFLOW = 1, DERR_DEPTH_OVERFLOW = 2, DERR_BAD_WEIGHTS = 3, DERR_NO_BEST_ACTION = 4 };
 
 // ------------------------------------------------------------------ lane groups
 template <int GL>

@@ -137,6 +137,27 @@ class Engine:
                                             C.byref(stats)))
         return out, stats.as_dict()
 
+    # ---- evaluation matches (replaces the game loops of evaluator.rs:129-228)
+    def match(self, players, seeds, explores=None, trace: bool = True):
+        """players: two `Player`s, players[0] moves first.  seeds[i] seeds match i's RolloutPolicy stream.
+        explores: optional int array [n][2] overriding the players' num_explores per match.
+        Returns (dict(result, n_moves, moves[, tree_nodes, child_visits]), stats)."""
+        sd = np.ascontiguousarray(seeds, dtype=np.uint64).reshape(-1)
+        n = sd.size
+        pc = (L.SynPlayerCfg * 2)(players[0].to_c(), players[1].to_c())
+        ex = None
+        if explores is not None:
+            ex = np.ascontiguousarray(explores, dtype=np.uint32).reshape(n, 2)
+        out = dict(result=np.zeros(n, np.float32), n_moves=np.zeros(n, np.uint8), moves=np.zeros((n, L.MAX_TURNS), np.uint8))
+        if trace:
+            out["tree_nodes"] = np.zeros((n, L.MAX_TURNS), np.uint32)
+            out["child_visits"] = np.zeros((n, L.MAX_TURNS, 9), np.float32)
+        stats = L.SynStats()
+        L.check(self._lib.syn_engine_match(self._h, pc, _ptr(sd), _ptr(ex), n, _ptr(out["result"]), _ptr(out["n_moves"]),
+                                           _ptr(out["moves"]), _ptr(out.get("tree_nodes")), _ptr(out.get("child_visits")),
+                                           C.byref(stats)))
+        return out, stats.as_dict()
+
     # ---- Policy::eval for Connect4Net on a batch
     def eval(self, my_bb, op_bb):
         my = np.ascontiguousarray(my_bb, dtype=np.uint64).reshape(-1)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Regenerates tests/golden/oracle_search.json and oracle_gather.npz FROM THE ORACLE.
+"""Regenerates tests/golden/oracle_search.json, oracle_match.json and oracle_gather.npz FROM THE ORACLE.
 
     python tests/golden/make_golden.py
 
@@ -62,6 +62,12 @@ def main():
     with open(G.SEARCH_JSON, "w") as f:
         json.dump({"_about": "oracle outputs; generator tests/golden/make_golden.py; see tests/golden_fixtures.py", "cases": cases}, f,
                   separators=(",", ":"))
+    mcases = []
+    for k0, k1, seed, ex in G.MATCH_CASES:
+        out, _ = orc.match((G.match_player(k0, ex[0]), G.match_player(k1, ex[1])), seed, ex)
+        mcases.append(dict(players=[k0, k1], seed=seed, explores=list(ex), out=G.match_case_outputs(out)))
+    with open(G.MATCH_JSON, "w") as f:
+        json.dump({"_about": "oracle outputs (orc_match); generator tests/golden/make_golden.py", "cases": mcases}, f, separators=(",", ":"))
     arrays = {}
     for case in G.GATHER_CASES:
         name, _, _, _, _, first, games, seed = case

@@ -3,6 +3,8 @@
   oracle_search.json   one tree per case: position (move list), config name, explores, seed,
                        tree kind -> child visits, child solutions, root_q bits, root solution,
                        best action, nodes.len()
+  oracle_match.json    evaluation matches (evaluator.rs:163-228): players, seed, explores per side ->
+                       result, moves, per-move nodes.len() and root child visit counts
   oracle_gather.npz    whole self-play games: experience rows (ReplayBuffer layout) + per-row trace
 
 Both are OUTPUTS OF THE ORACLE (tests/golden/make_golden.py is the generating script; the Rust
@@ -21,6 +23,7 @@ from synthesis_b200 import _lib as L
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SEARCH_JSON = os.path.join(GOLD, "oracle_search.json")
 GATHER_NPZ = os.path.join(GOLD, "oracle_gather.npz")
+MATCH_JSON = os.path.join(GOLD, "oracle_match.json")
 
 
 def named_cfg(name: str, explores: int) -> "s.RolloutConfig":
@@ -122,3 +125,43 @@ def check_gather_fixture(gather_fn):
             want = z[f"{name}.{k}"]
             assert v.shape == want.shape, f"gather fixture {name}: {k} shape {v.shape} != {want.shape}"
             assert v.tobytes() == want.tobytes(), f"gather fixture {name}: {k} differs"
+
+
+# ---------------------------------------------------------------- evaluation matches (rollout leaves only: no network involved)
+def match_player(kind: str, explores: int):
+    import synthesis_b200.evaluator as ev
+    if kind == "frozen_rollout":  # the evaluator's baseline (main.rs:72-82)
+        return ev.Player(L.TREE_FROZEN, L.LEAF_ROLLOUT, explores, s.study_connect4_rollout_mcts_cfg(), s.ActionSelection.Q)
+    if kind == "mcts_rollout":  # MCTS::exploit with RolloutPolicy (mcts.rs:111-121)
+        return ev.Player(L.TREE_MCTS, L.LEAF_ROLLOUT, explores, s.study_connect4_mcts_cfg(), s.ActionSelection.NumVisits)
+    raise KeyError(kind)
+
+
+MATCH_CASES = (
+    # first player kind, second player kind, seed, explores (first, second)
+    ("frozen_rollout", "frozen_rollout", 0, (100, 200)),
+    ("frozen_rollout", "frozen_rollout", 1, (400, 100)),
+    ("frozen_rollout", "frozen_rollout", 2, (800, 800)),
+    ("mcts_rollout", "frozen_rollout", 3, (150, 300)),
+    ("frozen_rollout", "mcts_rollout", 4, (300, 150)),
+    ("mcts_rollout", "mcts_rollout", 5, (64, 64)),
+)
+
+
+def match_case_outputs(out):
+    n = int(out["n_moves"])
+    return dict(result=float(out["result"]), moves=[int(x) for x in out["moves"][:n]],
+                tree_nodes=[int(x) for x in out["tree_nodes"][:n]],
+                child_visits=[[int(v) for v in row] for row in out["child_visits"][:n]])
+
+
+def check_match_fixture(match_fn):
+    """match_fn(players, seed, explores2) -> dict(result, n_moves, moves[63], tree_nodes[63], child_visits[63][9]) for ONE match."""
+    with open(MATCH_JSON) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) == len(MATCH_CASES)
+    for want, (k0, k1, seed, ex) in zip(cases, MATCH_CASES):
+        got = match_case_outputs(match_fn((match_player(k0, ex[0]), match_player(k1, ex[1])), seed, ex))
+        for k, v in want["out"].items():
+            assert got[k] == v, f"match fixture {k0} vs {k1} seed={seed} explores={ex}: {k} differs"
+    return len(cases)

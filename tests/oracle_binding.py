@@ -37,6 +37,8 @@ class Oracle:
                                  C.c_int, C.c_uint32, C.POINTER(L.SynExperience), C.POINTER(L.SynStats), C.c_void_p, C.c_void_p, C.c_void_p]
         l.orc_gather_reference.argtypes = [C.POINTER(L.SynRolloutCfg), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                            C.POINTER(L.SynExperience), C.POINTER(L.SynStats), C.c_void_p, C.c_void_p]
+        l.orc_match.argtypes = [C.POINTER(L.SynPlayerCfg), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32] + \
+                               [C.c_void_p] * 5 + [C.POINTER(L.SynStats)]
         l.orc_mlp_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         l.orc_c4_play.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8
         l.orc_c4_won.argtypes = [C.c_uint64]
@@ -107,6 +109,20 @@ class Oracle:
                                  C.cast(C.byref(nn), C.c_void_p), C.byref(st))
         assert rc == 0, rc
         return dict(child_visits=cv, child_solution=cs, root_q=rq, root_solution=rs.value, best_action=ba.value, num_nodes=nn.value), st.as_dict()
+
+    def match(self, players, seed, explores2=None, weights=None, callback=None, flags=0):
+        """One evaluation match (evaluator.rs:129-228); players = two objects with .to_c() -> SynPlayerCfg."""
+        pc = (L.SynPlayerCfg * 2)(players[0].to_c(), players[1].to_c())
+        res, nm = C.c_float(), C.c_uint8()
+        moves, nodes, cv = np.zeros(63, np.uint8), np.zeros(63, np.uint32), np.zeros((63, 9), np.float32)
+        ex = None if explores2 is None else np.ascontiguousarray(explores2, np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        cb = EVAL_FN(callback) if callback else None
+        st = L.SynStats()
+        rc = self.lib.orc_match(pc, int(seed), _p(ex), _p(w), C.cast(cb, C.c_void_p) if cb else None, None, flags,
+                                C.cast(C.byref(res), C.c_void_p), C.cast(C.byref(nm), C.c_void_p), _p(moves), _p(nodes), _p(cv), C.byref(st))
+        assert rc == 0, rc
+        return dict(result=res.value, n_moves=nm.value, moves=moves, tree_nodes=nodes, child_visits=cv), st.as_dict()
 
     def gather(self, ccfg, seed, first_game, num_games, weights=None, callback=None, threads=1, flags=0, trace=True):
         rows = 63 * num_games

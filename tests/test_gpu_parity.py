@@ -366,7 +366,7 @@ def test_engine_matches_committed_search_fixtures(engine):
         out, _ = engine.search(cfg, kind, [g.my_bb], [g.op_bb], [seed], tree_kind=tree_kind)
         return {k: v[0] for k, v in out.items()}
 
-    assert G.check_search_fixture(run, kinds=(L.TREE_MCTS,)) >= 90
+    assert G.check_search_fixture(run) >= 90
 
 
 def test_engine_matches_committed_gather_fixtures(engine):
@@ -377,3 +377,129 @@ def test_engine_matches_committed_gather_fixtures(engine):
         return a, t
 
     G.check_gather_fixture(run)
+
+
+# ---------------------------------------------------------------- configs[4]: FrozenMCTS and evaluation matches
+@pytest.mark.parametrize("explores", [1, 50, 800])
+def test_frozen_search_rollout_bit_exact(engine, oracle, explores):
+    """FrozenMCTS (evaluator.rs:299-534) with the evaluator's rollout-baseline config (main.rs:74-82)."""
+    rng = np.random.default_rng(100 + explores)
+    games = [s.Connect4.new()] + random_positions(rng, 39)
+    for ms in ([4, 4, 3, 3], [4, 3, 4, 3, 4, 3]):
+        g = s.Connect4.new()
+        for m in ms:
+            g.step(m)
+        games.append(g)
+    cfg = s.study_connect4_rollout_cfg(num_explores=explores, mcts_cfg=s.study_connect4_rollout_mcts_cfg())
+    cfg.action = s.ActionSelection.Q
+    seeds = np.arange(len(games), dtype=np.uint64) * 5 + 2
+    out, stats = engine.search(cfg, L.LEAF_ROLLOUT, [g.my_bb for g in games], [g.op_bb for g in games], seeds, tree_kind=L.TREE_FROZEN)
+    ccfg = cfg.to_c(L.LEAF_ROLLOUT)
+    tot = dict(explores=0, nodes=0, select_levels=0, children_scanned=0, expansions=0, leaf_evals=0, rollout_plies=0, backprop_levels=0)
+    for i, g in enumerate(games):
+        ref, st = oracle.search(ccfg, g.my_bb, g.op_bb, int(seeds[i]), tree_kind=L.TREE_FROZEN)
+        for k in tot:
+            tot[k] += st[k]
+        assert np.array_equal(out["child_visits"][i], ref["child_visits"]), (i, out["child_visits"][i], ref["child_visits"])
+        assert np.array_equal(out["child_solution"][i], ref["child_solution"]), i
+        assert np.array_equal(out["root_q"][i].view(np.uint32), ref["root_q"].view(np.uint32)), i
+        assert int(out["root_solution"][i]) == ref["root_solution"], i
+        assert int(out["best_action"][i]) == ref["best_action"], i
+        assert int(out["num_nodes"][i]) == ref["num_nodes"], i
+    for k in tot:
+        assert stats[k] == tot[k], (k, stats[k], tot[k])
+
+
+def test_frozen_search_nn_bit_exact_given_gpu_leaf_outputs(engine, oracle):
+    net = s.Connect4Net.new(4)
+    engine.set_weights(net.blob())
+    rng = np.random.default_rng(17)
+    games = [s.Connect4.new()] + random_positions(rng, 5, max_plies=30)
+    m = s.study_connect4_rollout_mcts_cfg()
+    m.fpu = s.Fpu.Const(1.0)
+    cfg = s.study_connect4_rollout_cfg(num_explores=150, mcts_cfg=m)
+    out, _ = engine.search(cfg, L.LEAF_NN, [g.my_bb for g in games], [g.op_bb for g in games], np.zeros(len(games), np.uint64),
+                           tree_kind=L.TREE_FROZEN)
+    ccfg = cfg.to_c(L.LEAF_NN)
+    cb = _gpu_leaf_callback(engine)
+    for i, g in enumerate(games):
+        ref, _ = oracle.search(ccfg, g.my_bb, g.op_bb, 0, tree_kind=L.TREE_FROZEN, callback=cb)
+        assert np.array_equal(out["child_visits"][i], ref["child_visits"]), (i, out["child_visits"][i], ref["child_visits"])
+        assert np.array_equal(out["root_q"][i].view(np.uint32), ref["root_q"].view(np.uint32)), i
+        assert int(out["best_action"][i]) == ref["best_action"], i
+        assert int(out["num_nodes"][i]) == ref["num_nodes"], i
+
+
+def _assert_match_equal(out, i, ref, what):
+    n = int(ref["n_moves"])
+    assert int(out["n_moves"][i]) == n, (what, i, int(out["n_moves"][i]), n)
+    assert list(out["moves"][i][:n]) == list(ref["moves"][:n]), (what, i)
+    assert float(out["result"][i]) == ref["result"], (what, i)
+    assert np.array_equal(out["tree_nodes"][i][:n], ref["tree_nodes"][:n]), (what, i)
+    assert np.array_equal(out["child_visits"][i][:n], ref["child_visits"][:n]), (what, i)
+
+
+def test_match_rollout_mcts_vs_mcts_bit_exact(engine, oracle):
+    """mcts_vs_mcts (evaluator.rs:200-228): both sides rollout FrozenMCTS on ONE shared stream, explores per side."""
+    import synthesis_b200.evaluator as ev
+    ro = ev.Player(L.TREE_FROZEN, L.LEAF_ROLLOUT, 400, s.study_connect4_rollout_mcts_cfg(), s.ActionSelection.Q)
+    seeds = np.arange(12, dtype=np.uint64)
+    ex = np.array([[100, 200], [200, 100], [400, 50], [50, 400]] * 3, np.uint32)
+    out, st = engine.match((ro, ro), seeds, ex)
+    tot = 0
+    for i in range(len(seeds)):
+        ref, rst = oracle.match((ro, ro), int(seeds[i]), ex[i])
+        _assert_match_equal(out, i, ref, "mcts_vs_mcts")
+        tot += rst["explores"]
+    assert st["explores"] == tot and st["games"] == len(seeds)
+
+
+def test_match_nn_mcts_vs_rollout_frozen_bit_exact(engine, oracle):
+    """eval_against_rollout_mcts (evaluator.rs:163-198), both colours: NN MCTS::exploit (PUCT c=3, Fpu 1.0,
+    NumVisits) against rollout FrozenMCTS::exploit (UCT c=2, Fpu inf, Q); the oracle is fed the GPU's
+    leaf outputs so every move's visit counts must be identical."""
+    import synthesis_b200.evaluator as ev
+    net = s.Connect4Net.new(6)
+    engine.set_weights(net.blob())
+    nn = ev.Player(L.TREE_MCTS, L.LEAF_NN, 120, s.study_connect4_mcts_cfg(), s.ActionSelection.NumVisits)
+    ro = ev.Player(L.TREE_FROZEN, L.LEAF_ROLLOUT, 300, s.study_connect4_rollout_mcts_cfg(), s.ActionSelection.Q)
+    cb = _gpu_leaf_callback(engine)
+    for players, what in (((nn, ro), "nn first"), ((ro, nn), "rollout first")):
+        seeds = np.arange(4, dtype=np.uint64) + 7
+        out, st = engine.match(players, seeds)
+        for i in range(len(seeds)):
+            ref, _ = oracle.match(players, int(seeds[i]), callback=cb)
+            _assert_match_equal(out, i, ref, what)
+
+
+def test_evaluator_sweep_and_pgn(engine):
+    """configs[4] through the host mirror of evaluator.rs:65-82: results are +-1/0 and the PGN text is the reference's."""
+    import io
+    import synthesis_b200.evaluator as ev
+    cfg = s.EvaluationConfig(policy_num_explores=100, policy_action=s.ActionSelection.NumVisits, policy_mcts_cfg=s.study_connect4_mcts_cfg(),
+                             rollout_action=s.ActionSelection.Q, rollout_num_explores=[100, 200, 400], rollout_mcts_cfg=s.study_connect4_rollout_mcts_cfg(),
+                             num_games_against_rollout=2)
+    pgn = io.StringIO()
+    rec = ev.evaluate_against_rollout_sweep(engine, cfg, s.Connect4Net.new(0), "model_0.ot", pgn)
+    assert len(rec) == 12 and all(r in (1.0, 0.0, -1.0) for _, _, r in rec)
+    lines = pgn.getvalue().splitlines()
+    assert lines[0] == '[White "model_0.ot"]' and lines[1] == '[Black "VanillaMCTS100"]' and lines[2].startswith('[Result "')
+    assert lines[4] == '[White "VanillaMCTS100"]' and lines[5] == '[Black "model_0.ot"]'
+
+
+def test_match_rejects_what_the_reference_panics_on(engine):
+    import synthesis_b200.evaluator as ev
+    bad = ev.Player(L.TREE_FROZEN, L.LEAF_ROLLOUT, 10, s.study_connect4_mcts_cfg(), s.ActionSelection.Q)  # PUCT in FrozenMCTS
+    with pytest.raises(L.EngineError) as e:
+        engine.match((bad, bad), [0])
+    assert e.value.code == L.SYN_ERR_UNSUPPORTED
+
+
+def test_engine_matches_committed_match_fixtures(engine):
+    import golden_fixtures as G
+
+    def run(players, seed, ex):
+        out, _ = engine.match(players, [seed], [list(ex)])
+        return {k: v[0] for k, v in out.items()}
+
+    assert G.check_match_fixture(run) == len(G.MATCH_CASES)
