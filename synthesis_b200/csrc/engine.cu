@@ -16,6 +16,7 @@
 
 #include "selfplay.cuh"
 #include "match.cuh"
+#include "tpg2.cuh"
 
 using namespace eng;
 
@@ -63,6 +64,9 @@ struct syn_engine {
     uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
     int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
     int tpg_teams = 8;     // teams of 128 threads per CTA in thread-per-game mode (8 teams share 4 MLP slots)
+    bool tpg_prof = false; // SYN_TPG_PROF=1: the instantiation with per-warp phase clocks
+    int tpg_version = 2;   // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
+    DevBuf<uint32_t> slot_state;
     DevBuf<uint4> nodes; // 2 x uint4 = one 32-byte record per tree node
     DevBuf<float> weights;
     DevBuf<uint8_t> weight_image; // mlptc layout (fp16 weights + fp32 biases)
@@ -126,6 +130,16 @@ static int validate_cfg(const syn_rollout_cfg* cfg, const syn_engine* e) {
 template <int TEAMS, int SLOTS>
 static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>);
+    if (e->tpg_version == 2 && e->tpg_prof) { // with per-warp phase clocks (syn_engine_debug_counters)
+        CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2_kernel<TEAMS, SLOTS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        selfplay_nn_tpg2_kernel<TEAMS, SLOTS, true><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+        return SYN_OK;
+    }
+    if (e->tpg_version == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2_kernel<TEAMS, SLOTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        selfplay_nn_tpg2_kernel<TEAMS, SLOTS, false><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+        return SYN_OK;
+    }
     CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg_kernel<TEAMS, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     selfplay_nn_tpg_kernel<TEAMS, SLOTS><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
     return SYN_OK;
@@ -204,6 +218,7 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.arena_nodes = e->arena_nodes;
     kp.nodes = e->nodes.p;
     kp.next_game = e->next_game.p;
+    kp.slot_state = e->slot_state.p;
     kp.counters = e->counters.p;
     kp.error = e->error.p;
     kp.weights = e->weights.p;
@@ -324,6 +339,10 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     const char* glenv = std::getenv("SYN_GROUP_LANES");
     e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : ((glenv && std::atoi(glenv) == 32) ? 32 : 1);
     const char* tenv = std::getenv("SYN_TPG_TEAMS");
+    const char* venv = std::getenv("SYN_TPG_V");
+    if (venv && std::atoi(venv) == 1) e->tpg_version = 1;
+    const char* penv = std::getenv("SYN_TPG_PROF");
+    e->tpg_prof = penv && std::atoi(penv) == 1;
     if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
     // round the in-flight game count up to whole CTAs of every kernel
     uint32_t unit = 1024;
@@ -336,7 +355,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     size_t total = (size_t)e->max_games * e->arena_nodes;
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
-        (ce = e->nodes.reserve(2 * total)) != cudaSuccess ||
+        (ce = e->nodes.reserve(2 * total)) != cudaSuccess || (ce = e->slot_state.reserve((size_t)e->max_games * 8)) != cudaSuccess ||
         (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->weight_image.reserve(mlptc::IMG_BYTES)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
         (ce = e->counters.reserve(CNT_ALL)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
         int rc = fail(SYN_ERR_CUDA, "engine allocation failed (%zu arena nodes = %.1f MiB): %s", total,
@@ -352,7 +371,7 @@ void syn_engine_destroy(syn_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->nodes.release(); e->weights.release(); e->weight_image.release(); e->next_game.release(); e->counters.release(); e->error.release();
+    e->nodes.release(); e->slot_state.release(); e->weights.release(); e->weight_image.release(); e->next_game.release(); e->counters.release(); e->error.release();
     e->row_my.release(); e->row_op.release(); e->row_off.release(); e->row_pi.release(); e->row_v.release(); e->row_visits.release();
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();

@@ -30,6 +30,7 @@ struct KParams {
     uint32_t arena_nodes;
     uint4* nodes; // tree arenas: arena_nodes 32-byte records per game slot (tree.cuh)
     unsigned int* next_game;
+    uint32_t* slot_state; // tpg2.cuh: 8 words of cold per-game state per arena slot
     // experience rows, [num_games][63]
     uint64_t* row_my;
     uint64_t* row_op;

@@ -1,0 +1,564 @@
+// tpg2.cuh — thread-per-game MCTS, round-synchronous form: ONE explore per thread per round.
+//
+// Replaces synthesis/src/mcts.rs:29-489 and synthesis/src/alpha_zero.rs:229-338 of the
+// reference, one THREAD per game, like tpg.cuh (same algorithm, same f32 operation order, same
+// results bit for bit).  What differs is the schedule, shaped by what ncu showed on tpg.cuh
+// (profiles/r1d_*): 12 of 32 lanes active per instruction, 6.3 % of all instructions register
+// spills whose local-memory sectors out-numbered the node loads, and a quarter of all stall samples
+// at the team barrier waiting for threads that ran a second descent.
+//
+//  * a round is exactly: [cold tree/game bookkeeping] -> descend -> (team forward) -> finish.
+//    An explore that ends on a proven node does NOT loop into another descent: it simply has no
+//    leaf in this round's tile, so all lanes of a warp walk the same code once per round.
+//  * backprop happens at ONE place for every kind of explore (leaf, proven node, auto-extended
+//    terminal), after the forward, so the lanes of a warp run it together.
+//  * per-thread state that is only touched once per move (game index, ply, stream positions)
+//    lives in a 32-byte slot record in global memory, and the statistics counters are summed per
+//    warp (redux) into shared memory — the hot loop keeps ~12 registers of state instead of ~35.
+//  * the root record is loaded once per round and serves both the explore_n stop test
+//    (mcts.rs:139-147) and the first level of selection.
+//
+// Node record (32 bytes = one sector), words: 0 num_visits | 1..3 outcome sums L,D,W |
+// 4 action_prob | 5 parent | 6 first_child | 7 num_children | solution<<8 | action<<16.
+#pragma once
+#include "mlp_team.cuh"
+#include "selfplay.cuh"
+
+namespace tp2 {
+
+using namespace eng;
+
+struct Rec {
+    float vis, o0, o1, o2;
+    uint32_t prior, parent, fc, pk;
+};
+
+__device__ __forceinline__ Rec load_rec(const uint4* nodes, uint32_t i) { // LDG.E.256: one sector, one request
+    Rec r;
+    unsigned long long q0, q1, q2, q3;
+    asm volatile("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(nodes + 2 * (size_t)i) : "memory");
+    r.vis = __uint_as_float((uint32_t)q0); r.o0 = __uint_as_float((uint32_t)(q0 >> 32));
+    r.o1 = __uint_as_float((uint32_t)q1); r.o2 = __uint_as_float((uint32_t)(q1 >> 32));
+    r.prior = (uint32_t)q2; r.parent = (uint32_t)(q2 >> 32); r.fc = (uint32_t)q3; r.pk = (uint32_t)(q3 >> 32);
+    return r;
+}
+__device__ __forceinline__ void store_rec(uint4* nodes, uint32_t i, float vis, float o0, float o1, float o2, uint32_t prior,
+                                          uint32_t parent, uint32_t fc, uint32_t pk) { // STG.E.256
+    unsigned long long q0 = (unsigned long long)__float_as_uint(vis) | ((unsigned long long)__float_as_uint(o0) << 32);
+    unsigned long long q1 = (unsigned long long)__float_as_uint(o1) | ((unsigned long long)__float_as_uint(o2) << 32);
+    unsigned long long q2 = (unsigned long long)prior | ((unsigned long long)parent << 32);
+    unsigned long long q3 = (unsigned long long)fc | ((unsigned long long)pk << 32);
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(nodes + 2 * (size_t)i), "l"(q0), "l"(q1), "l"(q2), "l"(q3) : "memory");
+}
+__device__ __forceinline__ void store_stat(uint4* nodes, uint32_t i, float vis, float o0, float o1, float o2) {
+    nodes[2 * (size_t)i] = make_uint4(__float_as_uint(vis), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2));
+}
+__device__ __forceinline__ uint32_t* meta_words(uint4* nodes, uint32_t i) { return reinterpret_cast<uint32_t*>(nodes + 2 * (size_t)i + 1); }
+enum { MW_PRIOR = 0, MW_PARENT = 1, MW_FC = 2, MW_PK = 3 };
+
+// Cold per-slot state (global memory, 32 bytes per game in flight).
+enum { SS_GI = 0, SS_PLY = 1, SS_APOS = 2, SS_FPU_POS = 3, SS_NOISE_POS = 4, SS_WORDS = 8 };
+
+enum { K_NONE = 0, K_LEAF = 1, K_TERMINAL = 2 };
+
+struct Game { // hot per-thread state
+    uint4* nodes;
+    uint32_t nn;      // nodes.len()
+    uint64_t my, op;  // root position of the current tree
+    uint32_t e_done;
+    int phase;        // PH_*
+    bool is_init;     // the explore in flight is the construction visit of MCTS::with_capacity
+};
+
+struct Pend { // what descend leaves for finish
+    uint32_t kind;  // K_*
+    uint32_t id;    // K_LEAF: the expanded node; K_TERMINAL: the proven node
+    uint32_t fc;    // K_LEAF: first child; K_TERMINAL: the node's packed solution
+    uint32_t lc;    // K_LEAF: legal mask | csol2 << 9 (2 bits per column: 0 none / 1 Lose(0) / 2 Draw(0))
+};
+
+struct RoundCnt { uint32_t levels, scanned, expansions, created, bp_levels, leaf_evals, explores; };
+
+__device__ __forceinline__ uint64_t stream_seed(const KParams& p, uint32_t gi, unsigned k) {
+    if (!p.search_mode) return syn_stream_seed(p.seed, p.first_game + gi, k);
+    uint64_t s = p.pos_seed[gi];
+    if (k == SYN_STREAM_ROLLOUT) return s;
+    if (k == SYN_STREAM_ACTION) return 0ull;
+    return (s ^ (1ull << 63)) + (k == SYN_STREAM_FPU ? 1ull : 0ull);
+}
+
+__device__ __noinline__ float fpu_normal_draw(const KParams& p, uint32_t* ss) { // mcts.rs:354 with the shipped closure; cold
+    rng::Stream st;
+    st.init(stream_seed(p, ss[SS_GI], SYN_STREAM_FPU), ss[SS_FPU_POS]);
+    float v = syn_normal(st, p.cfg.mcts.fpu_a, p.cfg.mcts.fpu_b);
+    ss[SS_FPU_POS] = (uint32_t)st.pos;
+    return v;
+}
+
+// One explore from the (already loaded) root up to the point where the policy is needed
+// (mcts.rs:310-325, 327-372, 374-406).  `my`/`op` enter as the root position and leave as the
+// leaf's.  Returns an error code (0 = none).
+// CW = child records requested per memory round trip (3 at 64 registers per thread, 9 at 128).
+template <int CW>
+__device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, const Rec& root, uint64_t& my, uint64_t& op, Pend& pd,
+                                       RoundCnt& rc) {
+    const syn_mcts_cfg& cfg = p.cfg.mcts;
+    uint4* nodes = g.nodes;
+    uint32_t cur = 0u;
+    float cvis = root.vis, cop0 = root.o0, cop2 = root.o2;
+    uint32_t cfc = root.fc, cpk = root.pk;
+    uint32_t depth = 0;
+    const bool puct = cfg.exploration_kind == SYN_EXPLORATION_POLYNOMIAL_UCT;
+    for (;;) {
+        uint32_t sol = (cpk >> 8) & 0xffu, nch = cpk & 0xffu;
+        if (sol) { pd.kind = K_TERMINAL; pd.id = cur; pd.fc = sol; return 0; } // mcts.rs:314-316
+        if (nch == 0u) break;
+        // ---- select_best_child (mcts.rs:327-372): first strict maximum in child order
+        const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
+        uint32_t b = 0u, bfc = 0u, bpk = 0u;
+        float bval = 0.0f, bvis = 0.0f, bo0 = 0.0f, bo2 = 0.0f;
+        for (uint32_t k0 = 0; k0 < nch; k0 += (uint32_t)CW) { // CW records per memory round trip
+            Rec chs[CW];
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)CW; ++j) chs[j] = load_rec(nodes, cfc + min(k0 + j, nch - 1u));
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)CW; ++j) {
+                const uint32_t k = k0 + j;
+                const Rec& ch = chs[j];
+                uint32_t csol = (ch.pk >> 8) & 0xffu, cn = ch.pk & 0xffu;
+                float q;
+                if (csol) {
+                    uint32_t kd = sol_kind(csol);
+                    q = cfg.select_solved_nodes ? (kd == SYN_KIND_WIN ? -1.0f : (kd == SYN_KIND_LOSE ? 1.0f : 0.0f)) : __uint_as_float(0xff800000u);
+                } else if (cn == 0u) {
+                    q = cfg.fpu_kind == SYN_FPU_CONST ? cfg.fpu_a
+                        : (cfg.fpu_kind == SYN_FPU_PARENT_Q ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : (k < nch ? fpu_normal_draw(p, ss) : 0.0f));
+                } else {
+                    q = -__fdiv_rn(__fsub_rn(ch.o2, ch.o0), ch.vis);
+                }
+                float u = puct ? __fdiv_rn(__fmul_rn(__fmul_rn(cfg.c, __uint_as_float(ch.prior)), pterm), __fadd_rn(1.0f, ch.vis))
+                               : __fdiv_rn(pterm, __fsqrt_rn(ch.vis));
+                float value = __fadd_rn(q, u);
+                if (k < nch && (k == 0u || value > bval)) { b = k; bval = value; bvis = ch.vis; bo0 = ch.o0; bo2 = ch.o2; bfc = ch.fc; bpk = ch.pk; }
+            }
+        }
+        rc.levels += 1u;
+        rc.scanned += nch;
+        cur = cfc + b;
+        cvis = bvis; cop0 = bo0; cop2 = bo2; cfc = bfc; cpk = bpk;
+        c4::step(my, op, (int)((cpk >> 16) & 0xffu));
+        if (++depth >= 64u) return DERR_DEPTH_OVERFLOW;
+    }
+    // ---- visit (mcts.rs:374-406): number the children of `cur`; auto-extend through only-children
+    for (;;) {
+        uint64_t occ = my | op;
+        uint32_t lm = 0u, cs2 = 0u, n = 0u;
+#pragma unroll
+        for (int col = 0; col < 9; ++col) {
+            uint32_t colbits = (uint32_t)((occ >> (7 * col)) & 0x7full);
+            if (colbits != 0x7fu) {
+                uint64_t bit = 1ull << (7 * col + __popc(colbits));
+                uint32_t s2 = c4::won(my | bit) ? 1u : (((occ | bit) == c4::ALL) ? 2u : 0u);
+                lm |= 1u << col;
+                cs2 |= s2 << (2 * col);
+                ++n;
+            }
+        }
+        uint32_t fc = g.nn;
+        if (fc + n > p.arena_nodes) return DERR_ARENA_OVERFLOW;
+        uint32_t* mw = meta_words(nodes, cur); // mark_visited (mcts.rs:399-400): fc and pk are adjacent words
+        *reinterpret_cast<uint2*>(mw + MW_FC) = make_uint2(fc, (cpk & 0xffffff00u) | n);
+        g.nn = fc + n;
+        rc.expansions += 1u;
+        rc.created += n;
+        if (cfg.auto_extend && n == 1u) { // mcts.rs:404-405: recurse into the only child, no policy call
+            int only = __ffs(lm) - 1;
+            uint32_t s2 = (cs2 >> (2 * only)) & 3u;
+            uint32_t osol = s2 == 1u ? c4::SOL_LOSE0 : (s2 == 2u ? c4::SOL_DRAW0 : 0u);
+            cpk = (osol << 8) | ((uint32_t)only << 16);
+            store_rec(nodes, fc, 0.f, 0.f, 0.f, 0.f, __float_as_uint(1.0f), cur, 0u, cpk);
+            c4::step(my, op, only);
+            cur = fc;
+            if (++depth >= 64u) return DERR_DEPTH_OVERFLOW;
+            if (osol) { pd.kind = K_TERMINAL; pd.id = cur; pd.fc = osol; return 0; } // mcts.rs:377-379
+            continue;
+        }
+        pd.kind = K_LEAF; pd.id = cur; pd.fc = fc; pd.lc = lm | (cs2 << 9);
+        return 0;
+    }
+}
+
+// mcts.rs:429-488 from node `id` up to the root, following parent links like the reference.
+__device__ __forceinline__ uint32_t backprop(const syn_mcts_cfg& cfg, uint4* nodes, uint32_t id, float v0, float v1, float v2, bool solved) {
+    uint32_t levels = 0;
+    for (;;) {
+        Rec n = load_rec(nodes, id);
+        ++levels;
+        if (cfg.solve && solved) {
+            uint32_t nch = n.pk & 0xffu, nsol = (n.pk >> 8) & 0xffu;
+            uint32_t bk = sol_key(nsol);
+            bool all_solved = true;
+            for (uint32_t k = 0; k < nch; ++k) {
+                uint32_t csol = (meta_words(nodes, n.fc + k)[MW_PK] >> 8) & 0xffu;
+                uint32_t rs = csol ? sol_reversed(csol) : 0u;
+                all_solved = all_solved && rs != 0u;
+                uint32_t key = sol_key(rs);
+                bk = key > bk ? key : bk;
+            }
+            uint32_t best = sol_from_key(bk);
+            bool mark = false;
+            int slot = 0;
+            if (sol_kind(best) == SYN_KIND_WIN) { mark = true; slot = 2; }
+            else if (best != 0u && all_solved) { mark = true; slot = sol_kind(best) == SYN_KIND_DRAW ? 1 : 0; }
+            if (mark) {
+                if (cfg.correct_values_on_solve) {
+                    v0 = -n.o0; v1 = -n.o1; v2 = -n.o2;
+                    float add = n.vis + 1.0f;
+                    if (slot == 2) v2 = v2 + add;
+                    else if (slot == 1) v1 = v1 + add;
+                    else v0 = v0 + add;
+                }
+                meta_words(nodes, id)[MW_PK] = (n.pk & 0xffff00ffu) | (best << 8);
+            } else {
+                solved = false;
+            }
+        }
+        store_stat(nodes, id, n.vis + 1.0f, n.o0 + v0, n.o1 + v1, n.o2 + v2);
+        if (id == 0u) break;
+        float tmp = v0; v0 = v2; v2 = tmp;
+        id = n.parent;
+    }
+    return levels;
+}
+
+// The rest of visit() after Policy::eval (mcts.rs:384-397 child records, 409-423 stable softmax over
+// the legal children in child order).  logits[col] is used for legal columns only.
+__device__ __forceinline__ void write_children(uint4* nodes, const Pend& pd, const float (&logits)[9]) {
+    const uint32_t legal = pd.lc & 0x1ffu, csol2 = pd.lc >> 9;
+    float e[9];
+    float total = 0.0f;
+    float mx = __uint_as_float(0xff800000u);
+#pragma unroll
+    for (int col = 0; col < 9; ++col)
+        if ((legal >> col) & 1u) mx = fmaxf(mx, logits[col]);
+#pragma unroll
+    for (int col = 0; col < 9; ++col) {
+        e[col] = 0.0f;
+        if ((legal >> col) & 1u) {
+            e[col] = syn_expf(__fsub_rn(logits[col], mx));
+            total = __fadd_rn(total, e[col]);
+        }
+    }
+    uint32_t rank = 0u;
+#pragma unroll
+    for (int col = 0; col < 9; ++col) {
+        if ((legal >> col) & 1u) {
+            uint32_t s2 = (csol2 >> (2 * col)) & 3u;
+            uint32_t csol = s2 == 1u ? c4::SOL_LOSE0 : (s2 == 2u ? c4::SOL_DRAW0 : 0u);
+            store_rec(nodes, pd.fc + rank, 0.f, 0.f, 0.f, 0.f, __float_as_uint(__fdiv_rn(e[col], total)), pd.id, 0u,
+                      (csol << 8) | ((uint32_t)col << 16));
+            ++rank;
+        }
+    }
+}
+
+// mcts.rs:229-269 after the construction visit.  Cold path.
+__device__ __noinline__ void add_root_noise(const KParams& p, uint32_t* ss, uint4* nodes) {
+    const syn_mcts_cfg& cfg = p.cfg.mcts;
+    if (cfg.noise_kind == SYN_NOISE_NONE) return;
+    Rec r = load_rec(nodes, 0u);
+    uint32_t nch = r.pk & 0xffu;
+    if (nch < 2u) return;
+    float w = cfg.noise_weight;
+    float vals[9];
+    for (int k = 0; k < 9; ++k) vals[k] = __fdiv_rn(1.0f, (float)nch);
+    if (cfg.noise_kind == SYN_NOISE_DIRICHLET) {
+        rng::Stream st;
+        st.init(stream_seed(p, ss[SS_GI], SYN_STREAM_NOISE), ss[SS_NOISE_POS]);
+        syn_dirichlet(st, cfg.noise_alpha, (int)nch, vals);
+        ss[SS_NOISE_POS] = (uint32_t)st.pos;
+    }
+    for (uint32_t k = 0; k < nch; ++k) {
+        uint32_t* mw = meta_words(nodes, r.fc + k);
+        float pr = __uint_as_float(mw[MW_PRIOR]);
+        pr = __fadd_rn(__fmul_rn(pr, __fsub_rn(1.0f, w)), __fmul_rn(w, vals[k]));
+        mw[MW_PRIOR] = __float_as_uint(pr);
+    }
+}
+
+struct RootOut {
+    float pi[9], visits[9];
+    uint32_t child_sol[9];
+    float q0, q1, q2;
+    uint32_t root_sol, legal;
+    int best_action;
+};
+
+// What the driver reads from a finished tree (mcts.rs:174-225, 273-306), by COLUMN.
+__device__ __noinline__ void read_root(const uint4* nodes, uint32_t action_selection, RootOut& r) {
+    Rec root = load_rec(nodes, 0u);
+    uint32_t nch = root.pk & 0xffu, rsol = (root.pk >> 8) & 0xffu;
+    for (int k = 0; k < 9; ++k) { r.pi[k] = 0.0f; r.visits[k] = 0.0f; r.child_sol[k] = 0u; }
+    float total = 0.0f, b0 = 0.0f, b1 = 0.0f;
+    int best = 0;
+    uint32_t legal = 0u;
+    for (uint32_t k = 0; k < nch; ++k) {
+        Rec ch = load_rec(nodes, root.fc + k);
+        uint32_t csol = (ch.pk >> 8) & 0xffu, act = (ch.pk >> 16) & 0xffu;
+        float v; // target_policy (mcts.rs:174-211)
+        if (root.vis == 1.0f) v = sol_kind(rsol) == SYN_KIND_WIN ? (sol_kind(csol) == SYN_KIND_LOSE ? 1.0f : 0.0f) : 1.0f;
+        else v = ch.vis;
+        total = __fadd_rn(total, v);
+        float k0, k1; // best_action (mcts.rs:273-294): key (k0, k1), strict lexicographic >, first child incumbent
+        uint32_t kind = sol_kind(csol);
+        if (kind == SYN_KIND_WIN) { k0 = 0.0f; k1 = (float)(csol & 63u); }
+        else if (kind == 0u) { k0 = 1.0f; k1 = action_selection == SYN_ACTION_Q ? -__fdiv_rn(__fsub_rn(ch.o2, ch.o0), ch.vis) : ch.vis; }
+        else if (kind == SYN_KIND_DRAW) { k0 = 2.0f; k1 = -(float)(csol & 63u); }
+        else { k0 = 3.0f; k1 = -(float)(csol & 63u); }
+        if (k == 0u || k0 > b0 || (k0 == b0 && k1 > b1)) { b0 = k0; b1 = k1; best = (int)act; }
+        legal |= 1u << act;
+#pragma unroll
+        for (int col = 0; col < 9; ++col)
+            if ((int)act == col) { r.pi[col] = v; r.visits[col] = ch.vis; r.child_sol[col] = csol; }
+    }
+#pragma unroll
+    for (int col = 0; col < 9; ++col) r.pi[col] = __fdiv_rn(r.pi[col], total); // illegal columns: 0 / total = 0
+    r.legal = legal;
+    r.best_action = best;
+    r.root_sol = rsol;
+    if (rsol) { // target_q (mcts.rs:213-225)
+        int idx = sol_index(rsol);
+        r.q0 = idx == 0 ? 1.0f : 0.0f; r.q1 = idx == 1 ? 1.0f : 0.0f; r.q2 = idx == 2 ? 1.0f : 0.0f;
+    } else {
+        r.q0 = __fdiv_rn(root.o0, root.vis); r.q1 = __fdiv_rn(root.o1, root.vis); r.q2 = __fdiv_rn(root.o2, root.vis);
+    }
+}
+
+// Ends the current move (alpha_zero.rs:246-267, 270-338): emit the row (or the search outputs),
+// choose and play the action, and either start the next tree or close the game.  Cold path (once
+// per tree).  Returns a device error code.
+__device__ __noinline__ int end_of_move(const KParams& p, uint32_t* ss, Game& g) {
+    const syn_rollout_cfg& cfg = p.cfg;
+    RootOut r;
+    read_root(g.nodes, cfg.action_selection, r);
+    const uint32_t gi = ss[SS_GI], ply = ss[SS_PLY];
+    atomicAdd(p.counters + CNT_NODES, (unsigned long long)g.nn);
+    atomicAdd(p.counters + CNT_EXPLORES, (unsigned long long)g.e_done);
+    if (p.search_mode) {
+        size_t i = gi;
+        for (int k = 0; k < 9; ++k) {
+            if (p.s_child_visits) p.s_child_visits[i * 9 + k] = r.visits[k];
+            if (p.s_child_sol) p.s_child_sol[i * 9 + k] = (uint8_t)r.child_sol[k];
+        }
+        if (p.s_root_q) { p.s_root_q[i * 3 + 0] = r.q0; p.s_root_q[i * 3 + 1] = r.q1; p.s_root_q[i * 3 + 2] = r.q2; }
+        if (p.s_root_sol) p.s_root_sol[i] = (uint8_t)r.root_sol;
+        if (p.s_best) p.s_best[i] = (uint8_t)r.best_action;
+        if (p.s_nodes) p.s_nodes[i] = g.nn;
+        atomicAdd(p.counters + CNT_GAMES, 1ull);
+        g.phase = PH_NEED_GAME;
+        return 0;
+    }
+    int err = 0;
+    size_t row = (size_t)gi * 63 + ply;
+    for (int k = 0; k < 9; ++k) {
+        p.row_pi[row * 9 + k] = r.pi[k];
+        p.row_visits[row * 9 + k] = r.visits[k];
+    }
+    // sample_action (alpha_zero.rs:270-294)
+    int action = r.best_action;
+    uint32_t best_sol = 0u;
+    for (int k = 0; k < 9; ++k)
+        if (k == action) best_sol = r.child_sol[k];
+    int mode = -1;
+    if (ply < cfg.random_actions_until) mode = 0;
+    else if (ply < cfg.sample_actions_until && (best_sol == 0u || !cfg.stop_games_when_solved)) mode = 1;
+    if (mode >= 0) {
+        uint32_t ap = ss[SS_APOS];
+        int a = sample_action_slow(stream_seed(p, gi, SYN_STREAM_ACTION), &ap, mode, r.legal, r.pi);
+        ss[SS_APOS] = ap;
+        if (a < 0 || a > 8) { err = DERR_BAD_WEIGHTS; a = r.best_action; }
+        action = a;
+    }
+    uint32_t solution = 0u; // mcts.solution(&action)
+    for (int k = 0; k < 9; ++k)
+        if (k == action) solution = r.child_sol[k];
+    p.row_my[row] = g.my;
+    p.row_op[row] = g.op;
+    p.row_v[row * 3 + 0] = r.q0; p.row_v[row * 3 + 1] = r.q1; p.row_v[row * 3 + 2] = r.q2; // StateInfo::q
+    p.row_action[row] = (uint8_t)action;
+    p.row_nodes[row] = g.nn;
+    uint32_t over = c4::step(g.my, g.op, action); // Outcome::from(reward(player)) when the game ended
+    const uint32_t n = ply + 1u;
+    ss[SS_PLY] = n;
+    uint32_t fin = over ? over : (cfg.stop_games_when_solved ? solution : 0u);
+    if (fin == 0u) { g.phase = PH_NEW_TREE; return err; }
+    // fill_state_info + store_rewards (alpha_zero.rs:296-338)
+    uint32_t okind = 4u - sol_kind(fin); // solution.reversed(): the last mover's outcome
+    for (uint32_t k = 0; k < n; ++k) {
+        uint32_t kind = okind;
+        if (((n - 1u - k) & 1u) && kind != SYN_KIND_DRAW) kind = 4u - kind;
+        size_t rr = (size_t)gi * 63 + k;
+        float q0 = p.row_v[rr * 3 + 0], q1 = p.row_v[rr * 3 + 1], q2 = p.row_v[rr * 3 + 2];
+        float z0 = kind == SYN_KIND_LOSE ? 1.0f : 0.0f, z1 = kind == SYN_KIND_DRAW ? 1.0f : 0.0f, z2 = kind == SYN_KIND_WIN ? 1.0f : 0.0f;
+        float v0, v1, v2;
+        if (cfg.value_target_kind == SYN_VALUE_Q) { v0 = q0; v1 = q1; v2 = q2; }
+        else if (cfg.value_target_kind == SYN_VALUE_Z) { v0 = z0; v1 = z1; v2 = z2; }
+        else if (cfg.value_target_kind == SYN_VALUE_QZ_AVERAGE) {
+            float pp = cfg.vt_a, om = __fsub_rn(1.0f, pp);
+            v0 = __fadd_rn(__fmul_rn(q0, pp), __fmul_rn(z0, om));
+            v1 = __fadd_rn(__fmul_rn(q1, pp), __fmul_rn(z1, om));
+            v2 = __fadd_rn(__fmul_rn(q2, pp), __fmul_rn(z2, om));
+        } else {
+            float tt = __fdiv_rn((float)(k + 1u), (float)n);
+            float pp = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, tt), cfg.vt_a), __fmul_rn(tt, cfg.vt_b));
+            float om = __fsub_rn(1.0f, pp);
+            v0 = __fadd_rn(__fmul_rn(q0, om), __fmul_rn(z0, pp));
+            v1 = __fadd_rn(__fmul_rn(q1, om), __fmul_rn(z1, pp));
+            v2 = __fadd_rn(__fmul_rn(q2, om), __fmul_rn(z2, pp));
+        }
+        p.row_v[rr * 3 + 0] = v0; p.row_v[rr * 3 + 1] = v1; p.row_v[rr * 3 + 2] = v2;
+    }
+    p.game_len[gi] = n;
+    atomicAdd(p.counters + CNT_ROWS, (unsigned long long)n);
+    atomicAdd(p.counters + CNT_GAMES, 1ull);
+    g.phase = PH_NEED_GAME;
+    return err;
+}
+
+// Takes the next game (or search root) from the global counter.  Cold path.
+__device__ __noinline__ void next_game(const KParams& p, uint32_t* ss, Game& g) {
+    uint32_t gi = atomicAdd(p.next_game, 1u);
+    if (gi >= p.num_games || *(volatile int*)p.error != 0) { g.phase = PH_DONE; return; }
+    ss[SS_GI] = gi; ss[SS_PLY] = 0u; ss[SS_APOS] = 0u; ss[SS_FPU_POS] = 0u; ss[SS_NOISE_POS] = 0u;
+    if (p.search_mode) { g.my = p.pos_my[gi]; g.op = p.pos_op[gi]; }
+    else { g.my = 0; g.op = 0; }
+    g.phase = PH_NEW_TREE;
+}
+
+} // namespace tp2
+
+namespace eng {
+
+// One persistent CTA per SM, TEAMS teams of 128 threads sharing SLOTS MLP slots (mlp_team.cuh).
+template <int TEAMS, int SLOTS, bool PROF>
+__global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ unsigned long long s_cnt[CNT_ALL];
+    mlpteam::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS, SLOTS>*>(smem_raw);
+    if (threadIdx.x < CNT_ALL) s_cnt[threadIdx.x] = 0ull;
+    mlpteam::setup<TEAMS, SLOTS>(ms, p.weight_image);
+    const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
+    const size_t slot_id = (size_t)blockIdx.x * (128 * TEAMS) + threadIdx.x;
+    uint32_t* const ss = p.slot_state + tp2::SS_WORDS * slot_id;
+    const syn_mcts_cfg& cfg = p.cfg.mcts;
+    tp2::Game g;
+    g.nodes = p.nodes + 2 * slot_id * p.arena_nodes;
+    g.nn = 1u; g.my = g.op = 0ull; g.e_done = 0u; g.phase = PH_NEED_GAME; g.is_init = false;
+    // per-warp phase clocks (syn_engine_debug_counters): only in the PROF instantiation, they cost 14 registers
+    long long t_adv = 0, t_wait = 0, t_mlp = 0, t_fin = 0, t_start = PROF ? clock64() : 0;
+    uint32_t rounds = 0, leaves = 0;
+    for (;;) {
+        long long t0 = PROF ? clock64() : 0;
+        // ---- cold bookkeeping, then at most one descent
+        tp2::Pend pd;
+        pd.kind = tp2::K_NONE; pd.id = 0u; pd.fc = 0u; pd.lc = 0u;
+        tp2::RoundCnt rc = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        uint64_t my = 0, op = 0;
+        int err = 0;
+        if (g.phase != PH_DONE) {
+            tp2::Rec root;
+            bool go = true;
+            if (g.phase == PH_EXPLORE) { // explore_n (mcts.rs:139-147): stop at num_explores or once the root is solved
+                root = tp2::load_rec(g.nodes, 0u);
+                if (g.e_done >= p.cfg.num_explores || ((root.pk >> 8) & 0xffu) != 0u) {
+                    err = tp2::end_of_move(p, ss, g);
+                    go = false; // the next tree starts next round
+                }
+            } else {
+                if (g.phase == PH_NEED_GAME) tp2::next_game(p, ss, g);
+                if (g.phase == PH_NEW_TREE) { // MCTS::with_capacity (mcts.rs:123-137): fresh arena, root only
+                    root.vis = root.o0 = root.o1 = root.o2 = 0.0f;
+                    root.prior = root.parent = root.fc = root.pk = 0u;
+                    tp2::store_rec(g.nodes, 0u, 0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u);
+                    g.nn = 1u; g.e_done = 0u; g.is_init = true;
+                    atomicAdd(&s_cnt[CNT_TREES], 1ull);
+                    g.phase = PH_EXPLORE;
+                } else {
+                    go = false; // PH_DONE
+                }
+            }
+            if (go && !err) {
+                my = g.my; op = g.op;
+                err = tp2::descend<(TEAMS >= 8 ? 3 : 5)>(p, ss, g, root, my, op, pd, rc);
+            }
+            if (err) { atomicCAS(p.error, 0, err); g.phase = PH_DONE; pd.kind = tp2::K_NONE; }
+        }
+        __syncwarp();
+        long long t1 = PROF ? clock64() : 0;
+        const bool need = pd.kind == tp2::K_LEAF;
+        if (PROF) leaves += (uint32_t)__popc(__ballot_sync(0xffffffffu, need));
+        if (!mlpteam::team_any(team, g.phase != PH_DONE)) break; // no thread of this team has a game left
+        uint32_t mma_phase;
+        const int slot = mlpteam::acquire_slot<TEAMS, SLOTS>(ms, team, r, mma_phase);
+        long long t2 = PROF ? clock64() : 0;
+        if (need) mlpteam::write_features(ms.a[slot], ms.col_lut, r, my, op);
+        float y[12];
+        mlpteam::forward<TEAMS, SLOTS>(ms, team, slot, r, mma_phase, y);
+        mlpteam::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
+        long long t3 = PROF ? clock64() : 0;
+        // ---- finish: child records for leaves, then ONE backprop site for every kind of explore
+        if (pd.kind != tp2::K_NONE) {
+            float v0, v1, v2;
+            bool solved;
+            if (need) {
+                // value.softmax(-1) (study-connect4/src/policies.rs:54-56)
+                float m = fmaxf(y[9], fmaxf(y[10], y[11]));
+                float e0 = syn_expf(__fsub_rn(y[9], m)), e1 = syn_expf(__fsub_rn(y[10], m)), e2 = syn_expf(__fsub_rn(y[11], m));
+                float tot = __fadd_rn(__fadd_rn(e0, e1), e2);
+                float lg[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) lg[k] = y[k];
+                tp2::write_children(g.nodes, pd, lg);
+                v0 = __fdiv_rn(e0, tot); v1 = __fdiv_rn(e1, tot); v2 = __fdiv_rn(e2, tot);
+                solved = (pd.lc >> 9) != 0u;
+                rc.leaf_evals = 1u;
+            } else {
+                int idx = sol_index(pd.fc);
+                v0 = idx == 0 ? 1.0f : 0.0f; v1 = idx == 1 ? 1.0f : 0.0f; v2 = idx == 2 ? 1.0f : 0.0f;
+                solved = true;
+            }
+            rc.bp_levels = tp2::backprop(cfg, g.nodes, pd.id, v0, v1, v2, solved);
+            if (g.is_init) { tp2::add_root_noise(p, ss, g.nodes); g.is_init = false; }
+            else g.e_done += 1u;
+        }
+        __syncwarp();
+        { // statistics: one shared-memory atomic per warp and counter
+            uint32_t a0 = __reduce_add_sync(0xffffffffu, rc.levels), a1 = __reduce_add_sync(0xffffffffu, rc.scanned);
+            uint32_t a2 = __reduce_add_sync(0xffffffffu, rc.expansions), a3 = __reduce_add_sync(0xffffffffu, rc.created);
+            uint32_t a4 = __reduce_add_sync(0xffffffffu, rc.bp_levels), a5 = __reduce_add_sync(0xffffffffu, rc.leaf_evals);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&s_cnt[CNT_SELECT_LEVELS], (unsigned long long)a0); atomicAdd(&s_cnt[CNT_CHILDREN_SCANNED], (unsigned long long)a1);
+                atomicAdd(&s_cnt[CNT_EXPANSIONS], (unsigned long long)a2); atomicAdd(&s_cnt[CNT_CHILDREN_CREATED], (unsigned long long)a3);
+                atomicAdd(&s_cnt[CNT_BACKPROP_LEVELS], (unsigned long long)a4); atomicAdd(&s_cnt[CNT_LEAF_EVALS], (unsigned long long)a5);
+            }
+        }
+        if (PROF) {
+            long long t4 = clock64();
+            t_adv += t1 - t0; t_wait += t2 - t1; t_mlp += t3 - t2; t_fin += t4 - t3; ++rounds;
+        }
+    }
+    if (PROF && (threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt[DBG_T_ADVANCE], (unsigned long long)t_adv);
+        atomicAdd(&s_cnt[DBG_T_TEAMWAIT], (unsigned long long)t_wait);
+        atomicAdd(&s_cnt[DBG_T_MLP], (unsigned long long)t_mlp);
+        atomicAdd(&s_cnt[DBG_T_FINISH], (unsigned long long)t_fin);
+        atomicAdd(&s_cnt[DBG_ROUNDS], (unsigned long long)rounds);
+        atomicAdd(&s_cnt[DBG_LEAVES], (unsigned long long)leaves);
+        atomicAdd(&s_cnt[DBG_T_TOTAL], (unsigned long long)(clock64() - t_start));
+    }
+    mlpteam::teardown<TEAMS, SLOTS>(ms); // ends with a CTA barrier: every warp's counters are in s_cnt
+    __syncthreads();
+    if (threadIdx.x < CNT_ALL && s_cnt[threadIdx.x]) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+} // namespace eng
