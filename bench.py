@@ -79,7 +79,8 @@ def config_dict(args, n_gpus):
         "driver": "random_actions_until=1, sample_actions_until=30, ValueTarget::Q, ActionSelection::NumVisits (main.rs:31-35)",
         "parallelism": "game-sharded x%d (no data-path collective)" % n_gpus,
         "games_in_flight_per_gpu": getattr(args, "in_flight", None),
-        "l2": "inputs larger than L2: the tree arenas of the games in flight (0.23 MB/game at 800 explores) total ~35 GB per GPU vs 126 MB L2; a new seed per step",
+        "l2": "inputs larger than L2: the tree arenas of the games in flight (%.2f MB/game at %d explores) total ~%.0f GB per GPU vs 126 MB L2; a new seed per step"
+              % ((9 * (args.explores + 1) + 8) * 32 / 1e6, args.explores, (getattr(args, "in_flight", 0) or 0) * (9 * (args.explores + 1) + 8) * 32 / 1e9),
     }
 
 
@@ -375,7 +376,7 @@ def run_ours(args):
         kernel_s = dev_ns * 1e-9 / max(1, args.steps)  # rank 0's kernel, average launch duration
         achieved = bpe * (acc["explores"] / max(1, args.steps)) / kernel_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args),
-                    "kernel": ("selfplay_nn_tpg_kernel" if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn" else "selfplay_rollout_kernel",
+                    "kernel": (("selfplay_nn_tpg2_kernel" if os.environ.get("SYN_TPG_V", "2") != "1" else "selfplay_nn_tpg_kernel") if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn" else "selfplay_rollout_kernel",
                     "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": acc["explores"] / max(1, args.steps),
                     "launch_ms": 1e3 * kernel_s, "peak_source": peak_src, **shape,
                     "note": "latency-bound pointer chasing over per-game trees; see DESIGN.md"}

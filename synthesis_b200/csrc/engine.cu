@@ -17,6 +17,7 @@
 #include "selfplay.cuh"
 #include "match.cuh"
 #include "tpg2.cuh"
+#include "tpg3.cuh"
 
 using namespace eng;
 
@@ -65,7 +66,8 @@ struct syn_engine {
     int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
     int tpg_teams = 8;     // teams of 128 threads per CTA in thread-per-game mode (8 teams share 4 MLP slots)
     bool tpg_prof = false; // SYN_TPG_PROF=1: the instantiation with per-warp phase clocks
-    int tpg_version = 2;   // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
+    int tpg_cw = 0;        // child records per memory round trip in tpg3 (0 = the default of the team count)
+    int tpg_version = 3;   // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
     DevBuf<uint32_t> slot_state;
     DevBuf<uint4> nodes; // 2 x uint4 = one 32-byte record per tree node
     DevBuf<float> weights;
@@ -127,6 +129,28 @@ static int validate_cfg(const syn_rollout_cfg* cfg, const syn_engine* e) {
     return SYN_OK;
 }
 
+template <int TEAMS, int SLOTS, int CW, bool PROF>
+static int launch_tpg3(syn_engine* e, KParams& kp, uint32_t blocks) {
+    size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>);
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg3_kernel<TEAMS, SLOTS, CW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_nn_tpg3_kernel<TEAMS, SLOTS, CW, PROF><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+    return SYN_OK;
+}
+
+// the split-record kernel (tpg3.cuh): instantiations by team count and children per round trip
+static int launch_tpg3_any(syn_engine* e, KParams& kp, uint32_t blocks) {
+    const int t = e->tpg_teams, cw = e->tpg_cw;
+    if (e->tpg_prof) {
+        if (t == 8) return launch_tpg3<8, 4, 5, true>(e, kp, blocks);
+        if (t == 4) return launch_tpg3<4, 4, 9, true>(e, kp, blocks);
+    }
+    if (t == 8) return cw == 3 ? launch_tpg3<8, 4, 3, false>(e, kp, blocks) : launch_tpg3<8, 4, 5, false>(e, kp, blocks);
+    if (t == 6) return launch_tpg3<6, 4, 5, false>(e, kp, blocks);
+    if (t == 4) return cw == 5 ? launch_tpg3<4, 4, 5, false>(e, kp, blocks) : launch_tpg3<4, 4, 9, false>(e, kp, blocks);
+    if (t == 2) return launch_tpg3<2, 2, 9, false>(e, kp, blocks);
+    return launch_tpg3<1, 1, 9, false>(e, kp, blocks);
+}
+
 template <int TEAMS, int SLOTS>
 static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>);
@@ -164,7 +188,9 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         if (blocks > max_blocks) blocks = max_blocks;
         if (blocks == 0) blocks = 1;
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-        int rc = e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
+        int rc = e->tpg_version == 3 ? launch_tpg3_any(e, kp, blocks)
+                 : e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
+                 : e->tpg_teams == 6 ? launch_tpg<6, 4>(e, kp, blocks)
                  : e->tpg_teams == 4 ? launch_tpg<4, 4>(e, kp, blocks)
                  : e->tpg_teams == 2 ? launch_tpg<2, 2>(e, kp, blocks) : launch_tpg<1, 1>(e, kp, blocks);
         if (rc) return rc;
@@ -331,6 +357,9 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
         return fail(SYN_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cuda_device, prop.major, prop.minor);
     if (max_games_in_flight == 0 || max_explores == 0) return fail(SYN_ERR_INVALID_ARGUMENT, "max_games_in_flight and max_explores must be > 0");
     CUDA_TRY(cudaSetDevice(cuda_device));
+    // node records are 16/32-byte random accesses: ask L2 to fetch single sectors from DRAM instead of pairs
+    const char* fenv = std::getenv("SYN_L2_FETCH");
+    if (fenv && std::atoi(fenv) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(fenv));
     syn_engine* e = new syn_engine();
     e->device = cuda_device;
     e->sm_count = prop.multiProcessorCount;
@@ -340,10 +369,12 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : ((glenv && std::atoi(glenv) == 32) ? 32 : 1);
     const char* tenv = std::getenv("SYN_TPG_TEAMS");
     const char* venv = std::getenv("SYN_TPG_V");
-    if (venv && std::atoi(venv) == 1) e->tpg_version = 1;
+    if (venv && (std::atoi(venv) == 1 || std::atoi(venv) == 2)) e->tpg_version = std::atoi(venv);
+    const char* cenv = std::getenv("SYN_TPG_CW");
+    if (cenv) e->tpg_cw = std::atoi(cenv);
     const char* penv = std::getenv("SYN_TPG_PROF");
     e->tpg_prof = penv && std::atoi(penv) == 1;
-    if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
+    if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 6 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
     // round the in-flight game count up to whole CTAs of every kernel
     uint32_t unit = 1024;
     e->max_games = ((max_games_in_flight + unit - 1) / unit) * unit;
@@ -355,7 +386,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     size_t total = (size_t)e->max_games * e->arena_nodes;
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
-        (ce = e->nodes.reserve(2 * total)) != cudaSuccess || (ce = e->slot_state.reserve((size_t)e->max_games * 8)) != cudaSuccess ||
+        (ce = e->nodes.reserve(2 * total)) != cudaSuccess || (ce = e->slot_state.reserve((size_t)e->max_games * tp2::SS_WORDS)) != cudaSuccess ||
         (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->weight_image.reserve(mlptc::IMG_BYTES)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
         (ce = e->counters.reserve(CNT_ALL)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
         int rc = fail(SYN_ERR_CUDA, "engine allocation failed (%zu arena nodes = %.1f MiB): %s", total,

@@ -56,18 +56,19 @@ __device__ __forceinline__ void store_stat(uint4* nodes, uint32_t i, float vis, 
 __device__ __forceinline__ uint32_t* meta_words(uint4* nodes, uint32_t i) { return reinterpret_cast<uint32_t*>(nodes + 2 * (size_t)i + 1); }
 enum { MW_PRIOR = 0, MW_PARENT = 1, MW_FC = 2, MW_PK = 3 };
 
-// Cold per-slot state (global memory, 32 bytes per game in flight).
-enum { SS_GI = 0, SS_PLY = 1, SS_APOS = 2, SS_FPU_POS = 3, SS_NOISE_POS = 4, SS_WORDS = 8 };
+// Per-slot state outside the registers (global memory, 64 bytes per game in flight): the root position of
+// the current tree (read once per round next to the root record) and what only changes once per move.
+enum { SS_MY = 0, SS_OP = 2, SS_GI = 4, SS_PLY = 5, SS_APOS = 6, SS_FPU_POS = 7, SS_NOISE_POS = 8, SS_WORDS = 16 };
 
-enum { K_NONE = 0, K_LEAF = 1, K_TERMINAL = 2 };
+enum { K_NONE = 0, K_LEAF = 1, K_TERMINAL = 2, K_INIT = 4 /* flag: the construction visit of MCTS::with_capacity */ };
 
-struct Game { // hot per-thread state
+// Hot per-thread state is three registers: the arena pointer is recomputed from the slot index, and
+// the explore count of the current tree IS the root's visit count (every backprop ends at the root:
+// num_visits(root) == 1 + explores done, mcts.rs:133, 480), so neither needs a register.
+struct Game {
     uint4* nodes;
-    uint32_t nn;      // nodes.len()
-    uint64_t my, op;  // root position of the current tree
-    uint32_t e_done;
-    int phase;        // PH_*
-    bool is_init;     // the explore in flight is the construction visit of MCTS::with_capacity
+    uint32_t nn; // nodes.len()
+    int phase;   // PH_*
 };
 
 struct Pend { // what descend leaves for finish
@@ -99,19 +100,22 @@ __device__ __noinline__ float fpu_normal_draw(const KParams& p, uint32_t* ss) { 
 // (mcts.rs:310-325, 327-372, 374-406).  `my`/`op` enter as the root position and leave as the
 // leaf's.  Returns an error code (0 = none).
 // CW = child records requested per memory round trip (3 at 64 registers per thread, 9 at 128).
-template <int CW>
+// FPU = the configured syn_fpu_kind, a template parameter so that the common Fpu::Const instantiation carries
+// neither the parent's outcome sums (ParentQ) nor a call in its inner loop (Normal).
+template <int CW, int FPU>
 __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, const Rec& root, uint64_t& my, uint64_t& op, Pend& pd,
                                        RoundCnt& rc) {
     const syn_mcts_cfg& cfg = p.cfg.mcts;
     uint4* nodes = g.nodes;
     uint32_t cur = 0u;
-    float cvis = root.vis, cop0 = root.o0, cop2 = root.o2;
+    constexpr bool PQ = FPU == SYN_FPU_PARENT_Q;
+    float cvis = root.vis, cop0 = PQ ? root.o0 : 0.0f, cop2 = PQ ? root.o2 : 0.0f;
     uint32_t cfc = root.fc, cpk = root.pk;
     uint32_t depth = 0;
     const bool puct = cfg.exploration_kind == SYN_EXPLORATION_POLYNOMIAL_UCT;
     for (;;) {
         uint32_t sol = (cpk >> 8) & 0xffu, nch = cpk & 0xffu;
-        if (sol) { pd.kind = K_TERMINAL; pd.id = cur; pd.fc = sol; return 0; } // mcts.rs:314-316
+        if (sol) { rc.levels = depth; pd.kind = K_TERMINAL; pd.id = cur; pd.fc = sol; return 0; } // mcts.rs:314-316
         if (nch == 0u) break;
         // ---- select_best_child (mcts.rs:327-372): first strict maximum in child order
         const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
@@ -131,24 +135,28 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
                     uint32_t kd = sol_kind(csol);
                     q = cfg.select_solved_nodes ? (kd == SYN_KIND_WIN ? -1.0f : (kd == SYN_KIND_LOSE ? 1.0f : 0.0f)) : __uint_as_float(0xff800000u);
                 } else if (cn == 0u) {
-                    q = cfg.fpu_kind == SYN_FPU_CONST ? cfg.fpu_a
-                        : (cfg.fpu_kind == SYN_FPU_PARENT_Q ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : (k < nch ? fpu_normal_draw(p, ss) : 0.0f));
+                    if (PQ) q = __fdiv_rn(__fsub_rn(cop2, cop0), cvis);
+                    else if (FPU == SYN_FPU_CONST) q = cfg.fpu_a;
+                    else q = k < nch ? fpu_normal_draw(p, ss) : 0.0f;
                 } else {
                     q = -__fdiv_rn(__fsub_rn(ch.o2, ch.o0), ch.vis);
                 }
                 float u = puct ? __fdiv_rn(__fmul_rn(__fmul_rn(cfg.c, __uint_as_float(ch.prior)), pterm), __fadd_rn(1.0f, ch.vis))
                                : __fdiv_rn(pterm, __fsqrt_rn(ch.vis));
                 float value = __fadd_rn(q, u);
-                if (k < nch && (k == 0u || value > bval)) { b = k; bval = value; bvis = ch.vis; bo0 = ch.o0; bo2 = ch.o2; bfc = ch.fc; bpk = ch.pk; }
+                if (k < nch && (k == 0u || value > bval)) {
+                    b = k; bval = value; bvis = ch.vis; bfc = ch.fc; bpk = ch.pk;
+                    if (PQ) { bo0 = ch.o0; bo2 = ch.o2; }
+                }
             }
         }
-        rc.levels += 1u;
         rc.scanned += nch;
         cur = cfc + b;
         cvis = bvis; cop0 = bo0; cop2 = bo2; cfc = bfc; cpk = bpk;
         c4::step(my, op, (int)((cpk >> 16) & 0xffu));
         if (++depth >= 64u) return DERR_DEPTH_OVERFLOW;
     }
+    rc.levels = depth; // one select_best_child call per level walked
     // ---- visit (mcts.rs:374-406): number the children of `cur`; auto-extend through only-children
     for (;;) {
         uint64_t occ = my | op;
@@ -336,11 +344,22 @@ __device__ __noinline__ void read_root(const uint4* nodes, uint32_t action_selec
 
 // Ends the current move (alpha_zero.rs:246-267, 270-338): emit the row (or the search outputs),
 // choose and play the action, and either start the next tree or close the game.  Cold path (once
-// per tree).  Returns a device error code.
-__device__ __noinline__ int end_of_move(const KParams& p, uint32_t* ss, Game& g) {
+// per tree).  Cold functions take and return the thread's state BY VALUE: a Game passed by reference
+// to a non-inlined function would pin the whole struct in local memory for the hot loop too.
+// The root position of the tree lives in the slot record (SS_MY, SS_OP).  Returns phase | err << 8.
+__device__ __forceinline__ uint64_t ss_load64(const uint32_t* ss, int w) { return *reinterpret_cast<const uint64_t*>(ss + w); }
+__device__ __forceinline__ void ss_store64(uint32_t* ss, int w, uint64_t v) { *reinterpret_cast<uint64_t*>(ss + w) = v; }
+
+struct ReadRoot2 { // the node layout of this file; tpg3.cuh passes its own reader
+    __device__ __forceinline__ void operator()(const uint4* nodes, uint32_t cap, uint32_t action_selection, RootOut& r) const { read_root(nodes, action_selection, r); }
+};
+
+template <class RR>
+__device__ __noinline__ int end_of_move(const KParams& p, uint32_t* ss, uint4* nodes, uint32_t nn, uint32_t e_done, RR reader) {
     const syn_rollout_cfg& cfg = p.cfg;
+    struct { uint4* nodes; uint32_t nn, e_done; uint64_t my, op; } g = {nodes, nn, e_done, ss_load64(ss, SS_MY), ss_load64(ss, SS_OP)};
     RootOut r;
-    read_root(g.nodes, cfg.action_selection, r);
+    reader(g.nodes, p.arena_nodes, cfg.action_selection, r);
     const uint32_t gi = ss[SS_GI], ply = ss[SS_PLY];
     atomicAdd(p.counters + CNT_NODES, (unsigned long long)g.nn);
     atomicAdd(p.counters + CNT_EXPLORES, (unsigned long long)g.e_done);
@@ -355,8 +374,7 @@ __device__ __noinline__ int end_of_move(const KParams& p, uint32_t* ss, Game& g)
         if (p.s_best) p.s_best[i] = (uint8_t)r.best_action;
         if (p.s_nodes) p.s_nodes[i] = g.nn;
         atomicAdd(p.counters + CNT_GAMES, 1ull);
-        g.phase = PH_NEED_GAME;
-        return 0;
+        return PH_NEED_GAME;
     }
     int err = 0;
     size_t row = (size_t)gi * 63 + ply;
@@ -391,7 +409,9 @@ __device__ __noinline__ int end_of_move(const KParams& p, uint32_t* ss, Game& g)
     const uint32_t n = ply + 1u;
     ss[SS_PLY] = n;
     uint32_t fin = over ? over : (cfg.stop_games_when_solved ? solution : 0u);
-    if (fin == 0u) { g.phase = PH_NEW_TREE; return err; }
+    ss_store64(ss, SS_MY, g.my);
+    ss_store64(ss, SS_OP, g.op);
+    if (fin == 0u) return PH_NEW_TREE | (err << 8);
     // fill_state_info + store_rewards (alpha_zero.rs:296-338)
     uint32_t okind = 4u - sol_kind(fin); // solution.reversed(): the last mover's outcome
     for (uint32_t k = 0; k < n; ++k) {
@@ -421,18 +441,17 @@ __device__ __noinline__ int end_of_move(const KParams& p, uint32_t* ss, Game& g)
     p.game_len[gi] = n;
     atomicAdd(p.counters + CNT_ROWS, (unsigned long long)n);
     atomicAdd(p.counters + CNT_GAMES, 1ull);
-    g.phase = PH_NEED_GAME;
-    return err;
+    return PH_NEED_GAME | (err << 8);
 }
 
 // Takes the next game (or search root) from the global counter.  Cold path.
-__device__ __noinline__ void next_game(const KParams& p, uint32_t* ss, Game& g) {
+__device__ __noinline__ int next_game(const KParams& p, uint32_t* ss) {
     uint32_t gi = atomicAdd(p.next_game, 1u);
-    if (gi >= p.num_games || *(volatile int*)p.error != 0) { g.phase = PH_DONE; return; }
+    if (gi >= p.num_games || *(volatile int*)p.error != 0) return PH_DONE;
     ss[SS_GI] = gi; ss[SS_PLY] = 0u; ss[SS_APOS] = 0u; ss[SS_FPU_POS] = 0u; ss[SS_NOISE_POS] = 0u;
-    if (p.search_mode) { g.my = p.pos_my[gi]; g.op = p.pos_op[gi]; }
-    else { g.my = 0; g.op = 0; }
-    g.phase = PH_NEW_TREE;
+    ss_store64(ss, SS_MY, p.search_mode ? p.pos_my[gi] : 0ull);
+    ss_store64(ss, SS_OP, p.search_mode ? p.pos_op[gi] : 0ull);
+    return PH_NEW_TREE;
 }
 
 } // namespace tp2
@@ -451,9 +470,11 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
     const size_t slot_id = (size_t)blockIdx.x * (128 * TEAMS) + threadIdx.x;
     uint32_t* const ss = p.slot_state + tp2::SS_WORDS * slot_id;
     const syn_mcts_cfg& cfg = p.cfg.mcts;
+    const float stop_vis = (float)(p.cfg.num_explores + 1u); // explore_n is over when the root has 1 + num_explores visits
+    constexpr int CW = TEAMS >= 6 ? 3 : 5;
     tp2::Game g;
     g.nodes = p.nodes + 2 * slot_id * p.arena_nodes;
-    g.nn = 1u; g.my = g.op = 0ull; g.e_done = 0u; g.phase = PH_NEED_GAME; g.is_init = false;
+    g.nn = 1u; g.phase = PH_NEED_GAME;
     // per-warp phase clocks (syn_engine_debug_counters): only in the PROF instantiation, they cost 14 registers
     long long t_adv = 0, t_wait = 0, t_mlp = 0, t_fin = 0, t_start = PROF ? clock64() : 0;
     uint32_t rounds = 0, leaves = 0;
@@ -464,23 +485,26 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
         pd.kind = tp2::K_NONE; pd.id = 0u; pd.fc = 0u; pd.lc = 0u;
         tp2::RoundCnt rc = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
         uint64_t my = 0, op = 0;
-        int err = 0;
         if (g.phase != PH_DONE) {
+            int err = 0;
             tp2::Rec root;
             bool go = true;
             if (g.phase == PH_EXPLORE) { // explore_n (mcts.rs:139-147): stop at num_explores or once the root is solved
                 root = tp2::load_rec(g.nodes, 0u);
-                if (g.e_done >= p.cfg.num_explores || ((root.pk >> 8) & 0xffu) != 0u) {
-                    err = tp2::end_of_move(p, ss, g);
+                my = tp2::ss_load64(ss, tp2::SS_MY); op = tp2::ss_load64(ss, tp2::SS_OP);
+                if (root.vis >= stop_vis || ((root.pk >> 8) & 0xffu) != 0u) {
+                    int pe = tp2::end_of_move(p, ss, g.nodes, g.nn, (uint32_t)root.vis - 1u, tp2::ReadRoot2());
+                    g.phase = pe & 0xff; err = pe >> 8;
                     go = false; // the next tree starts next round
                 }
             } else {
-                if (g.phase == PH_NEED_GAME) tp2::next_game(p, ss, g);
+                if (g.phase == PH_NEED_GAME) g.phase = tp2::next_game(p, ss);
                 if (g.phase == PH_NEW_TREE) { // MCTS::with_capacity (mcts.rs:123-137): fresh arena, root only
                     root.vis = root.o0 = root.o1 = root.o2 = 0.0f;
                     root.prior = root.parent = root.fc = root.pk = 0u;
                     tp2::store_rec(g.nodes, 0u, 0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u);
-                    g.nn = 1u; g.e_done = 0u; g.is_init = true;
+                    my = tp2::ss_load64(ss, tp2::SS_MY); op = tp2::ss_load64(ss, tp2::SS_OP);
+                    g.nn = 1u;
                     atomicAdd(&s_cnt[CNT_TREES], 1ull);
                     g.phase = PH_EXPLORE;
                 } else {
@@ -488,14 +512,26 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
                 }
             }
             if (go && !err) {
-                my = g.my; op = g.op;
-                err = tp2::descend<(TEAMS >= 8 ? 3 : 5)>(p, ss, g, root, my, op, pd, rc);
+                const uint32_t init = root.vis == 0.0f ? (uint32_t)tp2::K_INIT : 0u; // the construction visit (mcts.rs:133)
+                if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST>(p, ss, g, root, my, op, pd, rc);
+                else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q>(p, ss, g, root, my, op, pd, rc);
+                else err = tp2::descend<CW, SYN_FPU_NORMAL>(p, ss, g, root, my, op, pd, rc);
+                pd.kind |= init;
             }
             if (err) { atomicCAS(p.error, 0, err); g.phase = PH_DONE; pd.kind = tp2::K_NONE; }
         }
         __syncwarp();
+        { // statistics of the descent (summed per warp here so that they are not live across the forward)
+            uint32_t a0 = __reduce_add_sync(0xffffffffu, rc.levels), a1 = __reduce_add_sync(0xffffffffu, rc.scanned);
+            uint32_t a2 = __reduce_add_sync(0xffffffffu, rc.expansions), a3 = __reduce_add_sync(0xffffffffu, rc.created);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&s_cnt[CNT_SELECT_LEVELS], (unsigned long long)a0); atomicAdd(&s_cnt[CNT_CHILDREN_SCANNED], (unsigned long long)a1);
+                atomicAdd(&s_cnt[CNT_EXPANSIONS], (unsigned long long)a2); atomicAdd(&s_cnt[CNT_CHILDREN_CREATED], (unsigned long long)a3);
+            }
+            rc.bp_levels = 0u; rc.leaf_evals = 0u;
+        }
         long long t1 = PROF ? clock64() : 0;
-        const bool need = pd.kind == tp2::K_LEAF;
+        const bool need = (pd.kind & tp2::K_LEAF) != 0u;
         if (PROF) leaves += (uint32_t)__popc(__ballot_sync(0xffffffffu, need));
         if (!mlpteam::team_any(team, g.phase != PH_DONE)) break; // no thread of this team has a game left
         uint32_t mma_phase;
@@ -528,17 +564,12 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
                 solved = true;
             }
             rc.bp_levels = tp2::backprop(cfg, g.nodes, pd.id, v0, v1, v2, solved);
-            if (g.is_init) { tp2::add_root_noise(p, ss, g.nodes); g.is_init = false; }
-            else g.e_done += 1u;
+            if (pd.kind & tp2::K_INIT) tp2::add_root_noise(p, ss, g.nodes);
         }
         __syncwarp();
-        { // statistics: one shared-memory atomic per warp and counter
-            uint32_t a0 = __reduce_add_sync(0xffffffffu, rc.levels), a1 = __reduce_add_sync(0xffffffffu, rc.scanned);
-            uint32_t a2 = __reduce_add_sync(0xffffffffu, rc.expansions), a3 = __reduce_add_sync(0xffffffffu, rc.created);
+        { // statistics of the finish: one shared-memory atomic per warp and counter
             uint32_t a4 = __reduce_add_sync(0xffffffffu, rc.bp_levels), a5 = __reduce_add_sync(0xffffffffu, rc.leaf_evals);
             if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&s_cnt[CNT_SELECT_LEVELS], (unsigned long long)a0); atomicAdd(&s_cnt[CNT_CHILDREN_SCANNED], (unsigned long long)a1);
-                atomicAdd(&s_cnt[CNT_EXPANSIONS], (unsigned long long)a2); atomicAdd(&s_cnt[CNT_CHILDREN_CREATED], (unsigned long long)a3);
                 atomicAdd(&s_cnt[CNT_BACKPROP_LEVELS], (unsigned long long)a4); atomicAdd(&s_cnt[CNT_LEAF_EVALS], (unsigned long long)a5);
             }
         }
