@@ -37,7 +37,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--games", type=int, default=0, help="self-play games per GPU per step (default: --games-mult x games in flight)")
-    p.add_argument("--games-mult", type=int, default=3,
+    p.add_argument("--games-mult", type=int, default=6,
                    help="games per step as a multiple of the games one GPU holds in flight (amortises the end-of-step tail)")
     p.add_argument("--explores", type=int, default=800)
     p.add_argument("--leaf", default="nn", choices=["nn", "rollout"])
@@ -51,7 +51,7 @@ def parse_args():
 def size_workload(args):
     """Games one GPU holds in flight and games per step; identical for both arms so their `config` matches."""
     if args.leaf == "nn" and args.group_lanes == 1:
-        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "8"))  # one CTA per SM, teams of 128 games
+        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "4"))  # one CTA per SM, teams of 128 games
     elif args.leaf == "nn":
         in_flight = 148 * (512 // args.group_lanes)
     else:
@@ -376,7 +376,7 @@ def run_ours(args):
         kernel_s = dev_ns * 1e-9 / max(1, args.steps)  # rank 0's kernel, average launch duration
         achieved = bpe * (acc["explores"] / max(1, args.steps)) / kernel_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args),
-                    "kernel": (("selfplay_nn_tpg2_kernel" if os.environ.get("SYN_TPG_V", "2") != "1" else "selfplay_nn_tpg_kernel") if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn" else "selfplay_rollout_kernel",
+                    "kernel": ("selfplay_nn_tpg2_kernel" if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn" else "selfplay_rollout_kernel",
                     "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": acc["explores"] / max(1, args.steps),
                     "launch_ms": 1e3 * kernel_s, "peak_source": peak_src, **shape,
                     "note": "latency-bound pointer chasing over per-game trees; see DESIGN.md"}

@@ -36,7 +36,7 @@ with s.Engine(0, in_flight, explores) as eng:
         out, st = eng.search(cfg, L.LEAF_NN, my, op, seeds)
         d = eng.debug_counters()
         tot = max(1, d["t_total"])
-        tag = "v%s%s" % (os.environ.get("SYN_TPG_V", "2"), "p" if os.environ.get("SYN_TPG_PROF") == "1" else "")
+        tag = "prof" if os.environ.get("SYN_TPG_PROF") == "1" else "    "
         B = (st["select_levels"] * 20 + st["children_scanned"] * 18 + st["children_created"] * 47 + st["backprop_levels"] * 36 + st["leaf_evals"] * 64) / max(1, st["explores"])
         print(tag + " teams %d E %d roots %d: %.1f M explores/s (%.1f ms) | depth %.2f alg B/explore %.0f | advance %.1f%% teamwait %.1f%% mlp %.1f%% finish %.1f%% | cycles/round %.0f"
               % (teams, explores, n, st["explores"] / st["device_ns"] * 1e3, st["device_ns"] / 1e6, st["select_levels"] / max(1, st["explores"]), B,

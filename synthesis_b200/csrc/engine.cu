@@ -17,7 +17,6 @@
 #include "selfplay.cuh"
 #include "match.cuh"
 #include "tpg2.cuh"
-#include "tpg3.cuh"
 
 using namespace eng;
 
@@ -64,10 +63,9 @@ struct syn_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
     int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
-    int tpg_teams = 8;     // teams of 128 threads per CTA in thread-per-game mode (8 teams share 4 MLP slots)
+    int tpg_teams = 4;     // teams of 128 threads per CTA in thread-per-game mode (512 threads, 128 registers each)
     bool tpg_prof = false; // SYN_TPG_PROF=1: the instantiation with per-warp phase clocks
-    int tpg_cw = 0;        // child records per memory round trip in tpg3 (0 = the default of the team count)
-    int tpg_version = 3;   // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
+   // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
     DevBuf<uint32_t> slot_state;
     DevBuf<uint4> nodes; // 2 x uint4 = one 32-byte record per tree node
     DevBuf<float> weights;
@@ -129,43 +127,16 @@ static int validate_cfg(const syn_rollout_cfg* cfg, const syn_engine* e) {
     return SYN_OK;
 }
 
-template <int TEAMS, int SLOTS, int CW, bool PROF>
-static int launch_tpg3(syn_engine* e, KParams& kp, uint32_t blocks) {
-    size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>);
-    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg3_kernel<TEAMS, SLOTS, CW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    selfplay_nn_tpg3_kernel<TEAMS, SLOTS, CW, PROF><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
-    return SYN_OK;
-}
-
-// the split-record kernel (tpg3.cuh): instantiations by team count and children per round trip
-static int launch_tpg3_any(syn_engine* e, KParams& kp, uint32_t blocks) {
-    const int t = e->tpg_teams, cw = e->tpg_cw;
-    if (e->tpg_prof) {
-        if (t == 8) return launch_tpg3<8, 4, 5, true>(e, kp, blocks);
-        if (t == 4) return launch_tpg3<4, 4, 9, true>(e, kp, blocks);
-    }
-    if (t == 8) return cw == 3 ? launch_tpg3<8, 4, 3, false>(e, kp, blocks) : launch_tpg3<8, 4, 5, false>(e, kp, blocks);
-    if (t == 6) return launch_tpg3<6, 4, 5, false>(e, kp, blocks);
-    if (t == 4) return cw == 5 ? launch_tpg3<4, 4, 5, false>(e, kp, blocks) : launch_tpg3<4, 4, 9, false>(e, kp, blocks);
-    if (t == 2) return launch_tpg3<2, 2, 9, false>(e, kp, blocks);
-    return launch_tpg3<1, 1, 9, false>(e, kp, blocks);
-}
-
 template <int TEAMS, int SLOTS>
 static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>);
-    if (e->tpg_version == 2 && e->tpg_prof) { // with per-warp phase clocks (syn_engine_debug_counters)
+    if (e->tpg_prof) { // with per-warp phase clocks (syn_engine_debug_counters)
         CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2_kernel<TEAMS, SLOTS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         selfplay_nn_tpg2_kernel<TEAMS, SLOTS, true><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
         return SYN_OK;
     }
-    if (e->tpg_version == 2) {
-        CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2_kernel<TEAMS, SLOTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        selfplay_nn_tpg2_kernel<TEAMS, SLOTS, false><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
-        return SYN_OK;
-    }
-    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg_kernel<TEAMS, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    selfplay_nn_tpg_kernel<TEAMS, SLOTS><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2_kernel<TEAMS, SLOTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_nn_tpg2_kernel<TEAMS, SLOTS, false><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
     return SYN_OK;
 }
 
@@ -188,8 +159,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         if (blocks > max_blocks) blocks = max_blocks;
         if (blocks == 0) blocks = 1;
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-        int rc = e->tpg_version == 3 ? launch_tpg3_any(e, kp, blocks)
-                 : e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
+        int rc = e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
                  : e->tpg_teams == 6 ? launch_tpg<6, 4>(e, kp, blocks)
                  : e->tpg_teams == 4 ? launch_tpg<4, 4>(e, kp, blocks)
                  : e->tpg_teams == 2 ? launch_tpg<2, 2>(e, kp, blocks) : launch_tpg<1, 1>(e, kp, blocks);
@@ -368,10 +338,6 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     const char* glenv = std::getenv("SYN_GROUP_LANES");
     e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : ((glenv && std::atoi(glenv) == 32) ? 32 : 1);
     const char* tenv = std::getenv("SYN_TPG_TEAMS");
-    const char* venv = std::getenv("SYN_TPG_V");
-    if (venv && (std::atoi(venv) == 1 || std::atoi(venv) == 2)) e->tpg_version = std::atoi(venv);
-    const char* cenv = std::getenv("SYN_TPG_CW");
-    if (cenv) e->tpg_cw = std::atoi(cenv);
     const char* penv = std::getenv("SYN_TPG_PROF");
     e->tpg_prof = penv && std::atoi(penv) == 1;
     if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 6 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);

@@ -10,6 +10,7 @@
 //
 // FrozenMCTS reuses the 32-byte node record of tpg.cuh with word 1 = cum_value (words 2, 3 unused).
 #pragma once
+#include "mlp_team.cuh"
 #include "tpg.cuh"
 
 namespace frz {

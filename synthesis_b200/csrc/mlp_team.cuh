@@ -66,6 +66,13 @@ __device__ __forceinline__ uint32_t cvt_relu_sat_f16x2(float lo, float hi) {
     return d;
 }
 
+// Two IEEE fp32 additions in one instruction (FADD2): each lane of the pair is rounded to nearest
+// exactly like a scalar add, so results are unchanged.
+__device__ __forceinline__ void add2(float a0, float a1, float b0, float b1, float& r0, float& r1) {
+    asm("{\n\t.reg .b64 a, b, r;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 r, a, b;\n\tmov.b64 {%0, %1}, r;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // Game::features (connect4.rs:237-258) of one position, fp16, written as row `r` of the team's A tile
 // in the K-major UMMA layout with layer 0's permuted K axis (mlp_tc.cuh): chunk c = board column c =
 // 7 cells bottom-up + a zero.  +1 mine, -1 theirs, +0.1 the next playable cell, -0.1 any other empty
@@ -203,9 +210,12 @@ __device__ __forceinline__ void forward(Smem<TEAMS, SLOTS>& s, int team, int slo
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float4 b4 = *reinterpret_cast<const float4*>(bias + c16 * 16 + 4 * j);
-                    // bias, then ReLU + saturate to the fp16 range + round + pack in ONE instruction
-                    h[2 * j] = cvt_relu_sat_f16x2(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y);
-                    h[2 * j + 1] = cvt_relu_sat_f16x2(__uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
+                    // bias (two lanes per FADD2), then ReLU + saturate to the fp16 range + round + pack in ONE instruction
+                    float x0, x1, x2, x3;
+                    add2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), b4.x, b4.y, x0, x1);
+                    add2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), b4.z, b4.w, x2, x3);
+                    h[2 * j] = cvt_relu_sat_f16x2(x0, x1);
+                    h[2 * j + 1] = cvt_relu_sat_f16x2(x2, x3);
                 }
                 *reinterpret_cast<uint4*>(a_tile + (2 * c16) * (M_TILE * 16) + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(a_tile + (2 * c16 + 1) * (M_TILE * 16) + r * 16) = make_uint4(h[4], h[5], h[6], h[7]);

@@ -525,74 +525,6 @@ __global__ void __launch_bounds__(THREADS, 1) eval_kernel(const float* __restric
     }
 }
 
-// ------------------------------------------------------------------ NN-mode kernel, thread per game (tpg.cuh + mlp_team.cuh)
-// One persistent CTA per SM, TEAMS teams of 128 threads.  Every thread plays whole games; each round
-// it advances its tree to the next leaf, the team's <= 128 leaves go through ONE Connect4Net forward
-// on the tensor cores (thread r = tile row r), and the thread finishes its explore with the logits
-// it reads back from TMEM.  Teams are independent of each other (named barriers, one mbarrier and
-// 128 TMEM columns each) and share the resident weight image.
-} // namespace eng
-#include "mlp_team.cuh"
-#include "tpg.cuh"
-namespace eng {
-
-template <int TEAMS, int SLOTS>
-__global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg_kernel(const __grid_constant__ KParams p) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    mlpteam::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS, SLOTS>*>(smem_raw);
-    mlpteam::setup<TEAMS, SLOTS>(ms, p.weight_image);
-    const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
-    tpg::Ctx c;
-    c.cfg = &p.cfg.mcts; c.cap = p.arena_nodes; c.seed = p.seed; c.search_mode = p.search_mode != 0;
-    tpg::Game g;
-    tpg::init_game(p, g, (size_t)blockIdx.x * (128 * TEAMS) + threadIdx.x);
-    tpg::Leaf lf;
-    uint64_t my = 0, op = 0;
-    long long t_adv = 0, t_wait = 0, t_mlp = 0, t_fin = 0, t_start = clock64();
-    uint32_t rounds = 0, leaves = 0;
-    for (;;) {
-        long long t0 = clock64();
-        bool need = tpg::advance(p, c, g, lf, my, op);
-        __syncwarp();
-        long long t1 = clock64();
-        leaves += (uint32_t)__popc(__ballot_sync(0xffffffffu, need));
-        if (!mlpteam::team_any(team, need)) break; // no thread of this team has a game left
-        uint32_t mma_phase;
-        const int slot = mlpteam::acquire_slot<TEAMS, SLOTS>(ms, team, r, mma_phase);
-        long long t2 = clock64();
-        if (need) mlpteam::write_features(ms.a[slot], ms.col_lut, r, my, op);
-        float y[12];
-        mlpteam::forward<TEAMS, SLOTS>(ms, team, slot, r, mma_phase, y);
-        mlpteam::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
-        long long t3 = clock64();
-        if (need) {
-            // value.softmax(-1) (study-connect4/src/policies.rs:54-56)
-            float m = fmaxf(y[9], fmaxf(y[10], y[11]));
-            float e0 = syn_expf(__fsub_rn(y[9], m)), e1 = syn_expf(__fsub_rn(y[10], m)), e2 = syn_expf(__fsub_rn(y[11], m));
-            float tot = __fadd_rn(__fadd_rn(e0, e1), e2);
-            float lg[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) lg[k] = y[k];
-            tpg::finish(c, g, lf, false, lg, __fdiv_rn(e0, tot), __fdiv_rn(e1, tot), __fdiv_rn(e2, tot));
-            tpg::after_eval(c, g);
-        }
-        __syncwarp();
-        long long t4 = clock64();
-        t_adv += t1 - t0; t_wait += t2 - t1; t_mlp += t3 - t2; t_fin += t4 - t3; ++rounds;
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(p.counters + DBG_T_ADVANCE, (unsigned long long)t_adv);
-        atomicAdd(p.counters + DBG_T_TEAMWAIT, (unsigned long long)t_wait);
-        atomicAdd(p.counters + DBG_T_MLP, (unsigned long long)t_mlp);
-        atomicAdd(p.counters + DBG_T_FINISH, (unsigned long long)t_fin);
-        atomicAdd(p.counters + DBG_ROUNDS, (unsigned long long)rounds);
-        atomicAdd(p.counters + DBG_LEAVES, (unsigned long long)leaves);
-        atomicAdd(p.counters + DBG_T_TOTAL, (unsigned long long)(clock64() - t_start));
-    }
-    tpg::flush_counters(p, g);
-    mlpteam::teardown<TEAMS, SLOTS>(ms);
-}
-
 // ------------------------------------------------------------------ game rules on move lists (syn_engine_play)
 // One warp per game: lane c owns column c for the legal-move ballot and the feature plane.
 __global__ void play_kernel(const uint8_t* __restrict__ moves, const uint32_t* __restrict__ n_moves, uint32_t stride, uint32_t n_games,

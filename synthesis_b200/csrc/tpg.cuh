@@ -1,4 +1,6 @@
-// tpg.cuh — thread-per-game MCTS: the scalar form of tree.cuh for the batched-leaf kernels.
+// tpg.cuh — thread-per-game MCTS, scalar device functions on whole 32-byte node records: the first
+// thread-per-game implementation.  The self-play kernel built on it was replaced by tpg2.cuh (round-
+// synchronous schedule); these functions remain the MCTS half of the evaluation-match kernel (match.cuh).
 //
 // Replaces synthesis/src/mcts.rs:29-489 and synthesis/src/alpha_zero.rs:229-338 of the
 // reference, one THREAD per game.  The reference's loops over <= 9 children stay loops, in the
@@ -11,7 +13,7 @@
 // A tree is still a strictly serial object (one explore at a time, single writer): visit counts
 // stay bit-identical to the reference.  Node records: tree.cuh (32 bytes, one sector).
 #pragma once
-#include "tree.cuh"
+#include "selfplay.cuh"
 
 namespace tpg {
 
