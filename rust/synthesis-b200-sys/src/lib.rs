@@ -64,6 +64,18 @@ pub struct syn_rollout_cfg {
     pub leaf_eval_kind: u32,
 }
 
+/// One player of an evaluation match (`syn_player_cfg`): the argument list of `MCTS::exploit`
+/// (mcts.rs:111-121) / `FrozenMCTS::exploit` (evaluator.rs:308-318) minus the game.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct syn_player_cfg {
+    pub tree_kind: u32,      // 0 = MCTS, 1 = FrozenMCTS
+    pub leaf_eval_kind: u32, // 0 = Connect4Net, 1 = RolloutPolicy
+    pub num_explores: u32,
+    pub action_selection: u32,
+    pub mcts: syn_mcts_cfg,
+}
+
 #[repr(C)]
 pub struct syn_experience {
     pub capacity: usize,
@@ -119,6 +131,9 @@ extern "C" {
     pub fn syn_engine_search(e: *mut syn_engine, cfg: *const syn_rollout_cfg, tree_kind: u32, my_bb: *const u64, op_bb: *const u64,
                              seeds: *const u64, n_positions: u32, child_visits: *mut f32, child_solution: *mut u8, root_q: *mut f32,
                              root_solution: *mut u8, best_action: *mut u8, num_nodes: *mut u32, stats: *mut syn_stats) -> c_int;
+    pub fn syn_engine_match(e: *mut syn_engine, players: *const syn_player_cfg /* [2] */, seeds: *const u64, explores: *const u32 /* [n][2] or null */,
+                            n_matches: u32, result: *mut f32, n_moves: *mut u8, moves: *mut u8 /* [n][63] */, tree_nodes: *mut u32,
+                            child_visits: *mut f32, stats: *mut syn_stats) -> c_int;
     pub fn syn_engine_eval(e: *mut syn_engine, my_bb: *const u64, op_bb: *const u64, n_positions: u32, logits: *mut f32,
                            outcome_probs: *mut f32) -> c_int;
 }

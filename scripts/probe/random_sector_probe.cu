@@ -7,7 +7,7 @@
 // result is the ceiling the kernels' measured DRAM traffic should be compared with.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o random_sector_probe random_sector_probe.cu
-//   ./random_sector_probe [GiB=32]
+//   ./random_sector_probe [GiB=32] [CTAs=#SMs] [quick=0]
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -62,8 +62,15 @@ int main(int argc, char** argv) {
     cudaMemset(buf, 1, bytes);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (argc > 2 && atoi(argv[2]) > 0) sms = atoi(argv[2]);
+    const bool quick = argc > 3 && atoi(argv[3]) != 0;
     unsigned long long n_sectors = bytes / 32;
-    printf("random 32-byte sector reads over %.0f GiB, %d SMs\n", gib, sms);
+    printf("random 32-byte sector reads over %.0f GiB, %d CTAs\n", gib, sms);
+    if (quick) { // one launch pair per pattern: what ncu is pointed at
+        run<3, false>(buf, n_sectors, 512, 2048, sink, sms);
+        run<9, true>(buf, n_sectors, 512, 1024, sink, sms);
+        return 0;
+    }
     for (int threads : {256, 512, 1024}) {
         run<1, false>(buf, n_sectors, threads, 4096, sink, sms);
         run<3, false>(buf, n_sectors, threads, 2048, sink, sms);

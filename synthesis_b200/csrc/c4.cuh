@@ -35,6 +35,35 @@ __device__ __forceinline__ bool won(uint64_t bb) {
     return (d1 | d2 | h | v) != 0;
 }
 
+// All cells e such that `p | e` contains four in a row THROUGH e — the mover's winning cells for every
+// column at once (Connect4::step + won, connect4.rs:77-83, 221-233, evaluated for the nine candidate
+// moves of visit(), mcts.rs:384-397, in ~1/3 of the instructions of nine won() calls).  Stones are moved
+// one neighbour step at a time; without a sentinel row each step masks the row that would wrap into the
+// next column.  Equal to won(p | e) whenever p itself has no line yet (checked exhaustively against won()
+// on random positions: tests/test_host_and_cabi.py mirrors the algebra, the GPU parity suite the kernel).
+constexpr uint64_t ROW6 = ROW0 << 6;
+__device__ __forceinline__ uint64_t st_up(uint64_t x) { return (x & ~ROW6) << 1; }
+__device__ __forceinline__ uint64_t st_right(uint64_t x) { return (x << 7) & ALL; }
+__device__ __forceinline__ uint64_t st_left(uint64_t x) { return x >> 7; }
+__device__ __forceinline__ uint64_t st_ur(uint64_t x) { return ((x & ~ROW6) << 8) & ALL; }
+__device__ __forceinline__ uint64_t st_dl(uint64_t x) { return (x & ~ROW0) >> 8; }
+__device__ __forceinline__ uint64_t st_dr(uint64_t x) { return ((x & ~ROW0) << 6) & ALL; }
+__device__ __forceinline__ uint64_t st_ul(uint64_t x) { return (x & ~ROW6) >> 6; }
+#define SYN_LINE(F, B)                                                                  \
+    {                                                                                   \
+        uint64_t P1 = B(p), P2 = B(P1), P3 = B(P2), M1 = F(p), M2 = F(M1), M3 = F(M2);  \
+        w |= (P1 & P2 & P3) | (M1 & P1 & P2) | (M2 & M1 & P1) | (M3 & M2 & M1);         \
+    }
+__device__ __forceinline__ uint64_t winning_cells(uint64_t p) {
+    uint64_t b1 = st_up(p), b2 = st_up(b1), b3 = st_up(b2);
+    uint64_t w = b1 & b2 & b3; // vertical: three of the mover's stones right below
+    SYN_LINE(st_right, st_left)
+    SYN_LINE(st_ur, st_dl)
+    SYN_LINE(st_dr, st_ul)
+    return w;
+}
+#undef SYN_LINE
+
 // Bit of the lowest empty cell of column `col` (column must not be full): stones are bottom-
 // contiguous, so adding the column's bottom bit carries up to the first hole.
 __device__ __forceinline__ uint64_t drop_bit(uint64_t occ, int col) {

@@ -98,6 +98,13 @@ struct syn_engine {
     float* trace_visits = nullptr;
 };
 
+// Connect4::won on the host (connect4.rs:77-83), for argument validation only
+static bool host_won(uint64_t bb) {
+    const uint64_t d1 = bb & (bb >> 6) & (bb >> 12) & (bb >> 18) & c4::D1_MASK, d2 = bb & (bb >> 8) & (bb >> 16) & (bb >> 24) & c4::D2_MASK;
+    const uint64_t h = bb & (bb >> 7) & (bb >> 14) & (bb >> 21) & c4::H_MASK, v = bb & (bb >> 1) & (bb >> 2) & (bb >> 3) & c4::V_MASK;
+    return (d1 | d2 | h | v) != 0;
+}
+
 static bool is_device_ptr(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a;
@@ -161,6 +168,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         int rc = e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
                  : e->tpg_teams == 6 ? launch_tpg<6, 4>(e, kp, blocks)
+                 : e->tpg_teams == 5 ? launch_tpg<5, 4>(e, kp, blocks)
                  : e->tpg_teams == 4 ? launch_tpg<4, 4>(e, kp, blocks)
                  : e->tpg_teams == 2 ? launch_tpg<2, 2>(e, kp, blocks) : launch_tpg<1, 1>(e, kp, blocks);
         if (rc) return rc;
@@ -340,7 +348,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     const char* tenv = std::getenv("SYN_TPG_TEAMS");
     const char* penv = std::getenv("SYN_TPG_PROF");
     e->tpg_prof = penv && std::atoi(penv) == 1;
-    if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 6 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
+    if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 5 || std::atoi(tenv) == 6 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
     // round the in-flight game count up to whole CTAs of every kernel
     uint32_t unit = 1024;
     e->max_games = ((max_games_in_flight + unit - 1) / unit) * unit;
@@ -548,6 +556,7 @@ int syn_engine_search(syn_engine* e, const syn_rollout_cfg* cfg, uint32_t tree_k
         uint64_t my = my_bb[i], op = op_bb[i];
         if ((my & op) || ((my | op) >> 63)) return fail(SYN_ERR_INVALID_ARGUMENT, "position %u: overlapping or out-of-board stones", i);
         if ((my | op) == c4::ALL) return fail(SYN_ERR_INVALID_ARGUMENT, "position %u is a full board", i);
+        if (host_won(my) || host_won(op)) return fail(SYN_ERR_INVALID_ARGUMENT, "position %u is already won: MCTS::exploit is never called on a finished game", i);
     }
     CUDA_TRY(cudaSetDevice(e->device));
     e->h2d = 0; e->d2h = 0; e->launches = 0;

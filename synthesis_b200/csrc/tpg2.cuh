@@ -119,6 +119,7 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
         if (nch == 0u) break;
         // ---- select_best_child (mcts.rs:327-372): first strict maximum in child order
         const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
+        const float fpu_q = PQ ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : cfg.fpu_a; // Fpu::ParentQ = parent.q() (mcts.rs:353), once per level
         uint32_t b = 0u, bfc = 0u, bpk = 0u;
         float bval = 0.0f, bvis = 0.0f, bo0 = 0.0f, bo2 = 0.0f;
         for (uint32_t k0 = 0; k0 < nch; k0 += (uint32_t)CW) { // CW records per memory round trip
@@ -131,13 +132,14 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
                 const Rec& ch = chs[j];
                 uint32_t csol = (ch.pk >> 8) & 0xffu, cn = ch.pk & 0xffu;
                 float q;
+                // (a branch-free form — all three candidates computed and selected — measured 3 % slower: the extra
+                // divisions cost more than the divergence they remove)
                 if (csol) {
                     uint32_t kd = sol_kind(csol);
                     q = cfg.select_solved_nodes ? (kd == SYN_KIND_WIN ? -1.0f : (kd == SYN_KIND_LOSE ? 1.0f : 0.0f)) : __uint_as_float(0xff800000u);
                 } else if (cn == 0u) {
-                    if (PQ) q = __fdiv_rn(__fsub_rn(cop2, cop0), cvis);
-                    else if (FPU == SYN_FPU_CONST) q = cfg.fpu_a;
-                    else q = k < nch ? fpu_normal_draw(p, ss) : 0.0f;
+                    if (FPU == SYN_FPU_NORMAL) q = k < nch ? fpu_normal_draw(p, ss) : 0.0f;
+                    else q = fpu_q;
                 } else {
                     q = -__fdiv_rn(__fsub_rn(ch.o2, ch.o0), ch.vis);
                 }
@@ -160,13 +162,15 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
     // ---- visit (mcts.rs:374-406): number the children of `cur`; auto-extend through only-children
     for (;;) {
         uint64_t occ = my | op;
+        const uint64_t win = c4::winning_cells(my);   // where the mover completes four in a row
+        const bool last = __popcll(occ) == 62;        // this move fills the board: a draw unless it wins
         uint32_t lm = 0u, cs2 = 0u, n = 0u;
 #pragma unroll
         for (int col = 0; col < 9; ++col) {
             uint32_t colbits = (uint32_t)((occ >> (7 * col)) & 0x7full);
             if (colbits != 0x7fu) {
                 uint64_t bit = 1ull << (7 * col + __popc(colbits));
-                uint32_t s2 = c4::won(my | bit) ? 1u : (((occ | bit) == c4::ALL) ? 2u : 0u);
+                uint32_t s2 = (win & bit) ? 1u : (last ? 2u : 0u);
                 lm |= 1u << col;
                 cs2 |= s2 << (2 * col);
                 ++n;
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
     uint32_t* const ss = p.slot_state + tp2::SS_WORDS * slot_id;
     const syn_mcts_cfg& cfg = p.cfg.mcts;
     const float stop_vis = (float)(p.cfg.num_explores + 1u); // explore_n is over when the root has 1 + num_explores visits
-    constexpr int CW = TEAMS >= 6 ? 3 : 5;
+    constexpr int CW = TEAMS >= 5 ? 3 : 5;
     tp2::Game g;
     g.nodes = p.nodes + 2 * slot_id * p.arena_nodes;
     g.nn = 1u; g.phase = PH_NEED_GAME;

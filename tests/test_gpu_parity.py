@@ -503,3 +503,51 @@ def test_engine_matches_committed_match_fixtures(engine):
         return {k: v[0] for k, v in out.items()}
 
     assert G.check_match_fixture(run) == len(G.MATCH_CASES)
+
+
+# ---------------------------------------------------------------- configs[2]: 1600 explores, Dirichlet root noise, sampled actions
+def _config3(explores=1600):
+    m = s.study_connect4_mcts_cfg()
+    m.root_policy_noise = s.PolicyNoise.Dirichlet(1.0, 0.25)
+    return s.study_connect4_rollout_cfg(num_explores=explores, mcts_cfg=m, sample_actions_until=30)
+
+
+def test_gather_config3_rollout_bit_exact(engine, oracle):
+    cfg = _config3()
+    a, st, tr = engine.gather(cfg, L.LEAF_ROLLOUT, first_game_index=11, num_games=6, seed=9, trace=True)
+    ra, rst, rtr = oracle.gather(cfg.to_c(L.LEAF_ROLLOUT), 9, 11, 6, threads=6)
+    assert_rows_equal(tr, rtr, "trace")
+    assert_rows_equal(a, ra, "experience")
+    for k in ("explores", "leaf_evals", "rows", "trees", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels"):
+        assert st[k] == rst[k], (k, st[k], rst[k])
+
+
+def test_gather_config3_nn_bit_exact_given_gpu_leaf_outputs(engine, oracle):
+    net = s.Connect4Net.new(8)
+    engine.set_weights(net.blob())
+    cfg = _config3(explores=400)
+    a, st, tr = engine.gather(cfg, L.LEAF_NN, 0, 3, 5, trace=True)
+    ra, rst, rtr = oracle.gather(cfg.to_c(L.LEAF_NN), 5, 0, 3, callback=_gpu_leaf_callback(engine), threads=1)
+    assert_rows_equal(tr, rtr, "trace")
+    assert_rows_equal(a, ra, "experience")
+
+
+def test_gather_many_games_properties(engine):
+    """Size-independent properties at a size the oracle cannot replay: every game ends, rows are
+    ordered by game then ply, pi rows sum to 1 over legal moves only, value rows are distributions,
+    and the whole gather is reproducible bit for bit (a second run with the same seed)."""
+    net = s.Connect4Net.new(1)
+    engine.set_weights(net.blob())
+    cfg = s.study_connect4_rollout_cfg(num_explores=64)
+    a, st, _ = engine.gather(cfg, L.LEAF_NN, 0, 4736, 3)
+    b, st2, _ = engine.gather(cfg, L.LEAF_NN, 0, 4736, 3)
+    assert_rows_equal(a, b, "same seed, second run")
+    assert st["games"] == 4736 and st["rows"] == len(a["vs"])
+    ids = a["game_ids"].astype(np.int64)
+    assert ids[0] == 1 and ids[-1] == 4736 and np.all(np.diff(ids) >= 0) and np.all(np.diff(ids) <= 1)
+    stones = np.array([bin(int(x) | int(y)).count("1") for x, y in zip(a["my_bb"][:5000], a["op_bb"][:5000])])
+    first = np.r_[True, ids[1:5000] != ids[:4999]]
+    assert np.all(stones[first] == 0) and np.all(stones[~first] == stones[np.flatnonzero(~first) - 1] + 1)
+    assert np.allclose(a["pis"].sum(1), 1.0, atol=1e-5) and np.allclose(a["vs"].sum(1), 1.0, atol=1e-5)
+    full = a["height"] >= 7
+    assert np.all(a["pis"][full] == 0.0)

@@ -201,3 +201,58 @@ def test_stream_seeds(oracle):
         assert oracle.lib.orc_stream_seed(0, g, 0) == 2 * g and oracle.lib.orc_stream_seed(0, g, 1) == 2 * g + 1
     seen = {oracle.lib.orc_stream_seed(sd, g, k) for sd in range(3) for g in range(50) for k in range(4)}
     assert len(seen) == 3 * 50 * 4
+
+
+def test_winning_cells_algebra_equals_won_per_column():
+    """csrc/c4.cuh winning_cells(): the mover's winning cells for all nine columns from one pass of masked
+    neighbour shifts.  Mirrored here in Python integers and checked against Connect4::won (connect4.rs:77-83)
+    applied to every candidate move of random positions."""
+    import random
+    ROW0 = sum(1 << (7 * c) for c in range(9)); ROW6 = ROW0 << 6; ALL = (1 << 63) - 1; M64 = (1 << 64) - 1
+    C05 = (1 << 42) - 1
+    VM, HM, D2M, D1M = ROW0 * 0x0F, C05, C05 & (ROW0 * 0x0F), C05 & (ROW0 * 0x78)
+
+    def won(bb):
+        return ((bb & (bb >> 6) & (bb >> 12) & (bb >> 18) & D1M) | (bb & (bb >> 8) & (bb >> 16) & (bb >> 24) & D2M) |
+                (bb & (bb >> 7) & (bb >> 14) & (bb >> 21) & HM) | (bb & (bb >> 1) & (bb >> 2) & (bb >> 3) & VM)) != 0
+
+    up = lambda x: ((x & ~ROW6) << 1) & M64
+    right, left = (lambda x: (x << 7) & ALL), (lambda x: x >> 7)
+    ur, dl = (lambda x: ((x & ~ROW6) << 8) & ALL), (lambda x: (x & ~ROW0) >> 8)
+    dr, ul = (lambda x: ((x & ~ROW0) << 6) & ALL), (lambda x: (x & ~ROW6) >> 6)
+
+    def line(p, F, B):
+        P1 = B(p); P2 = B(P1); P3 = B(P2); M1 = F(p); M2 = F(M1); M3 = F(M2)
+        return (P1 & P2 & P3) | (M1 & P1 & P2) | (M2 & M1 & P1) | (M3 & M2 & M1)
+
+    def winning_cells(p):
+        b1 = up(p); b2 = up(b1); b3 = up(b2)
+        return (b1 & b2 & b3) | line(p, right, left) | line(p, ur, dl) | line(p, dr, ul)
+
+    rnd = random.Random(5)
+    checked = wins = 0
+    for _ in range(20000):
+        my = op = 0
+        h = [0] * 9
+        alive = True
+        for _ in range(rnd.randint(0, 60)):
+            cols = [c for c in range(9) if h[c] < 7]
+            if not cols:
+                break
+            c = rnd.choice(cols)
+            mover = my | (1 << (h[c] + 7 * c))
+            h[c] += 1
+            my, op = op, mover
+            if won(mover):
+                alive = False
+                break
+        if not alive:
+            continue
+        w = winning_cells(my)
+        for c in range(9):
+            if h[c] < 7:
+                bit = 1 << (h[c] + 7 * c)
+                assert won(my | bit) == ((w & bit) != 0), (hex(my), hex(op), c)
+                checked += 1
+                wins += won(my | bit)
+    assert checked > 50000 and wins > 1000
