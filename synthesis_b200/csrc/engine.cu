@@ -136,7 +136,7 @@ static int validate_cfg(const syn_rollout_cfg* cfg, const syn_engine* e) {
 
 template <int TEAMS, int SLOTS>
 static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
-    size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>);
+    size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>) + (size_t)tp2::path_cap(TEAMS) * 128 * TEAMS * sizeof(uint32_t);
     if (e->tpg_prof) { // with per-warp phase clocks (syn_engine_debug_counters)
         CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2_kernel<TEAMS, SLOTS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         selfplay_nn_tpg2_kernel<TEAMS, SLOTS, true><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
@@ -227,6 +227,8 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.error = e->error.p;
     kp.weights = e->weights.p;
     kp.weight_image = e->weight_image.p;
+    const char* nored = std::getenv("SYN_TPG_NO_RED"); // read per launch so that one test process can run both forms
+    kp.no_reductions = (nored && std::atoi(nored) == 1) ? 1u : 0u;
 }
 
 static int read_stats(syn_engine* e, syn_stats* stats, float ms) {

@@ -53,6 +53,18 @@ __device__ __forceinline__ void store_rec(uint4* nodes, uint32_t i, float vis, f
 __device__ __forceinline__ void store_stat(uint4* nodes, uint32_t i, float vis, float o0, float o1, float o2) {
     nodes[2 * (size_t)i] = make_uint4(__float_as_uint(vis), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2));
 }
+// Fire-and-forget form of store_stat(load + add): ONE vector reduction at the L2 (REDG.E.ADD.F32x4.RN), no
+// round trip.  Each component is an IEEE round-to-nearest-even f32 addition like the CPU's, EXCEPT that the
+// L2's adder flushes subnormal inputs and results to zero — red_exact() below says when that cannot happen.
+__device__ __forceinline__ void red_stat(uint4* nodes, uint32_t i, float v0, float v1, float v2) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(nodes + 2 * (size_t)i), "f"(1.0f), "f"(v0), "f"(v1), "f"(v2) : "memory");
+}
+// True when x is zero or |x| >= 2^-100.  As long as every value ever added into a tree passes this test,
+// every outcome sum in the tree is zero or normal (sums and differences of such values are zero or >= 2^-124),
+// so the flushing adder and the IEEE adder agree bit for bit.  The first value that fails makes the tree
+// "slow" (Game::slow) until it is reset: it then only uses load / FADD / store.
+__device__ __forceinline__ bool red_exact(float x) { return ((__float_as_uint(x) << 1) >= (27u << 24)) || ((__float_as_uint(x) << 1) == 0u); }
+__device__ __forceinline__ void prefetch_l2(const uint4* nodes, uint32_t i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + 2 * (size_t)i)); }
 __device__ __forceinline__ uint32_t* meta_words(uint4* nodes, uint32_t i) { return reinterpret_cast<uint32_t*>(nodes + 2 * (size_t)i + 1); }
 enum { MW_PRIOR = 0, MW_PARENT = 1, MW_FC = 2, MW_PK = 3 };
 
@@ -69,6 +81,7 @@ struct Game {
     uint4* nodes;
     uint32_t nn; // nodes.len()
     int phase;   // PH_*
+    bool slow;   // this tree has seen a value the L2's flushing adder would treat differently: no reductions (red_exact)
 };
 
 struct Pend { // what descend leaves for finish
@@ -76,7 +89,11 @@ struct Pend { // what descend leaves for finish
     uint32_t id;    // K_LEAF: the expanded node; K_TERMINAL: the proven node
     uint32_t fc;    // K_LEAF: first child; K_TERMINAL: the node's packed solution
     uint32_t lc;    // K_LEAF: legal mask | csol2 << 9 (2 bits per column: 0 none / 1 Lose(0) / 2 Draw(0))
+    uint32_t depth; // level of `id` (root = 0): path[0 .. depth-1] holds the ids of levels 1 .. depth
 };
+
+// Levels of the path table per thread: what fits beside the MLP state in 227 KB of shared memory.
+__host__ __device__ constexpr int path_cap(int teams) { return teams <= 4 ? 12 : teams == 5 ? 10 : teams == 6 ? 8 : 6; }
 
 struct RoundCnt { uint32_t levels, scanned, expansions, created, bp_levels, leaf_evals, explores; };
 
@@ -102,9 +119,11 @@ __device__ __noinline__ float fpu_normal_draw(const KParams& p, uint32_t* ss) { 
 // CW = child records requested per memory round trip (3 at 64 registers per thread, 9 at 128).
 // FPU = the configured syn_fpu_kind, a template parameter so that the common Fpu::Const instantiation carries
 // neither the parent's outcome sums (ParentQ) nor a call in its inner loop (Normal).
-template <int CW, int FPU>
+// path = this thread's column of the CTA's path table in shared memory (entry l-1 = the node walked at level l,
+// stride NT words, levels 1 .. PATH_CAP), so that backprop knows the way up without reading parent links.
+template <int CW, int FPU, int NT, int PATH_CAP>
 __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, const Rec& root, uint64_t& my, uint64_t& op, Pend& pd,
-                                       RoundCnt& rc) {
+                                       RoundCnt& rc, uint32_t* path) {
     const syn_mcts_cfg& cfg = p.cfg.mcts;
     uint4* nodes = g.nodes;
     uint32_t cur = 0u;
@@ -115,8 +134,11 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
     const bool puct = cfg.exploration_kind == SYN_EXPLORATION_POLYNOMIAL_UCT;
     for (;;) {
         uint32_t sol = (cpk >> 8) & 0xffu, nch = cpk & 0xffu;
-        if (sol) { rc.levels = depth; pd.kind = K_TERMINAL; pd.id = cur; pd.fc = sol; return 0; } // mcts.rs:314-316
+        if (sol) { rc.levels = depth; pd.kind = K_TERMINAL; pd.id = cur; pd.fc = sol; pd.depth = depth; return 0; } // mcts.rs:314-316
         if (nch == 0u) break;
+        // the children are read CW at a time; DRAM hands out whole 128-byte lines, so asking for the last child's line now
+        // makes the second batch an L2 hit instead of a second trip to HBM
+        if (nch > (uint32_t)CW) prefetch_l2(nodes, cfc + nch - 1u);
         // ---- select_best_child (mcts.rs:327-372): first strict maximum in child order
         const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
         const float fpu_q = PQ ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : cfg.fpu_a; // Fpu::ParentQ = parent.q() (mcts.rs:353), once per level
@@ -156,6 +178,7 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
         cur = cfc + b;
         cvis = bvis; cop0 = bo0; cop2 = bo2; cfc = bfc; cpk = bpk;
         c4::step(my, op, (int)((cpk >> 16) & 0xffu));
+        if (depth < (uint32_t)PATH_CAP) path[depth * NT] = cur;
         if (++depth >= 64u) return DERR_DEPTH_OVERFLOW;
     }
     rc.levels = depth; // one select_best_child call per level walked
@@ -191,54 +214,76 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
             store_rec(nodes, fc, 0.f, 0.f, 0.f, 0.f, __float_as_uint(1.0f), cur, 0u, cpk);
             c4::step(my, op, only);
             cur = fc;
+            if (depth < (uint32_t)PATH_CAP) path[depth * NT] = cur;
             if (++depth >= 64u) return DERR_DEPTH_OVERFLOW;
-            if (osol) { pd.kind = K_TERMINAL; pd.id = cur; pd.fc = osol; return 0; } // mcts.rs:377-379
+            if (osol) { pd.kind = K_TERMINAL; pd.id = cur; pd.fc = osol; pd.depth = depth; return 0; } // mcts.rs:377-379
             continue;
         }
-        pd.kind = K_LEAF; pd.id = cur; pd.fc = fc; pd.lc = lm | (cs2 << 9);
+        pd.kind = K_LEAF; pd.id = cur; pd.fc = fc; pd.lc = lm | (cs2 << 9); pd.depth = depth;
         return 0;
     }
 }
 
-// mcts.rs:429-488 from node `id` up to the root, following parent links like the reference.
-__device__ __forceinline__ uint32_t backprop(const syn_mcts_cfg& cfg, uint4* nodes, uint32_t id, float v0, float v1, float v2, bool solved) {
+// mcts.rs:429-488 from node `id` (at level `depth`) up to the root.  While the value is still "solved" the node and its
+// children are read like the reference does; once it is not (the common case from the first level on), a level is ONE
+// vector reduction into the node's {visits, outcome sums} and the way up comes from the path table, so nothing waits for
+// memory.  Beyond PATH_CAP levels the parent link is read.  `slow` (Game::slow) forces load / add / store everywhere.
+template <int NT, int PATH_CAP>
+__device__ __forceinline__ uint32_t backprop(const syn_mcts_cfg& cfg, uint4* nodes, const uint32_t* path, uint32_t depth, uint32_t id, float v0, float v1,
+                                             float v2, bool solved, bool& slow) {
     uint32_t levels = 0;
+    solved = solved && cfg.solve;
     for (;;) {
-        Rec n = load_rec(nodes, id);
         ++levels;
-        if (cfg.solve && solved) {
-            uint32_t nch = n.pk & 0xffu, nsol = (n.pk >> 8) & 0xffu;
-            uint32_t bk = sol_key(nsol);
-            bool all_solved = true;
-            for (uint32_t k = 0; k < nch; ++k) {
-                uint32_t csol = (meta_words(nodes, n.fc + k)[MW_PK] >> 8) & 0xffu;
-                uint32_t rs = csol ? sol_reversed(csol) : 0u;
-                all_solved = all_solved && rs != 0u;
-                uint32_t key = sol_key(rs);
-                bk = key > bk ? key : bk;
-            }
-            uint32_t best = sol_from_key(bk);
-            bool mark = false;
-            int slot = 0;
-            if (sol_kind(best) == SYN_KIND_WIN) { mark = true; slot = 2; }
-            else if (best != 0u && all_solved) { mark = true; slot = sol_kind(best) == SYN_KIND_DRAW ? 1 : 0; }
-            if (mark) {
-                if (cfg.correct_values_on_solve) {
-                    v0 = -n.o0; v1 = -n.o1; v2 = -n.o2;
-                    float add = n.vis + 1.0f;
-                    if (slot == 2) v2 = v2 + add;
-                    else if (slot == 1) v1 = v1 + add;
-                    else v0 = v0 + add;
+        uint32_t parent;
+        if (!slow && !(red_exact(v0) && red_exact(v1) && red_exact(v2))) slow = true;
+        if (solved || slow) {
+            Rec n = load_rec(nodes, id);
+            if (solved) {
+                uint32_t nch = n.pk & 0xffu, nsol = (n.pk >> 8) & 0xffu;
+                uint32_t cpk[9];
+#pragma unroll
+                for (uint32_t k = 0; k < 9u; ++k) cpk[k] = k < nch ? meta_words(nodes, n.fc + k)[MW_PK] : 0u; // all in flight together
+                uint32_t bk = sol_key(nsol);
+                bool all_solved = true;
+#pragma unroll
+                for (uint32_t k = 0; k < 9u; ++k) {
+                    if (k < nch) {
+                        uint32_t csol = (cpk[k] >> 8) & 0xffu;
+                        uint32_t rs = csol ? sol_reversed(csol) : 0u;
+                        all_solved = all_solved && rs != 0u;
+                        uint32_t key = sol_key(rs);
+                        bk = key > bk ? key : bk;
+                    }
                 }
-                meta_words(nodes, id)[MW_PK] = (n.pk & 0xffff00ffu) | (best << 8);
-            } else {
-                solved = false;
+                uint32_t best = sol_from_key(bk);
+                bool mark = false;
+                int slot = 0;
+                if (sol_kind(best) == SYN_KIND_WIN) { mark = true; slot = 2; }
+                else if (best != 0u && all_solved) { mark = true; slot = sol_kind(best) == SYN_KIND_DRAW ? 1 : 0; }
+                if (mark) {
+                    if (cfg.correct_values_on_solve) {
+                        v0 = -n.o0; v1 = -n.o1; v2 = -n.o2;
+                        float add = n.vis + 1.0f;
+                        if (slot == 2) v2 = v2 + add;
+                        else if (slot == 1) v1 = v1 + add;
+                        else v0 = v0 + add;
+                    }
+                    meta_words(nodes, id)[MW_PK] = (n.pk & 0xffff00ffu) | (best << 8);
+                } else {
+                    solved = false;
+                }
             }
+            store_stat(nodes, id, n.vis + 1.0f, n.o0 + v0, n.o1 + v1, n.o2 + v2);
+            parent = n.parent;
+        } else {
+            red_stat(nodes, id, v0, v1, v2);
+            parent = depth <= 1u ? 0u : (depth - 2u < (uint32_t)PATH_CAP ? path[(depth - 2u) * NT] : meta_words(nodes, id)[MW_PARENT]);
         }
-        store_stat(nodes, id, n.vis + 1.0f, n.o0 + v0, n.o1 + v1, n.o2 + v2);
         if (id == 0u) break;
         float tmp = v0; v0 = v2; v2 = tmp;
-        id = n.parent;
+        id = parent;
+        --depth;
     }
     return levels;
 }
@@ -468,6 +513,8 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ unsigned long long s_cnt[CNT_ALL];
     mlpteam::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS, SLOTS>*>(smem_raw);
+    constexpr int NT = 128 * TEAMS, PATH_CAP = tp2::path_cap(TEAMS);
+    uint32_t* const path = reinterpret_cast<uint32_t*>(smem_raw + sizeof(mlpteam::Smem<TEAMS, SLOTS>)) + threadIdx.x; // [PATH_CAP][NT] after the MLP state
     if (threadIdx.x < CNT_ALL) s_cnt[threadIdx.x] = 0ull;
     mlpteam::setup<TEAMS, SLOTS>(ms, p.weight_image);
     const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
@@ -478,7 +525,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
     constexpr int CW = TEAMS >= 5 ? 3 : 5;
     tp2::Game g;
     g.nodes = p.nodes + 2 * slot_id * p.arena_nodes;
-    g.nn = 1u; g.phase = PH_NEED_GAME;
+    g.nn = 1u; g.phase = PH_NEED_GAME; g.slow = p.no_reductions != 0u;
     // per-warp phase clocks (syn_engine_debug_counters): only in the PROF instantiation, they cost 14 registers
     long long t_adv = 0, t_wait = 0, t_mlp = 0, t_fin = 0, t_start = PROF ? clock64() : 0;
     uint32_t rounds = 0, leaves = 0;
@@ -486,7 +533,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
         long long t0 = PROF ? clock64() : 0;
         // ---- cold bookkeeping, then at most one descent
         tp2::Pend pd;
-        pd.kind = tp2::K_NONE; pd.id = 0u; pd.fc = 0u; pd.lc = 0u;
+        pd.kind = tp2::K_NONE; pd.id = 0u; pd.fc = 0u; pd.lc = 0u; pd.depth = 0u;
         tp2::RoundCnt rc = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
         uint64_t my = 0, op = 0;
         if (g.phase != PH_DONE) {
@@ -509,6 +556,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
                     tp2::store_rec(g.nodes, 0u, 0.f, 0.f, 0.f, 0.f, 0u, 0u, 0u, 0u);
                     my = tp2::ss_load64(ss, tp2::SS_MY); op = tp2::ss_load64(ss, tp2::SS_OP);
                     g.nn = 1u;
+                    g.slow = p.no_reductions != 0u;
                     atomicAdd(&s_cnt[CNT_TREES], 1ull);
                     g.phase = PH_EXPLORE;
                 } else {
@@ -517,9 +565,9 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
             }
             if (go && !err) {
                 const uint32_t init = root.vis == 0.0f ? (uint32_t)tp2::K_INIT : 0u; // the construction visit (mcts.rs:133)
-                if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST>(p, ss, g, root, my, op, pd, rc);
-                else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q>(p, ss, g, root, my, op, pd, rc);
-                else err = tp2::descend<CW, SYN_FPU_NORMAL>(p, ss, g, root, my, op, pd, rc);
+                if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                else err = tp2::descend<CW, SYN_FPU_NORMAL, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 pd.kind |= init;
             }
             if (err) { atomicCAS(p.error, 0, err); g.phase = PH_DONE; pd.kind = tp2::K_NONE; }
@@ -567,7 +615,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
                 v0 = idx == 0 ? 1.0f : 0.0f; v1 = idx == 1 ? 1.0f : 0.0f; v2 = idx == 2 ? 1.0f : 0.0f;
                 solved = true;
             }
-            rc.bp_levels = tp2::backprop(cfg, g.nodes, pd.id, v0, v1, v2, solved);
+            rc.bp_levels = tp2::backprop<NT, PATH_CAP>(cfg, g.nodes, path, pd.depth, pd.id, v0, v1, v2, solved, g.slow);
             if (pd.kind & tp2::K_INIT) tp2::add_root_noise(p, ss, g.nodes);
         }
         __syncwarp();

@@ -551,3 +551,56 @@ def test_gather_many_games_properties(engine):
     assert np.allclose(a["pis"].sum(1), 1.0, atol=1e-5) and np.allclose(a["vs"].sum(1), 1.0, atol=1e-5)
     full = a["height"] >= 7
     assert np.all(a["pis"][full] == 0.0)
+
+
+# ---------------------------------------------------------------- backprop by L2 reductions (tpg2.cuh red_stat) vs load / add / store
+def _with_env(name, value, fn):
+    import os
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+def test_backprop_reductions_equal_load_add_store(engine):
+    """The thread-per-game kernel adds a leaf's value into the path's nodes with one REDG.ADD.F32x4 per level; with
+    SYN_TPG_NO_RED=1 it loads, adds and stores like the CPU.  Same trees, same rows, same counters."""
+    engine.set_weights(s.Connect4Net.new(4).blob())
+    cfg = _config3(explores=300)
+    run = lambda: engine.gather(cfg, L.LEAF_NN, 0, 700, 2, trace=True)
+    a, st, tr = run()
+    b, st2, tr2 = _with_env("SYN_TPG_NO_RED", "1", run)
+    assert_rows_equal(a, b, "experience")
+    assert_rows_equal(tr, tr2, "trace")
+    for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels"):
+        assert st[k] == st2[k], k
+
+
+def test_backprop_with_subnormal_values_is_bit_exact(engine, oracle):
+    """The L2's adder flushes subnormals, the CPU's does not.  A net whose value head yields a subnormal draw probability
+    (zero weights, l_5.bias = [.., 0, -95, -60]) must still give the oracle's outcome sums bit for bit: the kernel notices
+    the value and keeps that tree on load / add / store (tpg2.cuh red_exact)."""
+    p = {}
+    for l in range(5):
+        i, o = s.policies.LAYER_DIMS[l], s.policies.LAYER_DIMS[l + 1]
+        p[f"l_{l + 1}.weight"] = np.zeros((o, i), np.float32)
+        p[f"l_{l + 1}.bias"] = np.zeros((o,), np.float32)
+    p["l_5.bias"][9:12] = [0.0, -95.0, -60.0]
+    net = s.Connect4Net(p)
+    engine.set_weights(net.blob())
+    _, pr = engine.eval([0], [0])
+    assert 0.0 < float(pr[0, 1]) < 1.1754944e-38, pr  # a subnormal probability reaches the tree
+    cfg = s.study_connect4_rollout_cfg(num_explores=120)  # ValueTarget::Q: the rows carry the root sums
+    a, st, tr = engine.gather(cfg, L.LEAF_NN, 0, 40, 6, trace=True)
+    b, st2, tr2 = _with_env("SYN_TPG_NO_RED", "1", lambda: engine.gather(cfg, L.LEAF_NN, 0, 40, 6, trace=True))
+    assert_rows_equal(a, b, "experience (reductions vs load/add/store)")
+    ra, rst, rtr = oracle.gather(cfg.to_c(L.LEAF_NN), 6, 0, 4, callback=_gpu_leaf_callback(engine), threads=1)
+    n = len(ra["vs"])
+    assert np.any((a["vs"][:n, 1] > 0) & (a["vs"][:n, 1] < 1.1754944e-38)), "no subnormal Q reached the experience rows"
+    for k in a:
+        assert a[k][:n].tobytes() == ra[k].tobytes(), k
