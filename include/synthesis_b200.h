@@ -230,6 +230,31 @@ int syn_engine_play(syn_engine* e, const uint8_t* moves, const uint32_t* n_moves
                     uint64_t* my_bb, uint64_t* op_bb, uint8_t* height /*[n][9]*/, uint8_t* legal_mask_lo /*[n] cols 0-7*/,
                     uint8_t* legal_mask_hi /*[n] col 8*/, uint8_t* status, float* features /*[n][63] or NULL*/);
 
+/* synthesis/src/data.rs:80-104  struct FlatBatch {states, pis, vs} + StateStatistics — what
+ * ReplayBuffer::deduplicate returns: one row per DISTINCT position of the buffer.  my_bb/op_bb/num
+ * (the HashMap key and StateStatistics::num) are extra and may be NULL, like every array.
+ * Pointers may be host or device memory. */
+typedef struct {
+    size_t capacity; /* in: rows available in every non-NULL array (n_rows always suffices) */
+    size_t len;      /* out: distinct positions */
+    float* states;   /* [cap][63]  StateStatistics::state = Game::features() of the position */
+    float* pis;      /* [cap][9]   sum_pi / num   (data.rs:220-224) */
+    float* vs;       /* [cap][3]   sum_v / num    (data.rs:225-229) */
+    uint64_t* my_bb; /* [cap] */
+    uint64_t* op_bb; /* [cap] */
+    uint32_t* num;   /* [cap]      rows merged into this one */
+} syn_flat_batch;
+
+/* Replaces ReplayBuffer::deduplicate (data.rs:196-235), the step that follows gather_experience in
+ * the training loop (alpha_zero.rs:53-58), on n_rows rows given as struct-of-arrays (the my_bb, op_bb,
+ * pis, vs arrays of syn_experience; host or device pointers).  Rows with equal (my_bb, op_bb) — the
+ * fields Connect4's Hash/Eq reduce to — are merged; sums run in row order in f32 like the reference's
+ * loop, so every output value is bit-identical to the reference's.  Output order: by first occurrence
+ * of the position in the buffer (the reference's order is HashMap-random; equal as a set).
+ * stats (optional): rows = distinct positions, device_ns, kernel_launches, h2d/d2h bytes. */
+int syn_engine_deduplicate(syn_engine* e, const uint64_t* my_bb, const uint64_t* op_bb, const float* pis, const float* vs,
+                           size_t n_rows, syn_flat_batch* out, syn_stats* stats);
+
 /* Optional per-row trace of the NEXT gather (arrays of `capacity` rows like syn_experience, host or
  * device; NULL to disable): the action played from the row's state, nodes.len() of that ply's
  * tree, and the root's child visit counts by column.  Not part of the reference's ReplayBuffer;

@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <thread>
+#include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "selfplay.hpp"
 
@@ -331,6 +334,46 @@ size_t orc_keep_last_n_games_prefix(const uint64_t* game_ids, size_t len, uint64
         remove = i + 1;
     }
     return remove;
+}
+
+// ---- ReplayBuffer::deduplicate (data.rs:196-235): HashMap<G, StateStatistics> keyed by the position; sums run in
+// buffer order (data.rs:199-215), averages are sum / num as f32 (data.rs:220-229).  The reference iterates the HashMap
+// (random order per process); the groups are emitted here in order of first occurrence, which is what the device emits.
+// Returns the number of distinct positions (which may exceed `capacity`: then nothing past capacity is written).
+size_t orc_deduplicate(const uint64_t* my_bb, const uint64_t* op_bb, const float* pis, const float* vs, size_t n, size_t capacity,
+                       float* out_states, float* out_pis, float* out_vs, uint64_t* out_my, uint64_t* out_op, uint32_t* out_num) {
+    struct Stat { float sum_pi[9]; float sum_v[3]; uint32_t num; size_t first; };
+    struct KeyHash { size_t operator()(const std::pair<uint64_t, uint64_t>& k) const { return (size_t)(k.first * 0x9E3779B97F4A7C15ull ^ (k.second + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull); } };
+    std::unordered_map<std::pair<uint64_t, uint64_t>, size_t, KeyHash> index;
+    std::vector<Stat> stats;
+    index.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        auto key = std::make_pair(my_bb[i], op_bb[i]);
+        auto it = index.find(key);
+        if (it == index.end()) {
+            it = index.emplace(key, stats.size()).first;
+            Stat st;
+            std::memset(&st, 0, sizeof(st));
+            st.first = i;
+            stats.push_back(st);
+        }
+        Stat& st = stats[it->second];
+        for (int j = 0; j < 9; ++j) st.sum_pi[j] += pis[9 * i + j];
+        for (int j = 0; j < 3; ++j) st.sum_v[j] += vs[3 * i + j];
+        st.num += 1;
+    }
+    for (size_t g = 0; g < stats.size() && g < capacity; ++g) {
+        const Stat& st = stats[g];
+        for (int j = 0; j < 9; ++j) if (out_pis) out_pis[9 * g + j] = st.sum_pi[j] / (float)st.num;
+        for (int j = 0; j < 3; ++j) if (out_vs) out_vs[3 * g + j] = st.sum_v[j] / (float)st.num;
+        if (out_my) out_my[g] = my_bb[st.first];
+        if (out_op) out_op[g] = op_bb[st.first];
+        if (out_num) out_num[g] = st.num;
+        if (out_states) {
+            Connect4::from_bitboards(my_bb[st.first], op_bb[st.first]).features(out_states + 63 * g);
+        }
+    }
+    return stats.size();
 }
 
 } // extern "C"

@@ -9,11 +9,11 @@ from .config import (ActionSelection, EvaluationConfig, Exploration, Fpu, Learni
                      RolloutConfig, ValueTarget, study_connect4_mcts_cfg, study_connect4_rollout_cfg,
                      study_connect4_rollout_mcts_cfg)
 from .connect4 import Connect4
-from .data import ReplayBuffer
+from .data import FlatBatch, ReplayBuffer
 from .engine import Engine
 from .policies import Connect4Net, RolloutPolicy
 
 __all__ = ["MCTS", "gather_experience", "engine_for", "ActionSelection", "EvaluationConfig", "Exploration", "Fpu",
-           "LearningConfig", "MCTSConfig", "PolicyNoise", "RolloutConfig", "ValueTarget", "Connect4", "ReplayBuffer",
+           "LearningConfig", "MCTSConfig", "PolicyNoise", "RolloutConfig", "ValueTarget", "Connect4", "FlatBatch", "ReplayBuffer",
            "Engine", "Connect4Net", "RolloutPolicy", "study_connect4_mcts_cfg", "study_connect4_rollout_cfg",
            "study_connect4_rollout_mcts_cfg"]

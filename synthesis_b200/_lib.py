@@ -67,6 +67,13 @@ class SynExperience(C.Structure):
     ]
 
 
+class SynFlatBatch(C.Structure):
+    _fields_ = [
+        ("capacity", C.c_size_t), ("len", C.c_size_t), ("states", C.c_void_p), ("pis", C.c_void_p), ("vs", C.c_void_p),
+        ("my_bb", C.c_void_p), ("op_bb", C.c_void_p), ("num", C.c_void_p),
+    ]
+
+
 class SynStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "explores", "leaf_evals", "rows", "games", "trees", "nodes", "select_levels", "children_scanned",
@@ -82,6 +89,7 @@ EXPORTED_SYMBOLS = (
     "syn_abi_version", "syn_build_info", "syn_last_error", "syn_engine_create", "syn_engine_destroy",
     "syn_engine_set_weights", "syn_engine_gather", "syn_engine_gather_launch", "syn_engine_gather_wait",
     "syn_engine_search", "syn_engine_match", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode", "syn_engine_debug_counters",
+    "syn_engine_deduplicate",
 )
 
 _lib = None
@@ -122,6 +130,7 @@ def load():
     lib.syn_engine_set_group_lanes.argtypes = [vp, i32]
     lib.syn_engine_set_mlp_mode.argtypes = [vp, i32]
     lib.syn_engine_debug_counters.argtypes = [vp, vp, u32]
+    lib.syn_engine_deduplicate.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(SynFlatBatch), C.POINTER(SynStats)]
     _lib = lib
     return lib
 

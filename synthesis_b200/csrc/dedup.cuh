@@ -277,8 +277,9 @@ __global__ void __launch_bounds__(T) reduce_kernel(const uint32_t* __restrict__ 
     emit_header(o, g, my[first_row], op[first_row], cnt, c, 16);
 }
 
-// One CTA per big group: all threads gather the next BIG_CHUNK rows into shared memory while lanes 0..11 of warp 0
-// add the previous chunk in row order.
+// One CTA per big group: warps 1..7 gather the next BIG_CHUNK rows into shared memory while lanes 0..11 of warp 0
+// add the previous chunk in row order (the chain of dependent f32 additions is the critical path of the whole
+// call: 4 cycles per row, loads hoisted eight rows ahead).
 __global__ void __launch_bounds__(T) reduce_big_kernel(const uint32_t* __restrict__ rows_sorted, const uint32_t* __restrict__ gstart,
                                                        const uint32_t* __restrict__ big_list, const uint64_t* __restrict__ my,
                                                        const uint64_t* __restrict__ op, const float* __restrict__ pis,
@@ -288,23 +289,32 @@ __global__ void __launch_bounds__(T) reduce_big_kernel(const uint32_t* __restric
     const uint32_t s = gstart[g], e = gstart[g + 1u], cnt = e - s;
     const uint32_t chunks = (cnt + BIG_CHUNK - 1) / BIG_CHUNK;
     float acc = 0.0f;
-    auto stage = [&](uint32_t k) {
+    auto stage = [&](uint32_t k, uint32_t t0, uint32_t step) {
         float* b = buf[k & 1u];
         const uint32_t j0 = s + k * BIG_CHUNK, m = min((uint32_t)BIG_CHUNK, e - j0);
-        for (uint32_t t = threadIdx.x; t < m * 12u; t += T) {
+        for (uint32_t t = t0; t < m * 12u; t += step) {
             const uint32_t r = t / 12u, c = t - r * 12u;
             const uint32_t idx = rows_sorted[j0 + r];
             b[t] = c < 9u ? pis[(size_t)idx * 9 + c] : vs[(size_t)idx * 3 + (c - 9u)];
         }
     };
-    stage(0);
+    stage(0, threadIdx.x, T);
     __syncthreads();
     for (uint32_t k = 0; k < chunks; ++k) {
-        if (k + 1u < chunks) stage(k + 1u);
-        if (threadIdx.x < 12) {
-            const float* b = buf[k & 1u];
+        if (threadIdx.x >= 32) {
+            if (k + 1u < chunks) stage(k + 1u, threadIdx.x - 32u, T - 32);
+        } else if (threadIdx.x < 12) {
+            const float* b = buf[k & 1u] + threadIdx.x;
             const uint32_t m = min((uint32_t)BIG_CHUNK, e - (s + k * BIG_CHUNK));
-            for (uint32_t r = 0; r < m; ++r) acc = __fadd_rn(acc, b[r * 12u + threadIdx.x]);
+            uint32_t r = 0;
+            for (; r + 8u <= m; r += 8u) {
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = b[(r + u) * 12u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, x[u]);
+            }
+            for (; r < m; ++r) acc = __fadd_rn(acc, b[r * 12u]);
         }
         __syncthreads();
     }

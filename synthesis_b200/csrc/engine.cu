@@ -7,6 +7,7 @@
 // syn_engine_create fails with SYN_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +18,7 @@
 #include "selfplay.cuh"
 #include "match.cuh"
 #include "tpg2.cuh"
+#include "dedup.cuh"
 
 using namespace eng;
 
@@ -87,6 +89,8 @@ struct syn_engine {
     DevBuf<float> s_visits, s_q;
     DevBuf<uint8_t> s_csol, s_rsol, s_best;
     DevBuf<uint32_t> s_nodes;
+    // deduplicate workspace (dedup.cuh)
+    DevBuf<uint8_t> dd_ws, dd_io;
     // pending gather
     bool pending = false;
     uint32_t pend_games = 0;
@@ -383,6 +387,7 @@ void syn_engine_destroy(syn_engine* e) {
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();
     e->s_csol.release(); e->s_rsol.release(); e->s_best.release(); e->s_nodes.release();
+    e->dd_ws.release(); e->dd_io.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -719,6 +724,152 @@ int syn_engine_play(syn_engine* e, const uint8_t* moves, const uint32_t* n_moves
     if ((rc = deliver(e, status, b + off_st, n_games))) return rc;
     if (features && (rc = deliver(e, features, b + off_f, (size_t)n_games * 63 * 4))) return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SYN_OK;
+}
+
+// ---- ReplayBuffer::deduplicate (data.rs:196-235) on the device, see dedup.cuh
+static int dd_scan(syn_engine* e, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, uint32_t* total) {
+    const uint32_t nb = (n + dd::SCAN_TILE - 1) / dd::SCAN_TILE;
+    if (nb <= 1u) {
+        dd::scan_down_kernel<<<1, dd::T, 0, e->stream>>>(in, out, n, nullptr, total);
+        e->launches += 1;
+        return SYN_OK;
+    }
+    dd::scan_reduce_kernel<<<nb, dd::T, 0, e->stream>>>(in, n, tmp);
+    e->launches += 1;
+    int rc = dd_scan(e, tmp, tmp, nb, tmp + (nb + 63u) / 64u * 64u, nullptr);
+    if (rc) return rc;
+    dd::scan_down_kernel<<<nb, dd::T, 0, e->stream>>>(in, out, n, tmp, total);
+    e->launches += 1;
+    return SYN_OK;
+}
+
+int syn_engine_deduplicate(syn_engine* e, const uint64_t* my_bb, const uint64_t* op_bb, const float* pis, const float* vs, size_t n_rows,
+                           syn_flat_batch* out, syn_stats* stats) {
+    if (!e || !out) return fail(SYN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is in flight on this engine");
+    out->len = 0;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n_rows == 0) return SYN_OK;
+    if (!my_bb || !op_bb || !pis || !vs) return fail(SYN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_rows > (1ull << 30)) return fail(SYN_ERR_CAPACITY, "deduplicate handles at most 2^30 rows per call, got %zu", n_rows);
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->h2d = 0; e->d2h = 0; e->launches = 0;
+    const uint32_t n = (uint32_t)n_rows;
+    uint32_t cap = 1024;
+    while (cap < 2u * n) cap <<= 1;
+    const uint32_t nblk = (n + dd::RS_TILE - 1) / dd::RS_TILE;
+    const uint32_t hist_n = 256u * nblk;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    // ---- workspace
+    const size_t scan_m = std::max<size_t>(n, hist_n);
+    const size_t scan_tmp = al((scan_m / dd::SCAN_TILE + 64) * 2 * 4 + 4096);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
+    const size_t o_srow = take((size_t)cap * 4), o_sfirst = take((size_t)cap * 4);
+    const size_t o_ka = take((size_t)(n + 1) * 4), o_va = take((size_t)(n + 1) * 4), o_kb = take((size_t)(n + 1) * 4), o_vb = take((size_t)(n + 1) * 4);
+    const size_t o_hist = take((size_t)hist_n * 4), o_tmp = take(scan_tmp), o_big = take((size_t)(n / dd::BIG + 2) * 4), o_scal = take(256);
+    CUDA_TRY(e->dd_ws.reserve(off));
+    uint8_t* w = e->dd_ws.p;
+    uint32_t *slot_row = (uint32_t*)(w + o_srow), *slot_first = (uint32_t*)(w + o_sfirst);
+    uint32_t *ka = (uint32_t*)(w + o_ka), *va = (uint32_t*)(w + o_va), *kb = (uint32_t*)(w + o_kb), *vb = (uint32_t*)(w + o_vb);
+    uint32_t *hist = (uint32_t*)(w + o_hist), *tmp = (uint32_t*)(w + o_tmp), *big_list = (uint32_t*)(w + o_big);
+    uint32_t *n_groups = (uint32_t*)(w + o_scal), *big_count = n_groups + 1;
+    // ---- inputs: used in place when they already live on the device
+    const void* src[4] = {my_bb, op_bb, pis, vs};
+    const size_t elt[4] = {8, 8, 36, 12};
+    const void* in[4];
+    size_t io = 0, in_off[4];
+    for (int i = 0; i < 4; ++i) { in_off[i] = io; if (!is_device_ptr(src[i])) io += al(elt[i] * n); }
+    // ---- outputs: staged when the destination is host memory (sized by the caller's capacity, at most n)
+    const size_t ocap = std::min<size_t>(out->capacity, n);
+    void* dst[6] = {out->my_bb, out->op_bb, out->num, out->states, out->pis, out->vs};
+    const size_t oelt[6] = {8, 8, 4, 252, 36, 12};
+    size_t out_off[6];
+    for (int i = 0; i < 6; ++i) { out_off[i] = io; if (dst[i] && !is_device_ptr(dst[i])) io += al(oelt[i] * ocap); }
+    CUDA_TRY(e->dd_io.reserve(io ? io : 256));
+    for (int i = 0; i < 4; ++i) {
+        if (is_device_ptr(src[i])) { in[i] = src[i]; continue; }
+        CUDA_TRY(cudaMemcpyAsync(e->dd_io.p + in_off[i], src[i], elt[i] * n, cudaMemcpyHostToDevice, e->stream));
+        e->h2d += elt[i] * n;
+        in[i] = e->dd_io.p + in_off[i];
+    }
+    const uint64_t* d_my = (const uint64_t*)in[0];
+    const uint64_t* d_op = (const uint64_t*)in[1];
+    const float* d_pis = (const float*)in[2];
+    const float* d_vs = (const float*)in[3];
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    const uint32_t gridn = (n + dd::T - 1) / dd::T;
+    // ---- group keys: rep[i] = first row holding row i's position
+    dd::fill_kernel<<<e->sm_count * 8, dd::T, 0, e->stream>>>(slot_row, (size_t)2 * cap, dd::EMPTY); // slot_row and slot_first are adjacent (cap * 4 is a multiple of 256)
+    dd::insert_kernel<<<gridn, dd::T, 0, e->stream>>>(d_my, d_op, n, slot_row, slot_first, cap - 1u, ka);
+    dd::rep_kernel<<<gridn, dd::T, 0, e->stream>>>(ka, slot_first, n);
+    e->launches += 3;
+    // ---- stable sort of (rep, row) by rep
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)n) ++bits;
+    uint32_t *kin = ka, *vin = nullptr, *kout = kb, *vout = vb;
+    for (int shift = 0; shift < bits; shift += 8) {
+        dd::rs_hist_kernel<<<nblk, dd::T, 0, e->stream>>>(kin, n, shift, hist, nblk);
+        e->launches += 1;
+        int rc = dd_scan(e, hist, hist, hist_n, tmp, nullptr);
+        if (rc) return rc;
+        dd::rs_scatter_kernel<<<nblk, dd::T, 0, e->stream>>>(kin, vin, kout, vout, n, shift, hist, nblk);
+        e->launches += 1;
+        uint32_t* nk = kout; uint32_t* nv = vout;
+        kout = kin; vout = (vin ? vin : va);
+        kin = nk; vin = nv;
+    }
+    uint32_t *rep_sorted = kin, *rows_sorted = vin, *gid = kout, *gstart = vout;
+    // ---- group boundaries and start table
+    dd::heads_kernel<<<gridn, dd::T, 0, e->stream>>>(rep_sorted, n, gid);
+    e->launches += 1;
+    {
+        int rc = dd_scan(e, gid, gid, n, tmp, n_groups);
+        if (rc) return rc;
+    }
+    dd::starts_kernel<<<gridn, dd::T, 0, e->stream>>>(rep_sorted, gid, n, n_groups, gstart);
+    e->launches += 1;
+    CUDA_TRY(cudaMemsetAsync(big_count, 0, 4, e->stream));
+    uint32_t U = 0;
+    CUDA_TRY(cudaMemcpyAsync(&U, n_groups, 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaGetLastError());
+    out->len = U;
+    if (U > out->capacity) return fail(SYN_ERR_CAPACITY, "deduplicate found %u distinct positions, caller provided room for %zu", U, out->capacity);
+    // ---- sums in row order, averages, features
+    dd::Out o;
+    void* tgt[6];
+    for (int i = 0; i < 6; ++i) tgt[i] = !dst[i] ? nullptr : (is_device_ptr(dst[i]) ? dst[i] : (void*)(e->dd_io.p + out_off[i]));
+    o.my_bb = (uint64_t*)tgt[0]; o.op_bb = (uint64_t*)tgt[1]; o.num = (uint32_t*)tgt[2];
+    o.states = (float*)tgt[3]; o.pis = (float*)tgt[4]; o.vs = (float*)tgt[5];
+    dd::reduce_kernel<<<(uint32_t)(((size_t)U * 16 + dd::T - 1) / dd::T), dd::T, 0, e->stream>>>(rows_sorted, gstart, n_groups, d_my, d_op, d_pis, d_vs, o,
+                                                                                                  big_list, big_count);
+    e->launches += 1;
+    uint32_t nbig = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nbig, big_count, 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (nbig) {
+        dd::reduce_big_kernel<<<nbig, dd::T, 0, e->stream>>>(rows_sorted, gstart, big_list, d_my, d_op, d_pis, d_vs, o);
+        e->launches += 1;
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    CUDA_TRY(cudaGetLastError());
+    for (int i = 0; i < 6; ++i)
+        if (dst[i] && !is_device_ptr(dst[i])) {
+            int rc = deliver(e, dst[i], e->dd_io.p + out_off[i], oelt[i] * U);
+            if (rc) return rc;
+        }
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (stats) {
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        stats->rows = U;
+        stats->device_ns = (uint64_t)((double)ms * 1e6);
+        stats->kernel_launches = e->launches;
+        stats->h2d_bytes = e->h2d;
+        stats->d2h_bytes = e->d2h + 8;
+    }
     return SYN_OK;
 }
 

@@ -11,6 +11,16 @@ _FIELDS = (("game_ids", np.uint64, ()), ("my_bb", np.uint64, ()), ("op_bb", np.u
            ("player", np.uint8, ()), ("states", np.float32, (63,)), ("pis", np.float32, (9,)), ("vs", np.float32, (3,)))
 
 
+class FlatBatch:
+    """data.rs:80-85: `states` [n][1][7][9] (Connect4::DIMS, connect4.rs:235), `pis` [n][9], `vs` [n][3]."""
+
+    def __init__(self, states, pis, vs):
+        self.states, self.pis, self.vs = states, pis, vs
+
+    def __len__(self):
+        return len(self.vs)
+
+
 class ReplayBuffer:
     def __init__(self, n: int = 0):  # data.rs:116-126 (n is only a capacity hint there too)
         self.game_id = 0
@@ -79,6 +89,14 @@ class ReplayBuffer:
     def _prefix(self, min_game_id: int) -> int:
         ge = np.nonzero(self.game_ids >= np.uint64(min_game_id))[0]
         return int(ge[0]) if len(ge) else len(self.game_ids)
+
+    # ---- data.rs:196-235
+    def deduplicate(self, engine) -> "FlatBatch":
+        """One row per distinct position, policy and value targets averaged over the rows that hold it.  Runs on the
+        GPU of `engine` (syn_engine_deduplicate); values are bit-identical to the reference's, rows come in order of
+        first occurrence where the reference's order is HashMap-random."""
+        out, _ = engine.deduplicate(self.my_bb, self.op_bb, self.pis, self.vs)
+        return FlatBatch(out["states"].reshape(-1, 1, 7, 9), out["pis"], out["vs"])
 
     # ---- construction from the C ABI's syn_experience arrays
     @staticmethod

@@ -158,6 +158,29 @@ class Engine:
                                            C.byref(stats)))
         return out, stats.as_dict()
 
+    # ---- ReplayBuffer::deduplicate (data.rs:196-235)
+    def deduplicate(self, my_bb, op_bb, pis, vs, states: bool = True):
+        """Merges rows with equal positions; sums in row order in f32, like the reference's loop.  Returns
+        (dict(states, pis, vs, my_bb, op_bb, num), stats); rows are ordered by first occurrence."""
+        my = np.ascontiguousarray(my_bb, dtype=np.uint64).reshape(-1)
+        op = np.ascontiguousarray(op_bb, dtype=np.uint64).reshape(-1)
+        n = my.size
+        pi = np.ascontiguousarray(pis, dtype=np.float32).reshape(n, 9)
+        v = np.ascontiguousarray(vs, dtype=np.float32).reshape(n, 3)
+        if op.size != n:
+            raise ValueError("my_bb and op_bb must have the same length")
+        out = dict(states=np.zeros((n, 63), np.float32) if states else None, pis=np.zeros((n, 9), np.float32),
+                   vs=np.zeros((n, 3), np.float32), my_bb=np.zeros(n, np.uint64), op_bb=np.zeros(n, np.uint64),
+                   num=np.zeros(n, np.uint32))
+        fb = L.SynFlatBatch()
+        fb.capacity = n
+        for k, a in out.items():
+            setattr(fb, k, a.ctypes.data if a is not None else None)
+        stats = L.SynStats()
+        L.check(self._lib.syn_engine_deduplicate(self._h, _ptr(my), _ptr(op), _ptr(pi), _ptr(v), n, C.byref(fb), C.byref(stats)))
+        u = int(fb.len)
+        return {k: (a[:u] if a is not None else None) for k, a in out.items()}, stats.as_dict()
+
     # ---- Policy::eval for Connect4Net on a batch
     def eval(self, my_bb, op_bb):
         my = np.ascontiguousarray(my_bb, dtype=np.uint64).reshape(-1)

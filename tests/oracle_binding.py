@@ -156,6 +156,20 @@ class Oracle:
         d["cache_hits"], d["cache_misses"] = hits.value, misses.value
         return d
 
+    def deduplicate(self, my_bb, op_bb, pis, vs):
+        my = np.ascontiguousarray(my_bb, np.uint64)
+        op = np.ascontiguousarray(op_bb, np.uint64)
+        n = my.size
+        pi = np.ascontiguousarray(pis, np.float32).reshape(n, 9)
+        v = np.ascontiguousarray(vs, np.float32).reshape(n, 3)
+        out = dict(states=np.zeros((n, 63), np.float32), pis=np.zeros((n, 9), np.float32), vs=np.zeros((n, 3), np.float32),
+                   my_bb=np.zeros(n, np.uint64), op_bb=np.zeros(n, np.uint64), num=np.zeros(n, np.uint32))
+        self.lib.orc_deduplicate.restype = C.c_size_t
+        self.lib.orc_deduplicate.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_size_t] + [C.c_void_p] * 6
+        u = self.lib.orc_deduplicate(_p(my), _p(op), _p(pi), _p(v), n, n, _p(out["states"]), _p(out["pis"]), _p(out["vs"]),
+                                     _p(out["my_bb"]), _p(out["op_bb"]), _p(out["num"]))
+        return {k: a[:u] for k, a in out.items()}
+
     def mlp_eval(self, weights, my_bb, op_bb, flags=0):
         w = np.ascontiguousarray(weights, np.float32)
         my = np.ascontiguousarray(my_bb, np.uint64)

@@ -604,3 +604,86 @@ def test_backprop_with_subnormal_values_is_bit_exact(engine, oracle):
     assert np.any((a["vs"][:n, 1] > 0) & (a["vs"][:n, 1] < 1.1754944e-38)), "no subnormal Q reached the experience rows"
     for k in a:
         assert a[k][:n].tobytes() == ra[k].tobytes(), k
+
+
+# ---------------------------------------------------------------- f1: ReplayBuffer::deduplicate (data.rs:196-235)
+def _dedup_inputs(rng, n_rows, n_keys, heavy=0):
+    """Rows over `n_keys` distinct reachable positions; `heavy` extra rows all hold the empty board (the group every
+    self-play game contributes to), targets are arbitrary f32 so that the order of the additions matters."""
+    pos = random_positions(rng, n_keys, max_plies=30)
+    which = rng.integers(0, n_keys, n_rows)
+    my = np.array([pos[k].my_bb for k in which] + [0] * heavy, np.uint64)
+    op = np.array([pos[k].op_bb for k in which] + [0] * heavy, np.uint64)
+    n = n_rows + heavy
+    pis = (rng.random((n, 9), np.float32) * np.float32(3.0)).astype(np.float32)
+    vs = rng.standard_normal((n, 3)).astype(np.float32)
+    perm = rng.permutation(n)
+    return my[perm], op[perm], pis[perm], vs[perm]
+
+
+@pytest.mark.parametrize("n_rows,n_keys,heavy", [(1, 1, 0), (17, 3, 0), (5000, 5000, 0), (40000, 900, 0), (30000, 200, 9000), (2049, 1, 0)])
+def test_deduplicate_bit_exact(engine, oracle, n_rows, n_keys, heavy):
+    """Every merged row equals the oracle's bit for bit (sums in buffer order, f32), groups in order of first occurrence;
+    sizes cover one row, one group, all rows distinct, a group larger than the per-CTA threshold (dedup.cuh BIG) and
+    multi-tile sorts."""
+    rng = np.random.default_rng(n_rows * 31 + n_keys)
+    my, op, pis, vs = _dedup_inputs(rng, n_rows, n_keys, heavy)
+    got, st = engine.deduplicate(my, op, pis, vs)
+    want = oracle.deduplicate(my, op, pis, vs)
+    assert st["rows"] == len(want["num"]) and st["kernel_launches"] > 0
+    assert_rows_equal(got, want, "deduplicate")
+    assert int(got["num"].sum()) == len(my)
+
+
+def test_deduplicate_of_a_gather_and_edge_cases(engine, oracle):
+    """The call the training loop makes (alpha_zero.rs:53-58): deduplicate what gather_experience produced; plus the
+    empty buffer, a too-small destination (SYN_ERR_CAPACITY) and the ReplayBuffer mirror."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=50, sample_actions_until=10)
+    a, _, _ = engine.gather(cfg, L.LEAF_ROLLOUT, 0, 300, 11)
+    got, st = engine.deduplicate(a["my_bb"], a["op_bb"], a["pis"], a["vs"])
+    want = oracle.deduplicate(a["my_bb"], a["op_bb"], a["pis"], a["vs"])
+    assert_rows_equal(got, want, "deduplicate(gather)")
+    assert got["num"][0] == 300 and got["my_bb"][0] == 0 and got["op_bb"][0] == 0  # every game starts from Connect4::new()
+    assert len(got["num"]) < len(a["vs"])
+    buf = s.ReplayBuffer.from_arrays(300, a)
+    fb = buf.deduplicate(engine)
+    assert fb.states.shape == (len(want["num"]), 1, 7, 9) and fb.pis.tobytes() == want["pis"].tobytes() and fb.vs.tobytes() == want["vs"].tobytes()
+    assert fb.states.reshape(-1, 63).tobytes() == want["states"].tobytes()
+    empty, st0 = engine.deduplicate(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros((0, 9), np.float32), np.zeros((0, 3), np.float32))
+    assert len(empty["num"]) == 0 and st0["rows"] == 0
+    import ctypes as C
+    fbc = L.SynFlatBatch()
+    fbc.capacity = 5
+    small = np.zeros((5, 9), np.float32)
+    fbc.pis = small.ctypes.data
+    rc = engine._lib.syn_engine_deduplicate(engine._h, a["my_bb"].ctypes.data, a["op_bb"].ctypes.data, a["pis"].ctypes.data,
+                                            a["vs"].ctypes.data, len(a["vs"]), C.byref(fbc), None)
+    assert rc == L.SYN_ERR_CAPACITY and fbc.len == len(want["num"])
+
+
+def test_deduplicate_large_properties(engine):
+    """At a size the oracle is not run on: 4M rows over 300k keys.  Group sizes add up, every group's key is distinct,
+    groups come in order of first occurrence, a row-order-independent statistic (num-weighted mean of exactly
+    representable targets) is reproduced exactly, and a second run is bit-identical."""
+    rng = np.random.default_rng(5)
+    n, k = 4_000_000, 300_000
+    keys_my = rng.integers(0, 1 << 62, k, dtype=np.uint64)
+    keys_op = rng.integers(0, 1 << 62, k, dtype=np.uint64)
+    which = rng.integers(0, k, n)
+    which[:100_000] = 7  # one very large group
+    which = which[rng.permutation(n)]
+    my, op = keys_my[which], keys_op[which]
+    pis = (rng.integers(0, 16, (n, 9)) / 16.0).astype(np.float32)  # sums of these are exact in f32 in any order
+    vs = (rng.integers(0, 16, (n, 3)) / 16.0).astype(np.float32)
+    got, st = engine.deduplicate(my, op, pis, vs, states=False)
+    again, _ = engine.deduplicate(my, op, pis, vs, states=False)
+    for f in ("pis", "vs", "my_bb", "op_bb", "num"):
+        assert got[f].tobytes() == again[f].tobytes()
+    uniq, first, counts = np.unique(which, return_index=True, return_counts=True)
+    order = np.argsort(first)
+    assert len(got["num"]) == len(uniq) and np.array_equal(got["num"], counts[order].astype(np.uint32))
+    assert np.array_equal(got["my_bb"], keys_my[uniq[order]]) and np.array_equal(got["op_bb"], keys_op[uniq[order]])
+    sums = np.zeros((k, 9), np.float64)
+    np.add.at(sums, which, pis.astype(np.float64))
+    want = (sums[uniq[order]].astype(np.float32) / counts[order].astype(np.float32)[:, None]).astype(np.float32)
+    assert got["pis"].tobytes() == want.tobytes()

@@ -46,10 +46,11 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(L.SynRolloutCfg) == 72
     assert C.sizeof(L.SynExperience) == 3 * C.sizeof(C.c_size_t) + 8 * C.sizeof(C.c_void_p)
     assert C.sizeof(L.SynStats) == 8 * len(L.SynStats._fields_)
+    assert C.sizeof(L.SynFlatBatch) == 2 * C.sizeof(C.c_size_t) + 6 * C.sizeof(C.c_void_p)
     src = r'''
 #include "synthesis_b200.h"
 #include <stdio.h>
-int main(void) { printf("%zu %zu %zu %zu\n", sizeof(syn_mcts_cfg), sizeof(syn_rollout_cfg), sizeof(syn_experience), sizeof(syn_stats)); return 0; }
+int main(void) { printf("%zu %zu %zu %zu %zu\n", sizeof(syn_mcts_cfg), sizeof(syn_rollout_cfg), sizeof(syn_experience), sizeof(syn_stats), sizeof(syn_flat_batch)); return 0; }
 '''
     import subprocess
     import tempfile
@@ -60,7 +61,8 @@ int main(void) { printf("%zu %zu %zu %zu\n", sizeof(syn_mcts_cfg), sizeof(syn_ro
         exe = os.path.join(d, "sz")
         subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), p, "-o", exe])  # the header is plain C
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    assert sizes == [C.sizeof(L.SynMctsCfg), C.sizeof(L.SynRolloutCfg), C.sizeof(L.SynExperience), C.sizeof(L.SynStats)]
+    assert sizes == [C.sizeof(L.SynMctsCfg), C.sizeof(L.SynRolloutCfg), C.sizeof(L.SynExperience), C.sizeof(L.SynStats),
+                     C.sizeof(L.SynFlatBatch)]
 
 
 @pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
@@ -184,6 +186,39 @@ def test_replay_buffer_extend_and_keep_last_n_games(oracle):
     buf.new_game()
     buf.add(g, np.full(9, 1 / 9, np.float32), np.zeros(3, np.float32))
     assert buf.game_ids[-1] == 6 and buf.curr_steps() == 10 and buf.games[-1] == g
+
+
+def test_oracle_deduplicate_follows_the_reference_loop(oracle):
+    """orc_deduplicate against a line-by-line Python restatement of data.rs:196-235 (a dict keyed by the position —
+    Python dicts iterate in insertion order — f32 sums in buffer order, then sum / num as f32), on the rows of an
+    oracle gather and on hand-made rows whose sums depend on the order of the additions."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=30, sample_actions_until=10)
+    a, _, _ = oracle.gather(cfg.to_c(L.LEAF_ROLLOUT), 3, 0, 12, threads=2)
+    rng = np.random.default_rng(0)
+    hand_my = rng.integers(0, 3, 200).astype(np.uint64)
+    hand = dict(my_bb=hand_my, op_bb=np.zeros(200, np.uint64), pis=(rng.random((200, 9)) * 1e3).astype(np.float32) ** 3,
+                vs=rng.standard_normal((200, 3)).astype(np.float32))
+    for rows in (a, hand):
+        got = oracle.deduplicate(rows["my_bb"], rows["op_bb"], rows["pis"], rows["vs"])
+        stats = {}
+        for i in range(len(rows["vs"])):
+            key = (int(rows["my_bb"][i]), int(rows["op_bb"][i]))
+            st = stats.setdefault(key, dict(sum_pi=np.zeros(9, np.float32), sum_v=np.zeros(3, np.float32), num=0))
+            st["sum_pi"] = st["sum_pi"] + rows["pis"][i]
+            st["sum_v"] = st["sum_v"] + rows["vs"][i]
+            st["num"] += 1
+        assert len(got["num"]) == len(stats)
+        for g, (key, st) in enumerate(stats.items()):
+            assert (int(got["my_bb"][g]), int(got["op_bb"][g])) == key and got["num"][g] == st["num"]
+            assert got["pis"][g].tobytes() == (st["sum_pi"] / np.float32(st["num"])).astype(np.float32).tobytes()
+            assert got["vs"][g].tobytes() == (st["sum_v"] / np.float32(st["num"])).astype(np.float32).tobytes()
+    # StateStatistics::state is the features of the position (data.rs:203)
+    got = oracle.deduplicate(a["my_bb"], a["op_bb"], a["pis"], a["vs"])
+    first = {}
+    for i in range(len(a["vs"])):
+        first.setdefault((int(a["my_bb"][i]), int(a["op_bb"][i])), i)
+    assert got["states"].tobytes() == a["states"][list(first.values())].tobytes()
+    assert got["num"][0] == 12  # the empty board, once per game
 
 
 def test_split_games_follows_the_reference_schedule():
