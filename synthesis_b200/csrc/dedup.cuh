@@ -36,7 +36,6 @@ constexpr int RS_TILE = T * RS_K; // keys per CTA and pass
 constexpr int SCAN_IPT = 8;
 constexpr int SCAN_TILE = T * SCAN_IPT;
 constexpr uint32_t BIG = 2048;    // groups with more rows than this get a CTA of their own
-constexpr int BIG_CHUNK = 512;    // rows staged per step by reduce_big_kernel (2 x 24 KB of shared memory)
 
 __device__ __forceinline__ uint64_t hash_key(uint64_t my, uint64_t op) {
     uint64_t x = (my * 0x9E3779B97F4A7C15ull) ^ ((op + 0xD1B54A32D192ED03ull) * 0xBF58476D1CE4E5B9ull);
@@ -277,34 +276,47 @@ __global__ void __launch_bounds__(T) reduce_kernel(const uint32_t* __restrict__ 
     emit_header(o, g, my[first_row], op[first_row], cnt, c, 16);
 }
 
-// One CTA per big group: warps 1..7 gather the next BIG_CHUNK rows into shared memory while lanes 0..11 of warp 0
-// add the previous chunk in row order (the chain of dependent f32 additions is the critical path of the whole
-// call: 4 cycles per row, loads hoisted eight rows ahead).
-__global__ void __launch_bounds__(T) reduce_big_kernel(const uint32_t* __restrict__ rows_sorted, const uint32_t* __restrict__ gstart,
-                                                       const uint32_t* __restrict__ big_list, const uint64_t* __restrict__ my,
-                                                       const uint64_t* __restrict__ op, const float* __restrict__ pis,
-                                                       const float* __restrict__ vs, Out o) {
-    __shared__ float buf[2][BIG_CHUNK * 12];
+// One CTA of 512 threads per big group: warps 1..15 gather the next BIG_CHUNK rows into shared memory (two rows per
+// thread, every load of a chunk issued before the first one is used) while lanes 0..11 of warp 0 add the previous
+// chunk in row order.  The chain of dependent f32 additions (4 cycles per row) is the critical path of the call.
+constexpr int BIG_T = 512;
+constexpr int BIG_STAGERS = BIG_T - 32;
+constexpr int BIG_CHUNK = 2 * BIG_STAGERS; // 960 rows, 2 x 45 KB of shared memory
+constexpr size_t BIG_SMEM = 2 * (size_t)BIG_CHUNK * 12 * sizeof(float);
+
+__global__ void __launch_bounds__(BIG_T) reduce_big_kernel(const uint32_t* __restrict__ rows_sorted, const uint32_t* __restrict__ gstart,
+                                                           const uint32_t* __restrict__ big_list, const uint64_t* __restrict__ my,
+                                                           const uint64_t* __restrict__ op, const float* __restrict__ pis,
+                                                           const float* __restrict__ vs, Out o) {
+    extern __shared__ __align__(16) float big_buf[]; // [2][BIG_CHUNK * 12]
     const uint32_t g = big_list[blockIdx.x];
     const uint32_t s = gstart[g], e = gstart[g + 1u], cnt = e - s;
     const uint32_t chunks = (cnt + BIG_CHUNK - 1) / BIG_CHUNK;
     float acc = 0.0f;
-    auto stage = [&](uint32_t k, uint32_t t0, uint32_t step) {
-        float* b = buf[k & 1u];
+    auto stage = [&](uint32_t k) { // threads 32 .. BIG_T-1
+        float* b = big_buf + (k & 1u) * (BIG_CHUNK * 12);
         const uint32_t j0 = s + k * BIG_CHUNK, m = min((uint32_t)BIG_CHUNK, e - j0);
-        for (uint32_t t = t0; t < m * 12u; t += step) {
-            const uint32_t r = t / 12u, c = t - r * 12u;
-            const uint32_t idx = rows_sorted[j0 + r];
-            b[t] = c < 9u ? pis[(size_t)idx * 9 + c] : vs[(size_t)idx * 3 + (c - 9u)];
+        const uint32_t r0 = threadIdx.x - 32u, r1 = r0 + BIG_STAGERS;
+        const uint32_t i0 = r0 < m ? rows_sorted[j0 + r0] : 0u, i1 = r1 < m ? rows_sorted[j0 + r1] : 0u;
+        float x0[12], x1[12];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            x0[c] = r0 < m ? (c < 9 ? pis[(size_t)i0 * 9 + c] : vs[(size_t)i0 * 3 + (c - 9)]) : 0.0f;
+            x1[c] = r1 < m ? (c < 9 ? pis[(size_t)i1 * 9 + c] : vs[(size_t)i1 * 3 + (c - 9)]) : 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < 12; c += 4) {
+            *reinterpret_cast<float4*>(b + r0 * 12u + c) = make_float4(x0[c], x0[c + 1], x0[c + 2], x0[c + 3]);
+            *reinterpret_cast<float4*>(b + r1 * 12u + c) = make_float4(x1[c], x1[c + 1], x1[c + 2], x1[c + 3]);
         }
     };
-    stage(0, threadIdx.x, T);
+    if (threadIdx.x >= 32) stage(0);
     __syncthreads();
     for (uint32_t k = 0; k < chunks; ++k) {
         if (threadIdx.x >= 32) {
-            if (k + 1u < chunks) stage(k + 1u, threadIdx.x - 32u, T - 32);
+            if (k + 1u < chunks) stage(k + 1u);
         } else if (threadIdx.x < 12) {
-            const float* b = buf[k & 1u] + threadIdx.x;
+            const float* b = big_buf + (k & 1u) * (BIG_CHUNK * 12) + threadIdx.x;
             const uint32_t m = min((uint32_t)BIG_CHUNK, e - (s + k * BIG_CHUNK));
             uint32_t r = 0;
             for (; r + 8u <= m; r += 8u) {
@@ -325,7 +337,7 @@ __global__ void __launch_bounds__(T) reduce_big_kernel(const uint32_t* __restric
         else { if (o.vs) o.vs[(size_t)g * 3 + (c - 9)] = avg; }
     }
     const uint32_t first_row = rows_sorted[s];
-    emit_header(o, g, my[first_row], op[first_row], cnt, threadIdx.x, T);
+    emit_header(o, g, my[first_row], op[first_row], cnt, threadIdx.x, BIG_T);
 }
 
 } // namespace dd

@@ -850,7 +850,8 @@ int syn_engine_deduplicate(syn_engine* e, const uint64_t* my_bb, const uint64_t*
     CUDA_TRY(cudaMemcpyAsync(&nbig, big_count, 4, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (nbig) {
-        dd::reduce_big_kernel<<<nbig, dd::T, 0, e->stream>>>(rows_sorted, gstart, big_list, d_my, d_op, d_pis, d_vs, o);
+        CUDA_TRY(cudaFuncSetAttribute(dd::reduce_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dd::BIG_SMEM));
+        dd::reduce_big_kernel<<<nbig, dd::BIG_T, dd::BIG_SMEM, e->stream>>>(rows_sorted, gstart, big_list, d_my, d_op, d_pis, d_vs, o);
         e->launches += 1;
     }
     CUDA_TRY(cudaEventRecord(e->ev1, e->stream));

@@ -56,6 +56,22 @@ class Connect4Net:
             p[f"l_{l + 1}.bias"] = blob[off:off + o].copy(); off += o
         return Connect4Net(p)
 
+    @staticmethod
+    def load_ot(path) -> "Connect4Net":
+        """`vs.load(path)` for the VarStore of Connect4Net (alpha_zero.rs:192-194): the variables are matched by name,
+        and like tch a missing or mis-shaped one is an error."""
+        from .weights import read_ot
+        named = read_ot(path)
+        missing = [f"l_{l + 1}.{k}" for l in range(5) for k in ("weight", "bias") if f"l_{l + 1}.{k}" not in named]
+        if missing:
+            raise KeyError(f"{path}: cannot find {missing[0]} in the archive")
+        return Connect4Net(named)
+
+    def save_ot(self, path) -> None:
+        """`vs.save(path)` (alpha_zero.rs:37, 102)."""
+        from .weights import write_ot
+        write_ot(path, self.params)
+
     def blob(self) -> np.ndarray:
         """l_1.weight, l_1.bias, ..., l_5.bias flattened (the layout syn_engine_set_weights takes)."""
         parts = []
