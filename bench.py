@@ -222,7 +222,7 @@ def run_reference(args):
         "positions_per_s": tot_rows / tot_t, "gpu_launches": 0,
         "note": "restated reference CPU path (C++ oracle, g++ -O3 -march=native -ffp-contract=off); the Rust reference cannot be built here",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -398,15 +398,34 @@ def run_ours(args):
             "positions_per_s": rows / t_dev, "leaf_evals_per_s": leafs / t_dev, "wall_ms_per_step": 1e3 * t_wall / max(1, args.steps),
             "group_lanes": args.group_lanes,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # Libraries write to fd 1 behind Python's back (NCCL prints its version line there when NCCL_DEBUG is set): everything
+    # but the JSON line goes to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
