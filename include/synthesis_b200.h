@@ -255,6 +255,36 @@ typedef struct {
 int syn_engine_deduplicate(syn_engine* e, const uint64_t* my_bb, const uint64_t* op_bb, const float* pis, const float* vs,
                            size_t n_rows, syn_flat_batch* out, syn_stats* stats);
 
+/* Hyper-parameters of one training pass: tch `nn::Adam::default()` (beta1 0.9, beta2 0.999, eps 1e-8; L2 weight decay
+ * added to the gradient, alpha_zero.rs:33-36), the learning rate of the current iteration (LearningConfig::lr_schedule,
+ * alpha_zero.rs:62-70) and the loss weights / batch size of synthesis/src/config.rs:40-56. */
+typedef struct {
+    float lr;
+    float beta1, beta2, eps;
+    float weight_decay;   /* LearningConfig::weight_decay */
+    float policy_weight;  /* LearningConfig::policy_weight */
+    float value_weight;   /* LearningConfig::value_weight */
+    uint32_t batch_size;  /* LearningConfig::batch_size; the device learner supports 32 */
+} syn_train_cfg;
+
+/* Replaces the batch loop of alpha_zero (alpha_zero.rs:73-92): n_batches optimizer steps on the engine's CURRENT
+ * weights, batch k = rows batch_index[k][0..batch_size) of the FlatBatch given as (my_bb, op_bb, pis, vs) — features are
+ * synthesised from the bitboards.  batch_index is what BatchRandSampler (data.rs:6-64) yields: chunks of a random
+ * permutation, last partial chunk dropped; the permutation is the caller's (torch's randperm stream is not
+ * reproduced).  Per step: forward, log_softmax, kl_div(Reduction::Sum)/batch_size per head, policy_weight*pi_loss +
+ * value_weight*v_loss, backward, Adam.  losses (optional, [n_batches][2]) = {pi_loss, v_loss} per step as the reference
+ * accumulates them.  Adam's moments and step count persist in the engine across calls (syn_engine_reset_optimizer
+ * clears them); afterwards gathers on this engine search with the updated weights.  fp32 throughout; results agree
+ * with libtorch's CPU ops to ~1e-5 relative per step (summation order differs). */
+int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my_bb, const uint64_t* op_bb, const float* pis,
+                     const float* vs, size_t n_rows, const uint32_t* batch_index, uint32_t n_batches, float* losses,
+                     syn_stats* stats);
+int syn_engine_reset_optimizer(syn_engine* e);
+
+/* Replaces `vs.save` (alpha_zero.rs:37, 102) as far as the engine is concerned: the current fp32 weights in the blob
+ * layout of syn_engine_set_weights (host or device destination). */
+int syn_engine_get_weights(syn_engine* e, float* blob, size_t n_floats);
+
 /* Optional per-row trace of the NEXT gather (arrays of `capacity` rows like syn_experience, host or
  * device; NULL to disable): the action played from the row's state, nodes.len() of that ply's
  * tree, and the root's child visit counts by column.  Not part of the reference's ReplayBuffer;

@@ -74,6 +74,11 @@ class SynFlatBatch(C.Structure):
     ]
 
 
+class SynTrainCfg(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("policy_weight", C.c_float), ("value_weight", C.c_float), ("batch_size", C.c_uint32)]
+
+
 class SynStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "explores", "leaf_evals", "rows", "games", "trees", "nodes", "select_levels", "children_scanned",
@@ -89,7 +94,7 @@ EXPORTED_SYMBOLS = (
     "syn_abi_version", "syn_build_info", "syn_last_error", "syn_engine_create", "syn_engine_destroy",
     "syn_engine_set_weights", "syn_engine_gather", "syn_engine_gather_launch", "syn_engine_gather_wait",
     "syn_engine_search", "syn_engine_match", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode", "syn_engine_debug_counters",
-    "syn_engine_deduplicate",
+    "syn_engine_deduplicate", "syn_engine_train", "syn_engine_reset_optimizer", "syn_engine_get_weights",
 )
 
 _lib = None
@@ -130,6 +135,9 @@ def load():
     lib.syn_engine_set_group_lanes.argtypes = [vp, i32]
     lib.syn_engine_set_mlp_mode.argtypes = [vp, i32]
     lib.syn_engine_debug_counters.argtypes = [vp, vp, u32]
+    lib.syn_engine_train.argtypes = [vp, C.POINTER(SynTrainCfg), vp, vp, vp, vp, C.c_size_t, vp, u32, vp, C.POINTER(SynStats)]
+    lib.syn_engine_reset_optimizer.argtypes = [vp]
+    lib.syn_engine_get_weights.argtypes = [vp, vp, C.c_size_t]
     lib.syn_engine_deduplicate.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(SynFlatBatch), C.POINTER(SynStats)]
     _lib = lib
     return lib

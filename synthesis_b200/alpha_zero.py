@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib as L
 from .config import LearningConfig, MCTSConfig, RolloutConfig, ValueTarget
 from .connect4 import Connect4
-from .data import ReplayBuffer
+from .data import BatchRandSampler, FlatBatch, ReplayBuffer
 from .engine import Engine
 from .policies import Connect4Net, RolloutPolicy
 
@@ -54,6 +54,53 @@ def gather_experience(cfg: LearningConfig, policy, buffer: ReplayBuffer, seed: i
     buffer.keep_last_n_games(cfg.games_to_keep - cfg.games_per_train)
     buffer.extend(worker)
     return stats if return_stats else None
+
+
+def lr_for_iteration(cfg: LearningConfig, i_iter: int) -> float:
+    """alpha_zero.rs:62-70: the last schedule entry whose iteration number is <= i_iter + 1."""
+    return [lr for it, lr in cfg.lr_schedule if it <= i_iter + 1][-1]
+
+
+def train_on(cfg: LearningConfig, dedup: FlatBatch, lr: float, engine: Engine, rng):
+    """The epoch loop of alpha_zero (alpha_zero.rs:73-100) on the engine's current weights: per epoch a fresh
+    BatchRandSampler(drop_last) over the deduplicated rows, one Adam step per batch, all on the device
+    (syn_engine_train; the weights stay in HBM for the next gather).  Returns the per-epoch [pi_loss, v_loss] the
+    reference prints (sum over batches * batch_size / n)."""
+    n = len(dedup)
+    epochs = []
+    for _ in range(cfg.num_epochs):
+        batches = BatchRandSampler(n, cfg.batch_size, True, rng).all_batches()
+        if len(batches) == 0:
+            epochs.append([0.0, 0.0])
+            continue
+        losses, _ = engine.train(dedup.my_bb, dedup.op_bb, dedup.pis, dedup.vs, batches, lr, weight_decay=cfg.weight_decay,
+                                 policy_weight=cfg.policy_weight, value_weight=cfg.value_weight, batch_size=cfg.batch_size)
+        tot = losses.astype(np.float32).sum(0, dtype=np.float32) * np.float32(cfg.batch_size) / np.float32(n)
+        epochs.append([float(tot[0]), float(tot[1])])
+    return epochs
+
+
+def alpha_zero(cfg: LearningConfig, policy: Connect4Net = None, *, engine: Engine = None, device: int = 0, on_iteration=None):
+    """`alpha_zero::<Connect4, Connect4Net, 9>(cfg)` (alpha_zero.rs:16-118) with every stage on the GPU: gather ->
+    deduplicate -> train, the weights never leaving HBM between iterations.  File outputs (model_{i}.ot, latest_*.npy,
+    git metadata) are the caller's business: `on_iteration(i_iter, engine, buffer, dedup, epoch_losses)` is called where
+    the reference saves them.  Returns the trained Connect4Net."""
+    n = int(cfg.games_per_train)
+    eng = engine or engine_for(device, min(max(n, 32), 18944), int(cfg.rollout_cfg.num_explores))
+    policy = policy or Connect4Net.new(cfg.seed)
+    eng.set_weights(policy.blob())
+    eng.reset_optimizer()
+    rng = np.random.default_rng(cfg.seed)
+    buffer = ReplayBuffer(256_000)
+    for i_iter in range(cfg.num_iterations):
+        arrays, _, _ = eng.gather(cfg.rollout_cfg, L.LEAF_NN, 0, n, i_iter)
+        buffer.keep_last_n_games(cfg.games_to_keep - cfg.games_per_train)
+        buffer.extend(ReplayBuffer.from_arrays(n, arrays))
+        dedup = buffer.deduplicate(eng)
+        epochs = train_on(cfg, dedup, lr_for_iteration(cfg, i_iter), eng, rng)
+        if on_iteration is not None:
+            on_iteration(i_iter, eng, buffer, dedup, epochs)
+    return Connect4Net.from_blob(eng.get_weights())
 
 
 class MCTS:

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 #include "match.cuh"
 #include "tpg2.cuh"
 #include "dedup.cuh"
+#include "train.cuh"
 
 using namespace eng;
 
@@ -89,6 +91,10 @@ struct syn_engine {
     DevBuf<float> s_visits, s_q;
     DevBuf<uint8_t> s_csol, s_rsol, s_best;
     DevBuf<uint32_t> s_nodes;
+    // learner state (train.cuh): Adam moments in the padded parameter layout, optimizer step count
+    DevBuf<float> adam_m, adam_v;
+    DevBuf<uint8_t> tr_io;
+    uint64_t adam_t = 0;
     // deduplicate workspace (dedup.cuh)
     DevBuf<uint8_t> dd_ws, dd_io;
     // pending gather
@@ -387,7 +393,7 @@ void syn_engine_destroy(syn_engine* e) {
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();
     e->s_csol.release(); e->s_rsol.release(); e->s_best.release(); e->s_nodes.release();
-    e->dd_ws.release(); e->dd_io.release();
+    e->dd_ws.release(); e->dd_io.release(); e->adam_m.release(); e->adam_v.release(); e->tr_io.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -870,6 +876,109 @@ int syn_engine_deduplicate(syn_engine* e, const uint64_t* my_bb, const uint64_t*
         stats->kernel_launches = e->launches;
         stats->h2d_bytes = e->h2d;
         stats->d2h_bytes = e->d2h + 8;
+    }
+    return SYN_OK;
+}
+
+// ---- the learner's inner loop (alpha_zero.rs:73-92) on the device, see train.cuh
+int syn_engine_reset_optimizer(syn_engine* e) {
+    if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(e->adam_m.reserve(trn::P_FLOATS));
+    CUDA_TRY(e->adam_v.reserve(trn::P_FLOATS));
+    CUDA_TRY(cudaMemsetAsync(e->adam_m.p, 0, trn::P_FLOATS * sizeof(float), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->adam_v.p, 0, trn::P_FLOATS * sizeof(float), e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->adam_t = 0;
+    return SYN_OK;
+}
+
+int syn_engine_get_weights(syn_engine* e, float* blob, size_t n_floats) {
+    if (!e || !blob) return fail(SYN_ERR_INVALID_ARGUMENT, "engine or blob is NULL");
+    if (n_floats != SYN_N_WEIGHTS) return fail(SYN_ERR_INVALID_ARGUMENT, "expected %d floats, got %zu", SYN_N_WEIGHTS, n_floats);
+    if (!e->has_weights) return fail(SYN_ERR_NO_WEIGHTS, "syn_engine_set_weights has not been called");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaMemcpyAsync(blob, e->weights.p, n_floats * sizeof(float), cudaMemcpyDefault, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SYN_OK;
+}
+
+int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my_bb, const uint64_t* op_bb, const float* pis, const float* vs,
+                     size_t n_rows, const uint32_t* batch_index, uint32_t n_batches, float* losses, syn_stats* stats) {
+    if (!e || !cfg) return fail(SYN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is in flight on this engine");
+    if (!e->has_weights) return fail(SYN_ERR_NO_WEIGHTS, "syn_engine_set_weights has not been called");
+    if (cfg->batch_size != (uint32_t)trn::B)
+        return fail(SYN_ERR_UNSUPPORTED, "batch_size %u: the device learner is built for batches of %d (study-connect4/src/main.rs:21)", cfg->batch_size, trn::B);
+    if (!(cfg->beta1 >= 0.0f && cfg->beta1 < 1.0f && cfg->beta2 >= 0.0f && cfg->beta2 < 1.0f && cfg->eps > 0.0f && cfg->lr >= 0.0f))
+        return fail(SYN_ERR_INVALID_ARGUMENT, "bad Adam hyper-parameters");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n_batches == 0) return SYN_OK;
+    if (!my_bb || !op_bb || !pis || !vs || !batch_index || n_rows == 0) return fail(SYN_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_rows > 0xffffffffull) return fail(SYN_ERR_CAPACITY, "at most 2^32-1 rows");
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->h2d = 0; e->d2h = 0; e->launches = 0;
+    if (!e->adam_m.p) {
+        int rc = syn_engine_reset_optimizer(e);
+        if (rc) return rc;
+    }
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const void* src[5] = {my_bb, op_bb, pis, vs, batch_index};
+    const size_t bytes[5] = {8 * n_rows, 8 * n_rows, 36 * n_rows, 12 * n_rows, (size_t)n_batches * trn::B * 4};
+    size_t off[5], io = 0;
+    for (int i = 0; i < 5; ++i) { off[i] = io; if (!is_device_ptr(src[i])) io += al(bytes[i]); }
+    const size_t o_sched = io; io += al((size_t)n_batches * sizeof(float2));
+    const size_t o_loss = io; io += al((size_t)n_batches * 2 * sizeof(float));
+    CUDA_TRY(e->tr_io.reserve(io));
+    const void* in[5];
+    for (int i = 0; i < 5; ++i) {
+        if (is_device_ptr(src[i])) { in[i] = src[i]; continue; }
+        CUDA_TRY(cudaMemcpyAsync(e->tr_io.p + off[i], src[i], bytes[i], cudaMemcpyHostToDevice, e->stream));
+        e->h2d += bytes[i];
+        in[i] = e->tr_io.p + off[i];
+    }
+    // bias corrections in double like torch::optim::Adam::step, one pair per optimizer step
+    std::vector<float2> sched(n_batches);
+    for (uint32_t k = 0; k < n_batches; ++k) {
+        const double t = (double)(e->adam_t + k + 1);
+        sched[k].x = (float)((double)cfg->lr / (1.0 - std::pow((double)cfg->beta1, t)));
+        sched[k].y = (float)std::sqrt(1.0 - std::pow((double)cfg->beta2, t));
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->tr_io.p + o_sched, sched.data(), (size_t)n_batches * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+    e->h2d += (size_t)n_batches * sizeof(float2);
+    CUDA_TRY(cudaMemsetAsync(e->error.p, 0, sizeof(int), e->stream));
+    trn::Params tp;
+    tp.blob = e->weights.p; tp.m = e->adam_m.p; tp.v = e->adam_v.p;
+    tp.my = (const uint64_t*)in[0]; tp.op = (const uint64_t*)in[1]; tp.pis = (const float*)in[2]; tp.vs = (const float*)in[3];
+    tp.batch_idx = (const uint32_t*)in[4]; tp.sched = (const float2*)(e->tr_io.p + o_sched);
+    tp.losses = (float*)(e->tr_io.p + o_loss); tp.error = e->error.p;
+    tp.n_rows = (uint32_t)n_rows; tp.n_steps = n_batches;
+    tp.beta1 = cfg->beta1; tp.beta2 = cfg->beta2; tp.eps = cfg->eps; tp.wd = cfg->weight_decay; tp.pw = cfg->policy_weight; tp.vw = cfg->value_weight;
+    CUDA_TRY(cudaFuncSetAttribute(trn::train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trn::Smem)));
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    trn::train_kernel<<<1, trn::NT, sizeof(trn::Smem), e->stream>>>(tp);
+    CUDA_TRY(cudaGetLastError());
+    mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p); // the search kernels see the new weights
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    e->launches += 2;
+    e->adam_t += n_batches;
+    if (losses) {
+        int rc = deliver(e, losses, e->tr_io.p + o_loss, (size_t)n_batches * 2 * sizeof(float));
+        if (rc) return rc;
+    }
+    int derr = 0;
+    CUDA_TRY(cudaMemcpyAsync(&derr, e->error.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (derr) return fail(SYN_ERR_INVALID_ARGUMENT, "batch_index holds a row >= n_rows (%zu)", n_rows);
+    if (stats) {
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        stats->rows = (uint64_t)n_batches * trn::B;
+        stats->device_ns = (uint64_t)((double)ms * 1e6);
+        stats->kernel_launches = e->launches;
+        stats->h2d_bytes = e->h2d;
+        stats->d2h_bytes = e->d2h + 4;
     }
     return SYN_OK;
 }

@@ -11,11 +11,40 @@ _FIELDS = (("game_ids", np.uint64, ()), ("my_bb", np.uint64, ()), ("op_bb", np.u
            ("player", np.uint8, ()), ("states", np.float32, (63,)), ("pis", np.float32, (9,)), ("vs", np.float32, (3,)))
 
 
-class FlatBatch:
-    """data.rs:80-85: `states` [n][1][7][9] (Connect4::DIMS, connect4.rs:235), `pis` [n][9], `vs` [n][3]."""
+class BatchRandSampler:
+    """data.rs:6-64: batches of a random permutation of 0..n, the last partial batch dropped when `drop_last`.  Yields
+    index arrays (the reference index_selects its three tensors with them).  The permutation comes from `rng`
+    (numpy Generator); torch's randperm stream (tch::manual_seed, alpha_zero.rs:28) is not reproduced."""
 
-    def __init__(self, states, pis, vs):
-        self.states, self.pis, self.vs = states, pis, vs
+    def __init__(self, n: int, batch_size: int, drop_last: bool, rng):
+        self.inds = rng.permutation(int(n)).astype(np.uint32)
+        self.size, self.batch_size, self.index, self.drop_last = int(n), int(batch_size), 0, bool(drop_last)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        nxt = min(self.index + self.batch_size, self.size)
+        if self.index >= self.size or (self.drop_last and nxt - self.index < self.batch_size):
+            raise StopIteration
+        out = self.inds[self.index:nxt]
+        self.index = nxt
+        return out
+
+    def all_batches(self) -> np.ndarray:
+        """Every remaining full batch as one [n_batches][batch_size] array (what syn_engine_train takes)."""
+        full = (self.size - self.index) // self.batch_size
+        out = self.inds[self.index:self.index + full * self.batch_size].reshape(full, self.batch_size)
+        self.index += full * self.batch_size
+        return out
+
+
+class FlatBatch:
+    """data.rs:80-85: `states` [n][1][7][9] (Connect4::DIMS, connect4.rs:235), `pis` [n][9], `vs` [n][3]; the positions
+    themselves (my_bb, op_bb) ride along so that the device learner can synthesise `states` on chip."""
+
+    def __init__(self, states, pis, vs, my_bb=None, op_bb=None):
+        self.states, self.pis, self.vs, self.my_bb, self.op_bb = states, pis, vs, my_bb, op_bb
 
     def __len__(self):
         return len(self.vs)
@@ -96,7 +125,7 @@ class ReplayBuffer:
         GPU of `engine` (syn_engine_deduplicate); values are bit-identical to the reference's, rows come in order of
         first occurrence where the reference's order is HashMap-random."""
         out, _ = engine.deduplicate(self.my_bb, self.op_bb, self.pis, self.vs)
-        return FlatBatch(out["states"].reshape(-1, 1, 7, 9), out["pis"], out["vs"])
+        return FlatBatch(out["states"].reshape(-1, 1, 7, 9), out["pis"], out["vs"], out["my_bb"], out["op_bb"])
 
     # ---- construction from the C ABI's syn_experience arrays
     @staticmethod

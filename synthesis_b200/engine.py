@@ -181,6 +181,33 @@ class Engine:
         u = int(fb.len)
         return {k: (a[:u] if a is not None else None) for k, a in out.items()}, stats.as_dict()
 
+    # ---- the learner's batch loop (alpha_zero.rs:73-92)
+    def train(self, my_bb, op_bb, pis, vs, batch_index, lr: float, weight_decay: float = 0.0, policy_weight: float = 1.0,
+              value_weight: float = 1.0, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, batch_size: int = 32):
+        """One optimizer step per row of `batch_index` ([n_batches][batch_size] row indices) on the engine's current
+        weights.  Returns (losses [n_batches][2] = pi_loss, v_loss per step, stats)."""
+        my = np.ascontiguousarray(my_bb, dtype=np.uint64).reshape(-1)
+        op = np.ascontiguousarray(op_bb, dtype=np.uint64).reshape(-1)
+        n = my.size
+        pi = np.ascontiguousarray(pis, dtype=np.float32).reshape(n, 9)
+        v = np.ascontiguousarray(vs, dtype=np.float32).reshape(n, 3)
+        bi = np.ascontiguousarray(batch_index, dtype=np.uint32).reshape(-1, int(batch_size))
+        cfg = L.SynTrainCfg(lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, policy_weight=policy_weight,
+                            value_weight=value_weight, batch_size=int(batch_size))
+        losses = np.zeros((bi.shape[0], 2), np.float32)
+        stats = L.SynStats()
+        L.check(self._lib.syn_engine_train(self._h, C.byref(cfg), _ptr(my), _ptr(op), _ptr(pi), _ptr(v), n, _ptr(bi), bi.shape[0],
+                                           _ptr(losses), C.byref(stats)))
+        return losses, stats.as_dict()
+
+    def reset_optimizer(self):
+        L.check(self._lib.syn_engine_reset_optimizer(self._h))
+
+    def get_weights(self) -> np.ndarray:
+        blob = np.zeros(L.N_WEIGHTS, np.float32)
+        L.check(self._lib.syn_engine_get_weights(self._h, _ptr(blob), L.N_WEIGHTS))
+        return blob
+
     # ---- Policy::eval for Connect4Net on a batch
     def eval(self, my_bb, op_bb):
         my = np.ascontiguousarray(my_bb, dtype=np.uint64).reshape(-1)

@@ -687,3 +687,69 @@ def test_deduplicate_large_properties(engine):
     np.add.at(sums, which, pis.astype(np.float64))
     want = (sums[uniq[order]].astype(np.float32) / counts[order].astype(np.float32)[:, None]).astype(np.float32)
     assert got["pis"].tobytes() == want.tobytes()
+
+
+# ---------------------------------------------------------------- f2: the learner's batch loop (alpha_zero.rs:73-92)
+def _training_rows(engine, games=64, explores=40, seed=2):
+    cfg = s.study_connect4_rollout_cfg(num_explores=explores, sample_actions_until=20)
+    a, _, _ = engine.gather(cfg, L.LEAF_ROLLOUT, 0, games, seed)
+    d, _ = engine.deduplicate(a["my_bb"], a["op_bb"], a["pis"], a["vs"])
+    return d
+
+
+@pytest.mark.parametrize("weight_decay,pw,vw", [(0.0, 1.0, 1.0), (1e-2, 0.7, 1.3)])
+def test_train_matches_torch_fp32(engine, weight_decay, pw, vw):
+    """Floating-point kernel: per-step losses and the weights after 1, 4 and 40 Adam steps against the same steps in
+    PyTorch fp32 on the CPU (the ops the reference runs through tch).  Tolerance (north_star): 1e-3 abs/rel; observed
+    differences are ~1e-6 (summation order)."""
+    from torch_learner import TorchLearner
+    d = _training_rows(engine, games=160)
+    n = len(d["num"])
+    rng = np.random.default_rng(0)
+    net = s.Connect4Net.new(4)
+    batches = np.concatenate([s.BatchRandSampler(n, 32, True, rng).all_batches() for _ in range(2)])[:40]
+    assert len(batches) == 40
+    ref = TorchLearner(net.blob(), 1e-3, weight_decay, pw, vw)
+    engine.set_weights(net.blob())
+    engine.reset_optimizer()
+    done = 0
+    for upto in (1, 4, 40):
+        want_losses = ref.run(d["states"], d["pis"], d["vs"], batches[done:upto])
+        got_losses, st = engine.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], batches[done:upto], 1e-3, weight_decay, pw, vw)
+        assert st["rows"] == 32 * (upto - done) and st["kernel_launches"] == 2
+        assert np.allclose(got_losses, want_losses, rtol=1e-3, atol=1e-3), (upto, np.abs(got_losses - want_losses).max())
+        got, want = engine.get_weights(), ref.blob()
+        print("train parity after %d steps: max |dw| %.3g, max |dloss| %.3g" % (upto, np.abs(got - want).max(), np.abs(got_losses - want_losses).max()))
+        assert np.allclose(got, want, rtol=1e-3, atol=1e-3), (upto, np.abs(got - want).max())
+        done = upto
+    assert np.abs(engine.get_weights() - net.blob()).max() > 1e-3  # it did move
+    # the search kernels see the trained weights without a set_weights call
+    lg, pr = engine.eval(d["my_bb"][:64], d["op_bb"][:64])
+    import torch
+    with torch.no_grad():
+        pl, vl = ref.forward(torch.from_numpy(d["states"][:64]))
+    assert np.allclose(lg, pl.numpy(), rtol=1e-3, atol=2e-3) and np.allclose(pr, torch.softmax(vl, -1).numpy(), rtol=1e-3, atol=2e-3)
+
+
+def test_train_loss_decreases_and_edge_cases(engine):
+    """Twenty epochs over a small FlatBatch through the host mirror of the epoch loop: the KL losses fall; bad
+    arguments are refused the way the header says."""
+    d = _training_rows(engine, games=48)
+    fb = s.FlatBatch(d["states"].reshape(-1, 1, 7, 9), d["pis"], d["vs"], d["my_bb"], d["op_bb"])
+    cfg = s.LearningConfig(seed=0, logs="", lr_schedule=[(1, 1e-3)], weight_decay=1e-6, num_iterations=1, num_epochs=20, batch_size=32,
+                           policy_weight=1.0, value_weight=1.0, games_to_keep=100, games_per_train=48,
+                           rollout_cfg=s.study_connect4_rollout_cfg(num_explores=40))
+    engine.set_weights(s.Connect4Net.new(0).blob())
+    engine.reset_optimizer()
+    epochs = s.train_on(cfg, fb, s.lr_for_iteration(cfg, 0), engine, np.random.default_rng(1))
+    assert len(epochs) == 20 and epochs[-1][0] < 0.97 * epochs[0][0] and epochs[-1][1] < 0.5 * epochs[0][1], epochs
+    assert np.all(np.isfinite(engine.get_weights()))
+    n = len(d["num"])
+    with pytest.raises(L.EngineError) as ei:
+        engine.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], np.full((2, 32), n, np.uint32), 1e-3)
+    assert ei.value.code == L.SYN_ERR_INVALID_ARGUMENT
+    with pytest.raises(L.EngineError) as ei:
+        engine.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], np.zeros((2, 16), np.uint32), 1e-3, batch_size=16)
+    assert ei.value.code == L.SYN_ERR_UNSUPPORTED
+    losses, st = engine.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], np.zeros((0, 32), np.uint32), 1e-3)
+    assert losses.shape == (0, 2)

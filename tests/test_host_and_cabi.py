@@ -47,10 +47,11 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(L.SynExperience) == 3 * C.sizeof(C.c_size_t) + 8 * C.sizeof(C.c_void_p)
     assert C.sizeof(L.SynStats) == 8 * len(L.SynStats._fields_)
     assert C.sizeof(L.SynFlatBatch) == 2 * C.sizeof(C.c_size_t) + 6 * C.sizeof(C.c_void_p)
+    assert C.sizeof(L.SynTrainCfg) == 32
     src = r'''
 #include "synthesis_b200.h"
 #include <stdio.h>
-int main(void) { printf("%zu %zu %zu %zu %zu\n", sizeof(syn_mcts_cfg), sizeof(syn_rollout_cfg), sizeof(syn_experience), sizeof(syn_stats), sizeof(syn_flat_batch)); return 0; }
+int main(void) { printf("%zu %zu %zu %zu %zu %zu\n", sizeof(syn_mcts_cfg), sizeof(syn_rollout_cfg), sizeof(syn_experience), sizeof(syn_stats), sizeof(syn_flat_batch), sizeof(syn_train_cfg)); return 0; }
 '''
     import subprocess
     import tempfile
@@ -62,7 +63,7 @@ int main(void) { printf("%zu %zu %zu %zu %zu\n", sizeof(syn_mcts_cfg), sizeof(sy
         subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), p, "-o", exe])  # the header is plain C
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(L.SynMctsCfg), C.sizeof(L.SynRolloutCfg), C.sizeof(L.SynExperience), C.sizeof(L.SynStats),
-                     C.sizeof(L.SynFlatBatch)]
+                     C.sizeof(L.SynFlatBatch), C.sizeof(L.SynTrainCfg)]
 
 
 @pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
@@ -291,3 +292,22 @@ def test_winning_cells_algebra_equals_won_per_column():
                 checked += 1
                 wins += won(my | bit)
     assert checked > 50000 and wins > 1000
+
+
+def test_batch_rand_sampler_and_lr_schedule():
+    """BatchRandSampler (data.rs:6-64): a permutation cut into batches, the short tail dropped iff drop_last; and the
+    learning-rate lookup of alpha_zero.rs:62-70."""
+    rng = np.random.default_rng(0)
+    sm = s.BatchRandSampler(70, 32, True, rng)
+    got = list(sm)
+    assert [len(b) for b in got] == [32, 32] and len(set(np.concatenate(got).tolist())) == 64
+    got = list(s.BatchRandSampler(70, 32, False, rng))
+    assert [len(b) for b in got] == [32, 32, 6] and sorted(np.concatenate(got).tolist()) == list(range(70))
+    assert list(s.BatchRandSampler(10, 32, True, rng)) == []
+    sm = s.BatchRandSampler(100, 32, True, np.random.default_rng(3))
+    ref = list(s.BatchRandSampler(100, 32, True, np.random.default_rng(3)))
+    assert np.array_equal(sm.all_batches(), np.stack(ref)) and sm.all_batches().shape == (0, 32)
+    cfg = s.LearningConfig(seed=0, logs="", lr_schedule=[(1, 1e-3), (20, 5e-4), (40, 1e-4)], weight_decay=0.0, num_iterations=1, num_epochs=1,
+                           batch_size=32, policy_weight=1.0, value_weight=1.0, games_to_keep=1, games_per_train=1,
+                           rollout_cfg=s.study_connect4_rollout_cfg())
+    assert [s.lr_for_iteration(cfg, i) for i in (0, 18, 19, 38, 39, 100)] == [1e-3, 1e-3, 5e-4, 5e-4, 1e-4, 1e-4]
