@@ -239,6 +239,8 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.weight_image = e->weight_image.p;
     const char* nored = std::getenv("SYN_TPG_NO_RED"); // read per launch so that one test process can run both forms
     kp.no_reductions = (nored && std::atoi(nored) == 1) ? 1u : 0u;
+    const char* l2h = std::getenv("SYN_TPG_L2HINT");
+    kp.l2_hints = (l2h && std::atoi(l2h) == 0) ? 0u : 1u;
 }
 
 static int read_stats(syn_engine* e, syn_stats* stats, float ms) {
