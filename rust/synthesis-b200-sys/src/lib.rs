@@ -112,6 +112,32 @@ pub struct syn_stats {
     pub d2h_bytes: u64,
 }
 
+/// data.rs:80-104 FlatBatch / StateStatistics — what ReplayBuffer::deduplicate returns
+#[repr(C)]
+pub struct syn_flat_batch {
+    pub capacity: usize,
+    pub len: usize,
+    pub states: *mut f32, // [cap][63]
+    pub pis: *mut f32,    // [cap][9]
+    pub vs: *mut f32,     // [cap][3]
+    pub my_bb: *mut u64,
+    pub op_bb: *mut u64,
+    pub num: *mut u32,
+}
+
+/// tch nn::Adam::default() + LearningConfig's loss weights / batch size (config.rs:76-94)
+#[repr(C)]
+pub struct syn_train_cfg {
+    pub lr: f32,
+    pub beta1: f32,
+    pub beta2: f32,
+    pub eps: f32,
+    pub weight_decay: f32,
+    pub policy_weight: f32,
+    pub value_weight: f32,
+    pub batch_size: u32,
+}
+
 #[repr(C)]
 pub struct syn_engine {
     _private: [u8; 0],
@@ -136,4 +162,11 @@ extern "C" {
                             child_visits: *mut f32, stats: *mut syn_stats) -> c_int;
     pub fn syn_engine_eval(e: *mut syn_engine, my_bb: *const u64, op_bb: *const u64, n_positions: u32, logits: *mut f32,
                            outcome_probs: *mut f32) -> c_int;
+    pub fn syn_engine_deduplicate(e: *mut syn_engine, my_bb: *const u64, op_bb: *const u64, pis: *const f32, vs: *const f32, n_rows: usize,
+                                  out: *mut syn_flat_batch, stats: *mut syn_stats) -> c_int;
+    pub fn syn_engine_train(e: *mut syn_engine, cfg: *const syn_train_cfg, my_bb: *const u64, op_bb: *const u64, pis: *const f32,
+                            vs: *const f32, n_rows: usize, batch_index: *const u32 /* [n_batches][batch_size] */, n_batches: u32,
+                            losses: *mut f32 /* [n_batches][2] or null */, stats: *mut syn_stats) -> c_int;
+    pub fn syn_engine_reset_optimizer(e: *mut syn_engine) -> c_int;
+    pub fn syn_engine_get_weights(e: *mut syn_engine, blob: *mut f32, n_floats: usize) -> c_int;
 }
