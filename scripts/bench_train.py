@@ -28,15 +28,18 @@ d, _ = eng.deduplicate(a["my_bb"], a["op_bb"], a["pis"], a["vs"])
 n = len(d["num"])
 rng = np.random.default_rng(0)
 batches = np.concatenate([s.BatchRandSampler(n, 32, True, rng).all_batches() for _ in range(gpu_steps * 32 // max(32, n - n % 32) + 1)])[:gpu_steps]
-eng.reset_optimizer()
-eng.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], batches[:100], 1e-3, 1e-6)  # warm-up
-eng.set_weights(net.blob())
-eng.reset_optimizer()
-t0 = time.perf_counter()
-losses, ts = eng.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], batches, 1e-3, 1e-6)
-wall = time.perf_counter() - t0
-line = {"op": "train", "rows": n, "steps": len(batches), "gpu_us_per_step": ts["device_ns"] / 1e3 / len(batches), "gpu_e2e_us_per_step": wall * 1e6 / len(batches),
-        "first_loss": [float(x) for x in losses[0]], "last_loss": [float(x) for x in losses[-100:].mean(0)]}
+line = {"op": "train", "rows": n, "steps": len(batches)}
+for kernel, env in (("single_cta", "0"), ("cluster8_sync", "1"), ("cluster8_async", "2")):
+    os.environ["SYN_TRAIN_CLUSTER"] = env
+    eng.reset_optimizer()
+    eng.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], batches[:100], 1e-3, 1e-6)  # warm-up
+    eng.set_weights(net.blob())
+    eng.reset_optimizer()
+    t0 = time.perf_counter()
+    losses, ts = eng.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], batches, 1e-3, 1e-6)
+    wall = time.perf_counter() - t0
+    line.update({kernel + "_us_per_step": ts["device_ns"] / 1e3 / len(batches), kernel + "_e2e_us_per_step": wall * 1e6 / len(batches),
+                 kernel + "_first_loss": [float(x) for x in losses[0]], kernel + "_last_loss": [float(x) for x in losses[-100:].mean(0)]})
 if cpu_steps:
     from torch_learner import TorchLearner
     ref = TorchLearner(net.blob(), 1e-3, 1e-6)

@@ -21,6 +21,7 @@
 #include "tpg2.cuh"
 #include "dedup.cuh"
 #include "train.cuh"
+#include "train_cluster.cuh"
 
 using namespace eng;
 
@@ -954,11 +955,21 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
     tp.my = (const uint64_t*)in[0]; tp.op = (const uint64_t*)in[1]; tp.pis = (const float*)in[2]; tp.vs = (const float*)in[3];
     tp.batch_idx = (const uint32_t*)in[4]; tp.sched = (const float2*)(e->tr_io.p + o_sched);
     tp.losses = (float*)(e->tr_io.p + o_loss); tp.error = e->error.p;
+    const char* tprof = std::getenv("SYN_TRAIN_PROF"); // per-phase clocks of the async cluster kernel, printed to stderr
+    tp.prof = (tprof && std::atoi(tprof) == 1) ? (unsigned long long*)e->counters.p : nullptr;
     tp.n_rows = (uint32_t)n_rows; tp.n_steps = n_batches;
     tp.beta1 = cfg->beta1; tp.beta2 = cfg->beta2; tp.eps = cfg->eps; tp.wd = cfg->weight_decay; tp.pw = cfg->policy_weight; tp.vw = cfg->value_weight;
-    CUDA_TRY(cudaFuncSetAttribute(trn::train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trn::Smem)));
+    // SYN_TRAIN_CLUSTER: 0 = the single-CTA kernel (train.cuh); 1 = a cluster of 8 CTAs exchanging through cluster.sync();
+    // 2 (default) = the cluster with asynchronous remote stores and mbarriers (train_cluster.cuh)
+    const char* tc = std::getenv("SYN_TRAIN_CLUSTER");
+    const int mode = tc ? std::atoi(tc) : 2;
+    if (mode == 2) CUDA_TRY(cudaFuncSetAttribute(trc::train_cluster_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trc::SmemA)));
+    else if (mode == 1) CUDA_TRY(cudaFuncSetAttribute(trc::train_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trc::Smem)));
+    else CUDA_TRY(cudaFuncSetAttribute(trn::train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trn::Smem)));
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
-    trn::train_kernel<<<1, trn::NT, sizeof(trn::Smem), e->stream>>>(tp);
+    if (mode == 2) trc::train_cluster_async_kernel<<<trc::NC, trc::NT, sizeof(trc::SmemA), e->stream>>>(tp);
+    else if (mode == 1) trc::train_cluster_kernel<<<trc::NC, trc::NT, sizeof(trc::Smem), e->stream>>>(tp);
+    else trn::train_kernel<<<1, trn::NT, sizeof(trn::Smem), e->stream>>>(tp);
     CUDA_TRY(cudaGetLastError());
     mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p); // the search kernels see the new weights
     CUDA_TRY(cudaGetLastError());
@@ -973,6 +984,14 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
     CUDA_TRY(cudaMemcpyAsync(&derr, e->error.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (derr) return fail(SYN_ERR_INVALID_ARGUMENT, "batch_index holds a row >= n_rows (%zu)", n_rows);
+    if (tp.prof && mode == 2) {
+        unsigned long long pc[14];
+        CUDA_TRY(cudaMemcpy(pc, tp.prof, sizeof(pc), cudaMemcpyDeviceToHost));
+        static const char* names[13] = {"stage", "fwd0", "fwd1", "fwd2", "fwd3", "fwd4", "loss", "bwd4", "bwd3", "bwd2", "bwd1", "bwd0", "endbar"};
+        std::fprintf(stderr, "train phases (cycles/step, rank 0 thread 0):");
+        for (int k = 0; k < 13; ++k) std::fprintf(stderr, " %s %.0f", names[k], (double)pc[k] / n_batches);
+        std::fprintf(stderr, "\n");
+    }
     if (stats) {
         float ms = 0.0f;
         CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));

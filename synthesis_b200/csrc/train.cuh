@@ -62,6 +62,7 @@ struct Params {
     const float2* sched;       // [n_steps] {lr / (1 - beta1^t), sqrt(1 - beta2^t)}
     float* losses;             // [n_steps][2] {pi_loss, v_loss} or null
     int* error;
+    unsigned long long* prof;  // optional [16]: cycles per phase of a step, summed over steps (rank 0, thread 0; SYN_TRAIN_PROF=1)
     uint32_t n_rows, n_steps;
     float beta1, beta2, eps, wd, pw, vw;
 };

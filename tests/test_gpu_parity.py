@@ -697,8 +697,15 @@ def _training_rows(engine, games=64, explores=40, seed=2):
     return d
 
 
+@pytest.mark.parametrize("cluster", ["2", "1", "0"])
 @pytest.mark.parametrize("weight_decay,pw,vw", [(0.0, 1.0, 1.0), (1e-2, 0.7, 1.3)])
-def test_train_matches_torch_fp32(engine, weight_decay, pw, vw):
+def test_train_matches_torch_fp32(engine, weight_decay, pw, vw, cluster):
+    """All three schedules of the learner: the 8-CTA cluster with asynchronous remote stores (default), the cluster with
+    cluster.sync() exchanges (train_cluster.cuh) and the single-CTA kernel (train.cuh)."""
+    _with_env("SYN_TRAIN_CLUSTER", cluster, lambda: _train_matches_torch_fp32(engine, weight_decay, pw, vw))
+
+
+def _train_matches_torch_fp32(engine, weight_decay, pw, vw):
     """Floating-point kernel: per-step losses and the weights after 1, 4 and 40 Adam steps against the same steps in
     PyTorch fp32 on the CPU (the ops the reference runs through tch).  Tolerance (north_star): 1e-3 abs/rel; observed
     differences are ~1e-6 (summation order)."""
@@ -753,3 +760,30 @@ def test_train_loss_decreases_and_edge_cases(engine):
     assert ei.value.code == L.SYN_ERR_UNSUPPORTED
     losses, st = engine.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], np.zeros((0, 32), np.uint32), 1e-3)
     assert losses.shape == (0, 2)
+
+
+def test_alpha_zero_loop_end_to_end(engine, tmp_path):
+    """gather -> deduplicate -> train -> gather with the weights never leaving the device: two iterations of the host
+    mirror of alpha_zero (alpha_zero.rs:16-118), model files written where the reference writes them and read back."""
+    cfg = s.LearningConfig(seed=3, logs=str(tmp_path), lr_schedule=[(1, 1e-3), (2, 5e-4)], weight_decay=1e-6, num_iterations=2, num_epochs=3,
+                           batch_size=32, policy_weight=1.0, value_weight=1.0, games_to_keep=96, games_per_train=64,
+                           rollout_cfg=s.study_connect4_rollout_cfg(num_explores=32))
+    seen = []
+
+    def on_iteration(i, eng, buffer, dedup, epochs):
+        s.Connect4Net.from_blob(eng.get_weights()).save_ot(str(tmp_path / f"model_{i + 1}.ot"))
+        seen.append((i, buffer.total_games_played(), buffer.curr_games(), len(dedup), epochs))
+
+    net0 = s.Connect4Net.new(cfg.seed)
+    net = s.alpha_zero(cfg, net0, engine=engine, on_iteration=on_iteration)
+    assert [x[0] for x in seen] == [0, 1] and seen[0][1] == 64 and seen[1][1] == 128
+    # keep_last_n_games(96 - 64) keeps ids >= 64 - 32, i.e. 33 games (data.rs:172-194 compares with >=), then extend adds 64
+    assert seen[1][2] == 97
+    assert all(len(x[4]) == 3 and np.all(np.isfinite(x[4])) for x in seen) and seen[1][3] > seen[0][3] > 64
+    assert np.abs(net.blob() - net0.blob()).max() > 1e-3
+    assert s.Connect4Net.load_ot(str(tmp_path / "model_2.ot")).blob().tobytes() == net.blob().tobytes()
+    # the engine's search weights ARE the trained ones
+    lg, _ = engine.eval([0], [0])
+    engine.set_weights(net.blob())
+    lg2, _ = engine.eval([0], [0])
+    assert lg.tobytes() == lg2.tobytes()
