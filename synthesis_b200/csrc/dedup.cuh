@@ -276,9 +276,9 @@ __global__ void __launch_bounds__(T) reduce_kernel(const uint32_t* __restrict__ 
     emit_header(o, g, my[first_row], op[first_row], cnt, c, 16);
 }
 
-// One CTA of 512 threads per big group: warps 1..15 gather the next BIG_CHUNK rows into shared memory (two rows per
-// thread, every load of a chunk issued before the first one is used) while lanes 0..11 of warp 0 add the previous
-// chunk in row order.  The chain of dependent f32 additions (4 cycles per row) is the critical path of the call.
+// One CTA of 512 threads per big group: warps 1..15 gather the next BIG_CHUNK rows into shared memory (a 16-lane group per
+// row, one component per lane, so a warp-wide load touches 4 sectors instead of 32; sixteen loads in flight per thread)
+// while lanes 0..11 of warp 0 add the previous chunk in row order.  The chain of dependent f32 additions (4 cycles per row) is the critical path of the call.
 constexpr int BIG_T = 512;
 constexpr int BIG_STAGERS = BIG_T - 32;
 constexpr int BIG_CHUNK = 2 * BIG_STAGERS; // 960 rows, 2 x 45 KB of shared memory
@@ -293,21 +293,30 @@ __global__ void __launch_bounds__(BIG_T) reduce_big_kernel(const uint32_t* __res
     const uint32_t s = gstart[g], e = gstart[g + 1u], cnt = e - s;
     const uint32_t chunks = (cnt + BIG_CHUNK - 1) / BIG_CHUNK;
     float acc = 0.0f;
-    auto stage = [&](uint32_t k) { // threads 32 .. BIG_T-1
+    auto stage = [&](uint32_t k) { // threads 32 .. BIG_T-1: 30 groups of 16 lanes, lane c < 12 of a group fetches component c of a row
         float* b = big_buf + (k & 1u) * (BIG_CHUNK * 12);
         const uint32_t j0 = s + k * BIG_CHUNK, m = min((uint32_t)BIG_CHUNK, e - j0);
-        const uint32_t r0 = threadIdx.x - 32u, r1 = r0 + BIG_STAGERS;
-        const uint32_t i0 = r0 < m ? rows_sorted[j0 + r0] : 0u, i1 = r1 < m ? rows_sorted[j0 + r1] : 0u;
-        float x0[12], x1[12];
+        const uint32_t wl = threadIdx.x - 32u, grp = wl >> 4, c = wl & 15u;
+        constexpr uint32_t GROUPS = BIG_STAGERS / 16, PASSES = BIG_CHUNK / GROUPS, U = 16; // 30 groups x 32 passes
+#pragma unroll 1
+        for (uint32_t p0 = 0; p0 < PASSES; p0 += U) {
+            uint32_t idx[U];
+            float x[U];
 #pragma unroll
-        for (int c = 0; c < 12; ++c) {
-            x0[c] = r0 < m ? (c < 9 ? pis[(size_t)i0 * 9 + c] : vs[(size_t)i0 * 3 + (c - 9)]) : 0.0f;
-            x1[c] = r1 < m ? (c < 9 ? pis[(size_t)i1 * 9 + c] : vs[(size_t)i1 * 3 + (c - 9)]) : 0.0f;
-        }
+            for (uint32_t u = 0; u < U; ++u) {
+                const uint32_t r = (p0 + u) * GROUPS + grp;
+                idx[u] = r < m ? rows_sorted[j0 + r] : 0u;
+            }
 #pragma unroll
-        for (int c = 0; c < 12; c += 4) {
-            *reinterpret_cast<float4*>(b + r0 * 12u + c) = make_float4(x0[c], x0[c + 1], x0[c + 2], x0[c + 3]);
-            *reinterpret_cast<float4*>(b + r1 * 12u + c) = make_float4(x1[c], x1[c + 1], x1[c + 2], x1[c + 3]);
+            for (uint32_t u = 0; u < U; ++u) {
+                const uint32_t r = (p0 + u) * GROUPS + grp;
+                x[u] = (r < m && c < 12u) ? (c < 9u ? pis[(size_t)idx[u] * 9 + c] : vs[(size_t)idx[u] * 3 + (c - 9u)]) : 0.0f;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < U; ++u) {
+                const uint32_t r = (p0 + u) * GROUPS + grp;
+                if (r < m && c < 12u) b[r * 12u + c] = x[u];
+            }
         }
     };
     if (threadIdx.x >= 32) stage(0);

@@ -953,7 +953,7 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
     for (uint32_t k = 0; k < n_batches; ++k) {
         const double t = (double)(e->adam_t + k + 1);
         sched[k].x = (float)((double)cfg->lr / (1.0 - std::pow((double)cfg->beta1, t)));
-        sched[k].y = (float)std::sqrt(1.0 - std::pow((double)cfg->beta2, t));
+        sched[k].y = (float)(1.0 / std::sqrt(1.0 - std::pow((double)cfg->beta2, t)));
     }
     CUDA_TRY(cudaMemcpyAsync(e->tr_io.p + o_sched, sched.data(), (size_t)n_batches * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
     e->h2d += (size_t)n_batches * sizeof(float2);

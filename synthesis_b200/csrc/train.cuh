@@ -59,7 +59,7 @@ struct Params {
     const float* pis;          // [n][9]
     const float* vs;           // [n][3]
     const uint32_t* batch_idx; // [n_steps][32] row indices
-    const float2* sched;       // [n_steps] {lr / (1 - beta1^t), sqrt(1 - beta2^t)}
+    const float2* sched;       // [n_steps] {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)}
     float* losses;             // [n_steps][2] {pi_loss, v_loss} or null
     int* error;
     unsigned long long* prof;  // optional [16]: cycles per phase of a step, summed over steps (rank 0, thread 0; SYN_TRAIN_PROF=1)
@@ -164,8 +164,9 @@ __device__ __forceinline__ float adam1(const Params& p, float2 sc, float w, floa
     if (p.wd != 0.0f) g = fmaf(p.wd, w, g);
     m = fmaf(p.beta1, m, (1.0f - p.beta1) * g);
     v = fmaf(p.beta2, v, (1.0f - p.beta2) * g * g);
-    const float denom = sqrtf(v) / sc.y + p.eps;
-    return w - sc.x * (m / denom);
+    // sc.y = 1 / sqrt(bias_correction2): one IEEE square root, one correctly rounded reciprocal, no division sequences
+    const float denom = __fsqrt_rn(v) * sc.y + p.eps;
+    return w - sc.x * (m * __frcp_rn(denom));
 }
 
 __device__ __forceinline__ void adam4(const Params& p, float2 sc, float* w, int idx, const float* g) {

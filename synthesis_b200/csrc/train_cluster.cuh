@@ -285,6 +285,7 @@ struct SmemA {
     float recv[2][NC][B * DSL]; // [layer parity][source rank]: partial input-deltas for the own columns
     float d[B * DSL];
     float target[B][12];
+    float loss_row[B][2];
     uint64_t bar_act[5];  // activations of layer l + 1 complete (all 8 slices)
     uint64_t bar_part[4]; // partials of layer L from all 8 CTAs, index L - 1
 };
@@ -418,17 +419,24 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
     sync_rows<3, true>(p, s, rank); sync_rows<4, true>(p, s, rank);
     uint64_t pf_my[2] = {0, 0}, pf_op[2] = {0, 0};
     float pf_t[2] = {0.f, 0.f};
-    auto prefetch = [&](uint32_t step) {
+    uint32_t pf_idx[2] = {0u, 0u};
+    auto fetch_idx = [&](uint32_t step) { // row indices first: the rows themselves are requested a whole step later
+#pragma unroll
+        for (int h = 0; h < 2; ++h) pf_idx[h] = step < p.n_steps ? p.batch_idx[(size_t)step * B + (t >> 5) + 16 * h] : 0u;
+    };
+    auto prefetch = [&]() {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            uint32_t idx = p.batch_idx[(size_t)step * B + (t >> 5) + 16 * h];
+            uint32_t idx = pf_idx[h];
             if (idx >= p.n_rows) { atomicExch(p.error, 1); idx = 0; }
             pf_my[h] = p.my[idx];
             pf_op[h] = p.op[idx];
             pf_t[h] = lane < 9 ? p.pis[(size_t)idx * 9 + lane] : (lane < 12 ? p.vs[(size_t)idx * 3 + (lane - 9)] : 0.0f);
         }
     };
-    if (p.n_steps) prefetch(0);
+    fetch_idx(0);
+    if (p.n_steps) prefetch();
+    fetch_idx(1);
     cluster.sync(); // every CTA resident, its mbarriers initialised and visible
     const bool prof = p.prof != nullptr && t == 0 && rank == 0;
     long long pc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tk = prof ? clock64() : 0;
@@ -449,7 +457,8 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
             if (lane < 12) s.target[b][lane] = pf_t[h];
         }
         const float2 sc = p.sched[step];
-        if (step + 1u < p.n_steps) prefetch(step + 1u);
+        if (step + 1u < p.n_steps) prefetch(); // rows of step + 1 (indices fetched during the previous step)
+        fetch_idx(step + 2u);
         __syncthreads();
         SYN_TICK(0)
         forward_async<0>(s, rank); bar_wait(&s.bar_act[0], par); SYN_TICK(1)
@@ -457,29 +466,46 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
         forward_async<2>(s, rank); bar_wait(&s.bar_act[2], par); SYN_TICK(3)
         forward_async<3>(s, rank); bar_wait(&s.bar_act[3], par); SYN_TICK(4)
         forward_async<4>(s, rank); bar_wait(&s.bar_act[4], par); SYN_TICK(5)
-        if (t < 64) {
-            const int head = t >> 5, n = head ? 3 : 9, o0 = head ? 9 : 0;
-            const float* z = s.act + act_off(5) + lane * 16 + o0;
-            const float* tg = &s.target[lane][o0];
-            float mx = z[0];
-            for (int k = 1; k < n; ++k) mx = fmaxf(mx, z[k]);
-            float se = 0.f, st = 0.f;
-            for (int k = 0; k < n; ++k) { se += expf(z[k] - mx); st += tg[k]; }
-            const float lse = mx + logf(se);
-            const float scale = (head ? p.vw : p.pw) * (1.0f / (float)B);
-            const int lo = (int)rank * Own<4>::sl;
-            float loss = 0.f;
-            for (int k = 0; k < n; ++k) {
-                const float lp = z[k] - lse, tk = tg[k];
-                if (tk > 0.f) loss += tk * (logf(tk) - lp);
-                const int o = o0 + k;
-                if (o >= lo && o < lo + Own<4>::sl) s.d[lane * DSL + (o - lo)] = scale * (expf(lp) * st - tk);
-            }
+        { // 16 lanes per batch row, lane k < 12 owns logit k: head maxima and sums by xor-shuffles inside the half-warp
+            const int b = t >> 4, k = t & 15;
+            const bool isp = k < 9, isv = k >= 9 && k < 12;
+            const float ninf = __uint_as_float(0xff800000u);
+            const float z = k < 12 ? s.act[act_off(5) + b * 16 + k] : ninf;
+            const float tgt = k < 12 ? s.target[b][k] : 0.0f;
+            float mp = isp ? z : ninf, mv = isv ? z : ninf;
 #pragma unroll
-            for (int dlt = 16; dlt; dlt >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, dlt);
-            if (lane == 0 && rank == 0 && p.losses) p.losses[(size_t)step * 2 + head] = loss * (1.0f / (float)B);
+            for (int dlt = 8; dlt; dlt >>= 1) {
+                mp = fmaxf(mp, __shfl_xor_sync(0xffffffffu, mp, dlt));
+                mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, dlt));
+            }
+            const float mx = isp ? mp : mv;
+            const float ex = k < 12 ? expf(z - mx) : 0.0f;
+            float sep = isp ? ex : 0.f, sev = isv ? ex : 0.f, stp = isp ? tgt : 0.f, stv = isv ? tgt : 0.f;
+#pragma unroll
+            for (int dlt = 8; dlt; dlt >>= 1) {
+                sep += __shfl_xor_sync(0xffffffffu, sep, dlt); sev += __shfl_xor_sync(0xffffffffu, sev, dlt);
+                stp += __shfl_xor_sync(0xffffffffu, stp, dlt); stv += __shfl_xor_sync(0xffffffffu, stv, dlt);
+            }
+            const float se = isp ? sep : sev, st = isp ? stp : stv;
+            const float lp = z - (mx + logf(se));
+            float lk = (k < 12 && tgt > 0.f) ? tgt * (logf(tgt) - lp) : 0.f; // kl_div: xlogy(t, t) - t * input
+            const float scale = (isp ? p.pw : p.vw) * (1.0f / (float)B);
+            const int lo = (int)rank * Own<4>::sl;
+            if (k >= lo && k < lo + Own<4>::sl && k < 12) s.d[b * DSL + (k - lo)] = scale * (__fdividef(ex, se) * st - tgt);
+            float lpol = isp ? lk : 0.f, lval = isv ? lk : 0.f;
+#pragma unroll
+            for (int dlt = 8; dlt; dlt >>= 1) {
+                lpol += __shfl_xor_sync(0xffffffffu, lpol, dlt);
+                lval += __shfl_xor_sync(0xffffffffu, lval, dlt);
+            }
+            if (k == 0) { s.loss_row[b][0] = lpol; s.loss_row[b][1] = lval; }
         }
         __syncthreads();
+        if (rank == 0 && t < 2 && p.losses) {
+            float tot = 0.f;
+            for (int r = 0; r < B; ++r) tot += s.loss_row[r][t];
+            p.losses[(size_t)step * 2 + t] = tot * (1.0f / (float)B);
+        }
         SYN_TICK(6)
         backward_layer_async<4>(p, s, sc, rank, par); SYN_TICK(7)
         backward_layer_async<3>(p, s, sc, rank, par); SYN_TICK(8)
