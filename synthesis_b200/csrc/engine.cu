@@ -240,8 +240,6 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.weight_image = e->weight_image.p;
     const char* nored = std::getenv("SYN_TPG_NO_RED"); // read per launch so that one test process can run both forms
     kp.no_reductions = (nored && std::atoi(nored) == 1) ? 1u : 0u;
-    const char* l2h = std::getenv("SYN_TPG_L2HINT");
-    kp.l2_hints = (l2h && std::atoi(l2h) == 0) ? 0u : 1u;
 }
 
 static int read_stats(syn_engine* e, syn_stats* stats, float ms) {
@@ -353,14 +351,6 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     // node records are 16/32-byte random accesses: ask L2 to fetch single sectors from DRAM instead of pairs
     const char* fenv = std::getenv("SYN_L2_FETCH");
     if (fenv && std::atoi(fenv) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(fenv));
-    // Experiment knob only: a persisting-L2 carve-out for tpg2.cuh's evict_last lines.  Measured on B200
-    // (profiles/r1_l2_persist_ab.txt): the maximum carve-out cuts DRAM reads by 14 % and throughput by 31 % — the
-    // ordinary lines need the capacity more — so nothing is set aside unless SYN_L2_PERSIST_MB asks for it.
-    const char* penv2 = std::getenv("SYN_L2_PERSIST_MB");
-    if (penv2 && std::atoi(penv2) > 0) {
-        size_t persist = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)std::atoi(penv2) << 20);
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) != cudaSuccess) cudaGetLastError();
-    }
     syn_engine* e = new syn_engine();
     e->device = cuda_device;
     e->sm_count = prop.multiProcessorCount;

@@ -27,7 +27,6 @@ struct KParams {
     uint64_t seed, first_game;
     uint32_t num_games;
     uint32_t search_mode; // 1: one tree per given position, no game loop (syn_engine_search)
-    uint32_t l2_hints;      // tpg2.cuh: 1 = L2 eviction priorities by tree level (SYN_TPG_L2HINT=0 turns them off)
     uint32_t no_reductions; // tpg2.cuh: 1 = backprop by load / add / store only (SYN_TPG_NO_RED=1; the parity suite runs both)
     uint32_t arena_nodes;
     uint4* nodes; // tree arenas: arena_nodes 32-byte records per game slot (tree.cuh)

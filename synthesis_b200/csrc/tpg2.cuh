@@ -42,40 +42,6 @@ __device__ __forceinline__ Rec load_rec(const uint4* nodes, uint32_t i) { // LDG
     r.prior = (uint32_t)q2; r.parent = (uint32_t)(q2 >> 32); r.fc = (uint32_t)q3; r.pk = (uint32_t)(q3 >> 32);
     return r;
 }
-// L2 eviction priorities.  The arenas in flight (17 GB) stream through the 126 MB L2 many times per move, so without
-// help even a tree's root and the root's children — read by EVERY explore — are gone from L2 by the next round.  Those
-// lines (4 per tree, 39 MB over all trees, the same addresses for every tree a slot plays) are requested evict_last;
-// levels >= 2, which are not coming back soon, evict_first; level 1 normal.  A policy operand lives in a uniform
-// register: it must be the same for all active lanes, which holds per level (warps walk levels in lockstep).
-struct L2Pol { uint64_t top, mid, deep; };
-__device__ __forceinline__ L2Pol l2_policies(bool hints) {
-    L2Pol q;
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(q.mid));
-    if (hints) {
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(q.top));
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(q.deep));
-    } else {
-        q.top = q.mid; q.deep = q.mid;
-    }
-    return q;
-}
-__device__ __forceinline__ Rec load_rec(const uint4* nodes, uint32_t i, uint64_t pol) { // LDG.E.256 with an L2 cache-policy descriptor
-    Rec r;
-    unsigned long long q0, q1, q2, q3;
-    asm volatile("ld.global.L2::cache_hint.v4.b64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(nodes + 2 * (size_t)i), "l"(pol) : "memory");
-    r.vis = __uint_as_float((uint32_t)q0); r.o0 = __uint_as_float((uint32_t)(q0 >> 32));
-    r.o1 = __uint_as_float((uint32_t)q1); r.o2 = __uint_as_float((uint32_t)(q1 >> 32));
-    r.prior = (uint32_t)q2; r.parent = (uint32_t)(q2 >> 32); r.fc = (uint32_t)q3; r.pk = (uint32_t)(q3 >> 32);
-    return r;
-}
-__device__ __forceinline__ void store_rec(uint4* nodes, uint32_t i, float vis, float o0, float o1, float o2, uint32_t prior,
-                                          uint32_t parent, uint32_t fc, uint32_t pk, uint64_t pol) { // STG.E.256 with a policy
-    unsigned long long q0 = (unsigned long long)__float_as_uint(vis) | ((unsigned long long)__float_as_uint(o0) << 32);
-    unsigned long long q1 = (unsigned long long)__float_as_uint(o1) | ((unsigned long long)__float_as_uint(o2) << 32);
-    unsigned long long q2 = (unsigned long long)prior | ((unsigned long long)parent << 32);
-    unsigned long long q3 = (unsigned long long)fc | ((unsigned long long)pk << 32);
-    asm volatile("st.global.L2::cache_hint.v4.b64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(nodes + 2 * (size_t)i), "l"(q0), "l"(q1), "l"(q2), "l"(q3), "l"(pol) : "memory");
-}
 __device__ __forceinline__ void store_rec(uint4* nodes, uint32_t i, float vis, float o0, float o1, float o2, uint32_t prior,
                                           uint32_t parent, uint32_t fc, uint32_t pk) { // STG.E.256
     unsigned long long q0 = (unsigned long long)__float_as_uint(vis) | ((unsigned long long)__float_as_uint(o0) << 32);
@@ -98,10 +64,6 @@ __device__ __forceinline__ void red_stat(uint4* nodes, uint32_t i, float v0, flo
 // so the flushing adder and the IEEE adder agree bit for bit.  The first value that fails makes the tree
 // "slow" (Game::slow) until it is reset: it then only uses load / FADD / store.
 __device__ __forceinline__ bool red_exact(float x) { return ((__float_as_uint(x) << 1) >= (27u << 24)) || ((__float_as_uint(x) << 1) == 0u); }
-__device__ __forceinline__ void red_stat(uint4* nodes, uint32_t i, float v0, float v1, float v2, uint64_t pol) {
-    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(nodes + 2 * (size_t)i), "f"(1.0f), "f"(v0), "f"(v1), "f"(v2), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2_last(const uint4* nodes, uint32_t i) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nodes + 2 * (size_t)i)); }
 __device__ __forceinline__ void prefetch_l2(const uint4* nodes, uint32_t i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + 2 * (size_t)i)); }
 __device__ __forceinline__ uint32_t* meta_words(uint4* nodes, uint32_t i) { return reinterpret_cast<uint32_t*>(nodes + 2 * (size_t)i + 1); }
 enum { MW_PRIOR = 0, MW_PARENT = 1, MW_FC = 2, MW_PK = 3 };
@@ -161,7 +123,7 @@ __device__ __noinline__ float fpu_normal_draw(const KParams& p, uint32_t* ss) { 
 // stride NT words, levels 1 .. PATH_CAP), so that backprop knows the way up without reading parent links.
 template <int CW, int FPU, int NT, int PATH_CAP>
 __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, const Rec& root, uint64_t& my, uint64_t& op, Pend& pd,
-                                       RoundCnt& rc, uint32_t* path, const L2Pol& l2) {
+                                       RoundCnt& rc, uint32_t* path) {
     const syn_mcts_cfg& cfg = p.cfg.mcts;
     uint4* nodes = g.nodes;
     uint32_t cur = 0u;
@@ -176,11 +138,7 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
         if (nch == 0u) break;
         // the children are read CW at a time; DRAM hands out whole 128-byte lines, so asking for the last child's line now
         // makes the second batch an L2 hit instead of a second trip to HBM
-        const uint64_t pol = depth == 0u ? l2.top : (depth == 1u ? l2.mid : l2.deep); // the children of a level-`depth` node
-        if (nch > (uint32_t)CW) {
-            if (depth == 0u && p.l2_hints) prefetch_l2_last(nodes, cfc + nch - 1u);
-            else prefetch_l2(nodes, cfc + nch - 1u);
-        }
+        if (nch > (uint32_t)CW) prefetch_l2(nodes, cfc + nch - 1u);
         // ---- select_best_child (mcts.rs:327-372): first strict maximum in child order
         const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
         const float fpu_q = PQ ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : cfg.fpu_a; // Fpu::ParentQ = parent.q() (mcts.rs:353), once per level
@@ -189,7 +147,7 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
         for (uint32_t k0 = 0; k0 < nch; k0 += (uint32_t)CW) { // CW records per memory round trip
             Rec chs[CW];
 #pragma unroll
-            for (uint32_t j = 0; j < (uint32_t)CW; ++j) chs[j] = load_rec(nodes, cfc + min(k0 + j, nch - 1u), pol);
+            for (uint32_t j = 0; j < (uint32_t)CW; ++j) chs[j] = load_rec(nodes, cfc + min(k0 + j, nch - 1u));
 #pragma unroll
             for (uint32_t j = 0; j < (uint32_t)CW; ++j) {
                 const uint32_t k = k0 + j;
@@ -272,7 +230,7 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
 // memory.  Beyond PATH_CAP levels the parent link is read.  `slow` (Game::slow) forces load / add / store everywhere.
 template <int NT, int PATH_CAP>
 __device__ __forceinline__ uint32_t backprop(const syn_mcts_cfg& cfg, uint4* nodes, const uint32_t* path, uint32_t depth, uint32_t id, float v0, float v1,
-                                             float v2, bool solved, bool& slow, const L2Pol& l2) {
+                                             float v2, bool solved, bool& slow) {
     uint32_t levels = 0;
     solved = solved && cfg.solve;
     for (;;) {
@@ -319,8 +277,7 @@ __device__ __forceinline__ uint32_t backprop(const syn_mcts_cfg& cfg, uint4* nod
             store_stat(nodes, id, n.vis + 1.0f, n.o0 + v0, n.o1 + v1, n.o2 + v2);
             parent = n.parent;
         } else {
-            if (depth <= 1u) red_stat(nodes, id, v0, v1, v2, l2.top); // lanes are at different levels here: one policy per branch
-            else red_stat(nodes, id, v0, v1, v2);
+            red_stat(nodes, id, v0, v1, v2);
             parent = depth <= 1u ? 0u : (depth - 2u < (uint32_t)PATH_CAP ? path[(depth - 2u) * NT] : meta_words(nodes, id)[MW_PARENT]);
         }
         if (id == 0u) break;
@@ -333,7 +290,7 @@ __device__ __forceinline__ uint32_t backprop(const syn_mcts_cfg& cfg, uint4* nod
 
 // The rest of visit() after Policy::eval (mcts.rs:384-397 child records, 409-423 stable softmax over
 // the legal children in child order).  logits[col] is used for legal columns only.
-__device__ __forceinline__ void write_children(uint4* nodes, const Pend& pd, const float (&logits)[9], const L2Pol& l2) {
+__device__ __forceinline__ void write_children(uint4* nodes, const Pend& pd, const float (&logits)[9]) {
     const uint32_t legal = pd.lc & 0x1ffu, csol2 = pd.lc >> 9;
     float e[9];
     float total = 0.0f;
@@ -355,10 +312,8 @@ __device__ __forceinline__ void write_children(uint4* nodes, const Pend& pd, con
         if ((legal >> col) & 1u) {
             uint32_t s2 = (csol2 >> (2 * col)) & 3u;
             uint32_t csol = s2 == 1u ? c4::SOL_LOSE0 : (s2 == 2u ? c4::SOL_DRAW0 : 0u);
-            const uint32_t prior = __float_as_uint(__fdiv_rn(e[col], total)), pk = (csol << 8) | ((uint32_t)col << 16);
-            if (pd.depth == 0u) store_rec(nodes, pd.fc + rank, 0.f, 0.f, 0.f, 0.f, prior, pd.id, 0u, pk, l2.top); // the root's children
-            else if (pd.depth == 1u) store_rec(nodes, pd.fc + rank, 0.f, 0.f, 0.f, 0.f, prior, pd.id, 0u, pk, l2.mid);
-            else store_rec(nodes, pd.fc + rank, 0.f, 0.f, 0.f, 0.f, prior, pd.id, 0u, pk, l2.deep);
+            store_rec(nodes, pd.fc + rank, 0.f, 0.f, 0.f, 0.f, __float_as_uint(__fdiv_rn(e[col], total)), pd.id, 0u,
+                      (csol << 8) | ((uint32_t)col << 16));
             ++rank;
         }
     }
@@ -568,7 +523,6 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
     const syn_mcts_cfg& cfg = p.cfg.mcts;
     const float stop_vis = (float)(p.cfg.num_explores + 1u); // explore_n is over when the root has 1 + num_explores visits
     constexpr int CW = TEAMS >= 5 ? 3 : 5;
-    const tp2::L2Pol l2 = tp2::l2_policies(p.l2_hints != 0u);
     tp2::Game g;
     g.nodes = p.nodes + 2 * slot_id * p.arena_nodes;
     g.nn = 1u; g.phase = PH_NEED_GAME; g.slow = p.no_reductions != 0u;
@@ -587,7 +541,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
             tp2::Rec root;
             bool go = true;
             if (g.phase == PH_EXPLORE) { // explore_n (mcts.rs:139-147): stop at num_explores or once the root is solved
-                root = tp2::load_rec(g.nodes, 0u, l2.top);
+                root = tp2::load_rec(g.nodes, 0u);
                 my = tp2::ss_load64(ss, tp2::SS_MY); op = tp2::ss_load64(ss, tp2::SS_OP);
                 if (root.vis >= stop_vis || ((root.pk >> 8) & 0xffu) != 0u) {
                     int pe = tp2::end_of_move(p, ss, g.nodes, g.nn, (uint32_t)root.vis - 1u, tp2::ReadRoot2());
@@ -611,9 +565,9 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
             }
             if (go && !err) {
                 const uint32_t init = root.vis == 0.0f ? (uint32_t)tp2::K_INIT : 0u; // the construction visit (mcts.rs:133)
-                if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path, l2);
-                else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path, l2);
-                else err = tp2::descend<CW, SYN_FPU_NORMAL, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path, l2);
+                if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                else err = tp2::descend<CW, SYN_FPU_NORMAL, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 pd.kind |= init;
             }
             if (err) { atomicCAS(p.error, 0, err); g.phase = PH_DONE; pd.kind = tp2::K_NONE; }
@@ -652,7 +606,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
                 float lg[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) lg[k] = y[k];
-                tp2::write_children(g.nodes, pd, lg, l2);
+                tp2::write_children(g.nodes, pd, lg);
                 v0 = __fdiv_rn(e0, tot); v1 = __fdiv_rn(e1, tot); v2 = __fdiv_rn(e2, tot);
                 solved = (pd.lc >> 9) != 0u;
                 rc.leaf_evals = 1u;
@@ -661,7 +615,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
                 v0 = idx == 0 ? 1.0f : 0.0f; v1 = idx == 1 ? 1.0f : 0.0f; v2 = idx == 2 ? 1.0f : 0.0f;
                 solved = true;
             }
-            rc.bp_levels = tp2::backprop<NT, PATH_CAP>(cfg, g.nodes, path, pd.depth, pd.id, v0, v1, v2, solved, g.slow, l2);
+            rc.bp_levels = tp2::backprop<NT, PATH_CAP>(cfg, g.nodes, path, pd.depth, pd.id, v0, v1, v2, solved, g.slow);
             if (pd.kind & tp2::K_INIT) tp2::add_root_noise(p, ss, g.nodes);
         }
         __syncwarp();

@@ -98,3 +98,38 @@ def broadcast_weights(blob_or_none, *, group=None, device=None, src: int = 0):
         t.copy_(torch.from_numpy(np.ascontiguousarray(blob_or_none, dtype=np.float32).reshape(-1)))
     dist.broadcast(t, src=src, group=group)
     return t
+
+
+def alpha_zero_distributed(cfg, engine, *, policy=None, group=None, device=None, dst: int = 0, on_iteration=None):
+    """`alpha_zero` (alpha_zero.rs:16-118) over a process group, one engine (one GPU) per rank: every iteration the
+    trainer rank `dst` broadcasts its current weights (ONE collective, replaces the model_{i}.ot round trip), all ranks
+    play their shard of `games_per_train`, the rows are gathered to `dst` (ONE gather), which deduplicates and trains
+    on its own GPU.  Returns the trained Connect4Net on `dst`, None elsewhere."""
+    import torch.distributed as dist
+
+    from . import _lib as L
+    from .alpha_zero import lr_for_iteration, train_on
+    from .policies import Connect4Net
+
+    rank = dist.get_rank(group)
+    if rank == dst:
+        engine.set_weights((policy or Connect4Net.new(cfg.seed)).blob())
+        engine.reset_optimizer()
+    rng = np.random.default_rng(cfg.seed)
+    buffer = ReplayBuffer(256_000) if rank == dst else None
+    for i_iter in range(cfg.num_iterations):
+        w = broadcast_weights(engine.get_weights() if rank == dst else None, group=group, device=device, src=dst)
+        if rank != dst:
+            engine.set_weights(int(w.data_ptr()) if w.is_cuda else w.numpy())
+
+        def play(first, count, _i=i_iter):
+            arrays, _, _ = engine.gather(cfg.rollout_cfg, L.LEAF_NN, first, count, _i)
+            return arrays
+
+        gather_experience_distributed(play, cfg.games_per_train, buffer, cfg.games_to_keep, group=group, device=device, dst=dst)
+        if rank == dst:
+            dedup = buffer.deduplicate(engine)
+            epochs = train_on(cfg, dedup, lr_for_iteration(cfg, i_iter), engine, rng)
+            if on_iteration is not None:
+                on_iteration(i_iter, engine, buffer, dedup, epochs)
+    return Connect4Net.from_blob(engine.get_weights()) if rank == dst else None

@@ -787,3 +787,25 @@ def test_alpha_zero_loop_end_to_end(engine, tmp_path):
     engine.set_weights(net.blob())
     lg2, _ = engine.eval([0], [0])
     assert lg.tobytes() == lg2.tobytes()
+
+
+def test_alpha_zero_distributed_world_of_one_equals_local(engine):
+    """The process-group form of the loop (broadcast weights -> sharded gather -> gather rows -> dedup + train on the
+    trainer rank) with a world of one rank (gloo) reproduces the local loop bit for bit: same games, same rows, same
+    batches, same kernels."""
+    import socket
+    import torch.distributed as dist
+    from synthesis_b200 import distributed as D
+    cfg = s.LearningConfig(seed=5, logs="", lr_schedule=[(1, 1e-3)], weight_decay=0.0, num_iterations=2, num_epochs=2, batch_size=32,
+                           policy_weight=1.0, value_weight=1.0, games_to_keep=200, games_per_train=48,
+                           rollout_cfg=s.study_connect4_rollout_cfg(num_explores=24))
+    local = s.alpha_zero(cfg, s.Connect4Net.new(cfg.seed), engine=engine)
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        net = D.alpha_zero_distributed(cfg, engine, policy=s.Connect4Net.new(cfg.seed))
+    finally:
+        dist.destroy_process_group()
+    assert net.blob().tobytes() == local.blob().tobytes()
