@@ -19,6 +19,7 @@
 //   sort     : stable LSD radix sort of (rep, row) pairs, 8 bits per pass, ceil(log2 n / 8) passes;
 //              per-warp match_any ranking keeps equal keys in row order
 //   heads    : group boundaries -> exclusive scan -> group start table
+//   gather   : policy/value targets permuted into sorted order (the only pass of random reads)
 //   reduce   : 16 lanes per group (9 policy + 3 value components, sequential f32 sums in row
 //              order); groups above BIG rows are streamed by one CTA each through shared memory
 //   features : Game::features() of the group's position, synthesised from the bitboards
@@ -218,6 +219,17 @@ __global__ void starts_kernel(const uint32_t* __restrict__ rep_sorted, const uin
     if (j == n - 1u) gstart[*n_groups] = n;
 }
 
+// Targets in sorted order: pv[j][0..9) = pis[row_j], pv[j][9..12) = vs[row_j].  The one pass of random reads; both
+// reduce kernels then stream contiguous memory (a big group's rows are spread over the whole buffer, and chasing them
+// from a single CTA is bound by TLB misses and DRAM latency, not bandwidth).
+__global__ void __launch_bounds__(T) gather_kernel(const uint32_t* __restrict__ rows_sorted, uint32_t n, const float* __restrict__ pis,
+                                                   const float* __restrict__ vs, float* __restrict__ pv) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, c = threadIdx.x & 15u;
+    if (j >= n || c >= 12u) return;
+    const uint32_t idx = rows_sorted[j];
+    pv[(size_t)j * 12 + c] = c < 9u ? pis[(size_t)idx * 9 + c] : vs[(size_t)idx * 3 + (c - 9u)];
+}
+
 struct Out {
     uint64_t* my_bb; // [U]
     uint64_t* op_bb; // [U]
@@ -237,48 +249,42 @@ __device__ __forceinline__ void emit_header(const Out& o, uint32_t g, uint64_t m
         for (int i = lane; i < 63; i += lanes) o.states[(size_t)g * 63 + i] = c4::feature(m, p, i);
 }
 
-// 16 lanes per group; lane c < 9 owns sum_pi[c], lanes 9..11 own sum_v[c - 9].
+// 16 lanes per group; lane c < 9 owns sum_pi[c], lanes 9..11 own sum_v[c - 9].  pv = targets in sorted order.
 __global__ void __launch_bounds__(T) reduce_kernel(const uint32_t* __restrict__ rows_sorted, const uint32_t* __restrict__ gstart,
                                                    const uint32_t* __restrict__ n_groups, const uint64_t* __restrict__ my,
-                                                   const uint64_t* __restrict__ op, const float* __restrict__ pis, const float* __restrict__ vs,
-                                                   Out o, uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_count) {
+                                                   const uint64_t* __restrict__ op, const float* __restrict__ pv, Out o,
+                                                   uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_count) {
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const int c = threadIdx.x & 15;
-    const uint32_t half_mask = 0xffffu << (threadIdx.x & 16);
     if (g >= *n_groups) return;
     const uint32_t s = gstart[g], e = gstart[g + 1u], cnt = e - s;
     if (cnt > BIG) {
         if (c == 0) big_list[atomicAdd(big_count, 1u)] = g;
         return;
     }
-    const float* src = c < 9 ? pis + c : vs + (c - 9);
-    const uint32_t stride = c < 9 ? 9u : 3u;
-    const bool comp = c < 12;
     float acc = 0.0f;
-    uint32_t first_row = 0u;
-    for (uint32_t j0 = s; j0 < e; j0 += 16u) {
-        const uint32_t m = min(16u, e - j0);
-        const uint32_t idxv = (uint32_t)c < m ? rows_sorted[j0 + c] : 0u;
-        if (j0 == s) first_row = __shfl_sync(half_mask, idxv, 0, 16);
-        float x[16];
+    if (c < 12) {
+        const float* src = pv + (size_t)s * 12 + c;
+        uint32_t r = 0;
+        for (; r + 8u <= cnt; r += 8u) {
+            float x[8];
 #pragma unroll
-        for (uint32_t u = 0; u < 16u; ++u) {
-            const uint32_t idx = __shfl_sync(half_mask, idxv, u, 16);
-            x[u] = (u < m && comp) ? src[(size_t)idx * stride] : 0.0f;
+            for (int u = 0; u < 8; ++u) x[u] = src[(size_t)(r + u) * 12];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, x[u]);
         }
-#pragma unroll
-        for (uint32_t u = 0; u < 16u; ++u)
-            if (u < m) acc = __fadd_rn(acc, x[u]);
+        for (; r < cnt; ++r) acc = __fadd_rn(acc, src[(size_t)r * 12]);
     }
     const float avg = __fdiv_rn(acc, (float)cnt);
     if (c < 9) { if (o.pis) o.pis[(size_t)g * 9 + c] = avg; }
     else if (c < 12) { if (o.vs) o.vs[(size_t)g * 3 + (c - 9)] = avg; }
+    const uint32_t first_row = rows_sorted[s];
     emit_header(o, g, my[first_row], op[first_row], cnt, c, 16);
 }
 
-// One CTA of 512 threads per big group: warps 1..15 gather the next BIG_CHUNK rows into shared memory (a 16-lane group per
-// row, one component per lane, so a warp-wide load touches 4 sectors instead of 32; sixteen loads in flight per thread)
-// while lanes 0..11 of warp 0 add the previous chunk in row order.  The chain of dependent f32 additions (4 cycles per row) is the critical path of the call.
+// One CTA of 512 threads per big group: warps 1..15 copy the next BIG_CHUNK rows of the sorted targets (contiguous: 128-bit
+// loads, one round trip per chunk) into shared memory while lanes 0..11 of warp 0 add the previous chunk in row order.
+// The chain of dependent f32 additions (4 cycles per row) is the critical path of the whole call.
 constexpr int BIG_T = 512;
 constexpr int BIG_STAGERS = BIG_T - 32;
 constexpr int BIG_CHUNK = 2 * BIG_STAGERS; // 960 rows, 2 x 45 KB of shared memory
@@ -286,38 +292,23 @@ constexpr size_t BIG_SMEM = 2 * (size_t)BIG_CHUNK * 12 * sizeof(float);
 
 __global__ void __launch_bounds__(BIG_T) reduce_big_kernel(const uint32_t* __restrict__ rows_sorted, const uint32_t* __restrict__ gstart,
                                                            const uint32_t* __restrict__ big_list, const uint64_t* __restrict__ my,
-                                                           const uint64_t* __restrict__ op, const float* __restrict__ pis,
-                                                           const float* __restrict__ vs, Out o) {
+                                                           const uint64_t* __restrict__ op, const float* __restrict__ pv, Out o) {
     extern __shared__ __align__(16) float big_buf[]; // [2][BIG_CHUNK * 12]
     const uint32_t g = big_list[blockIdx.x];
     const uint32_t s = gstart[g], e = gstart[g + 1u], cnt = e - s;
     const uint32_t chunks = (cnt + BIG_CHUNK - 1) / BIG_CHUNK;
     float acc = 0.0f;
-    auto stage = [&](uint32_t k) { // threads 32 .. BIG_T-1: 30 groups of 16 lanes, lane c < 12 of a group fetches component c of a row
-        float* b = big_buf + (k & 1u) * (BIG_CHUNK * 12);
+    auto stage = [&](uint32_t k) { // threads 32 .. BIG_T-1; a row is 48 bytes, so every chunk starts 16-byte aligned
+        float4* b = reinterpret_cast<float4*>(big_buf + (k & 1u) * (BIG_CHUNK * 12));
         const uint32_t j0 = s + k * BIG_CHUNK, m = min((uint32_t)BIG_CHUNK, e - j0);
-        const uint32_t wl = threadIdx.x - 32u, grp = wl >> 4, c = wl & 15u;
-        constexpr uint32_t GROUPS = BIG_STAGERS / 16, PASSES = BIG_CHUNK / GROUPS, U = 16; // 30 groups x 32 passes
-#pragma unroll 1
-        for (uint32_t p0 = 0; p0 < PASSES; p0 += U) {
-            uint32_t idx[U];
-            float x[U];
+        const float4* src = reinterpret_cast<const float4*>(pv + (size_t)j0 * 12);
+        const uint32_t n4 = m * 3u, t0 = threadIdx.x - 32u;
+        float4 x[6];
 #pragma unroll
-            for (uint32_t u = 0; u < U; ++u) {
-                const uint32_t r = (p0 + u) * GROUPS + grp;
-                idx[u] = r < m ? rows_sorted[j0 + r] : 0u;
-            }
+        for (uint32_t u = 0; u < 6u; ++u) x[u] = t0 + u * BIG_STAGERS < n4 ? src[t0 + u * BIG_STAGERS] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (uint32_t u = 0; u < U; ++u) {
-                const uint32_t r = (p0 + u) * GROUPS + grp;
-                x[u] = (r < m && c < 12u) ? (c < 9u ? pis[(size_t)idx[u] * 9 + c] : vs[(size_t)idx[u] * 3 + (c - 9u)]) : 0.0f;
-            }
-#pragma unroll
-            for (uint32_t u = 0; u < U; ++u) {
-                const uint32_t r = (p0 + u) * GROUPS + grp;
-                if (r < m && c < 12u) b[r * 12u + c] = x[u];
-            }
-        }
+        for (uint32_t u = 0; u < 6u; ++u)
+            if (t0 + u * BIG_STAGERS < n4) b[t0 + u * BIG_STAGERS] = x[u];
     };
     if (threadIdx.x >= 32) stage(0);
     __syncthreads();
@@ -327,13 +318,24 @@ __global__ void __launch_bounds__(BIG_T) reduce_big_kernel(const uint32_t* __res
         } else if (threadIdx.x < 12) {
             const float* b = big_buf + (k & 1u) * (BIG_CHUNK * 12) + threadIdx.x;
             const uint32_t m = min((uint32_t)BIG_CHUNK, e - (s + k * BIG_CHUNK));
+            // the dependent additions (4 cycles each) are the critical path: the next sixteen operands are always in
+            // registers before the current sixteen have been added
             uint32_t r = 0;
-            for (; r + 8u <= m; r += 8u) {
-                float x[8];
+            float x[16], y[16];
+            if (m >= 16u) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = b[(r + u) * 12u];
+                for (int u = 0; u < 16; ++u) x[u] = b[u * 12u];
+                for (; r + 32u <= m; r += 16u) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, x[u]);
+                    for (int u = 0; u < 16; ++u) y[u] = b[(r + 16u + u) * 12u];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, x[u]);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) x[u] = y[u];
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, x[u]);
+                r += 16u;
             }
             for (; r < m; ++r) acc = __fadd_rn(acc, b[r * 12u]);
         }

@@ -776,12 +776,14 @@ int syn_engine_deduplicate(syn_engine* e, const uint64_t* my_bb, const uint64_t*
     const size_t o_srow = take((size_t)cap * 4), o_sfirst = take((size_t)cap * 4);
     const size_t o_ka = take((size_t)(n + 1) * 4), o_va = take((size_t)(n + 1) * 4), o_kb = take((size_t)(n + 1) * 4), o_vb = take((size_t)(n + 1) * 4);
     const size_t o_hist = take((size_t)hist_n * 4), o_tmp = take(scan_tmp), o_big = take((size_t)(n / dd::BIG + 2) * 4), o_scal = take(256);
+    const size_t o_pv = take((size_t)n * 48);
     CUDA_TRY(e->dd_ws.reserve(off));
     uint8_t* w = e->dd_ws.p;
     uint32_t *slot_row = (uint32_t*)(w + o_srow), *slot_first = (uint32_t*)(w + o_sfirst);
     uint32_t *ka = (uint32_t*)(w + o_ka), *va = (uint32_t*)(w + o_va), *kb = (uint32_t*)(w + o_kb), *vb = (uint32_t*)(w + o_vb);
     uint32_t *hist = (uint32_t*)(w + o_hist), *tmp = (uint32_t*)(w + o_tmp), *big_list = (uint32_t*)(w + o_big);
     uint32_t *n_groups = (uint32_t*)(w + o_scal), *big_count = n_groups + 1;
+    float* pv = (float*)(w + o_pv);
     // ---- inputs: used in place when they already live on the device
     const void* src[4] = {my_bb, op_bb, pis, vs};
     const size_t elt[4] = {8, 8, 36, 12};
@@ -850,15 +852,16 @@ int syn_engine_deduplicate(syn_engine* e, const uint64_t* my_bb, const uint64_t*
     for (int i = 0; i < 6; ++i) tgt[i] = !dst[i] ? nullptr : (is_device_ptr(dst[i]) ? dst[i] : (void*)(e->dd_io.p + out_off[i]));
     o.my_bb = (uint64_t*)tgt[0]; o.op_bb = (uint64_t*)tgt[1]; o.num = (uint32_t*)tgt[2];
     o.states = (float*)tgt[3]; o.pis = (float*)tgt[4]; o.vs = (float*)tgt[5];
-    dd::reduce_kernel<<<(uint32_t)(((size_t)U * 16 + dd::T - 1) / dd::T), dd::T, 0, e->stream>>>(rows_sorted, gstart, n_groups, d_my, d_op, d_pis, d_vs, o,
-                                                                                                  big_list, big_count);
-    e->launches += 1;
+    dd::gather_kernel<<<(uint32_t)(((size_t)n * 16 + dd::T - 1) / dd::T), dd::T, 0, e->stream>>>(rows_sorted, n, d_pis, d_vs, pv);
+    dd::reduce_kernel<<<(uint32_t)(((size_t)U * 16 + dd::T - 1) / dd::T), dd::T, 0, e->stream>>>(rows_sorted, gstart, n_groups, d_my, d_op, pv, o, big_list,
+                                                                                                  big_count);
+    e->launches += 2;
     uint32_t nbig = 0;
     CUDA_TRY(cudaMemcpyAsync(&nbig, big_count, 4, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (nbig) {
         CUDA_TRY(cudaFuncSetAttribute(dd::reduce_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dd::BIG_SMEM));
-        dd::reduce_big_kernel<<<nbig, dd::BIG_T, dd::BIG_SMEM, e->stream>>>(rows_sorted, gstart, big_list, d_my, d_op, d_pis, d_vs, o);
+        dd::reduce_big_kernel<<<nbig, dd::BIG_T, dd::BIG_SMEM, e->stream>>>(rows_sorted, gstart, big_list, d_my, d_op, pv, o);
         e->launches += 1;
     }
     CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
