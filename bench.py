@@ -54,8 +54,10 @@ def size_workload(args):
         in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "4"))  # one CTA per SM, teams of 128 games
     elif args.leaf == "nn":
         in_flight = 148 * (512 // args.group_lanes)
+    elif args.group_lanes == 1:
+        in_flight = 148 * int(os.environ.get("SYN_ROLLOUT_THREADS", "512"))  # one CTA per SM, a thread per game
     else:
-        in_flight = 148 * 8 * (256 // (16 if args.group_lanes == 1 else args.group_lanes))
+        in_flight = 148 * 8 * (256 // args.group_lanes)
     args.in_flight = in_flight
     args.games = args.games or args.games_mult * in_flight
     return in_flight, args.games
@@ -376,7 +378,7 @@ def run_ours(args):
         kernel_s = dev_ns * 1e-9 / max(1, args.steps)  # rank 0's kernel, average launch duration
         achieved = bpe * (acc["explores"] / max(1, args.steps)) / kernel_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args),
-                    "kernel": ("selfplay_nn_tpg2_kernel" if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn" else "selfplay_rollout_kernel",
+                    "kernel": ("selfplay_nn_tpg2_kernel" if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn" else ("selfplay_rollout_tpg2_kernel" if args.group_lanes == 1 else "selfplay_rollout_kernel"),
                     "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": acc["explores"] / max(1, args.steps),
                     "launch_ms": 1e3 * kernel_s, "peak_source": peak_src, **shape,
                     "note": "latency-bound pointer chasing over per-game trees; see DESIGN.md"}

@@ -19,6 +19,7 @@
 #include "selfplay.cuh"
 #include "match.cuh"
 #include "tpg2.cuh"
+#include "tpg2_rollout.cuh"
 #include "dedup.cuh"
 #include "train.cuh"
 #include "train_cluster.cuh"
@@ -69,6 +70,7 @@ struct syn_engine {
     uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
     int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
     int tpg_teams = 4;     // teams of 128 threads per CTA in thread-per-game mode (512 threads, 128 registers each)
+    int rollout_threads = 512; // threads (= games) per CTA of the thread-per-game rollout kernel: 512, 640, 768 or 1024
     bool tpg_prof = false; // SYN_TPG_PROF=1: the instantiation with per-warp phase clocks
    // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
     DevBuf<uint32_t> slot_state;
@@ -158,6 +160,14 @@ static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     return SYN_OK;
 }
 
+template <int NT, int CW>
+static int launch_rollout_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
+    const size_t smem = tp2r::smem_bytes(NT);
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_rollout_tpg2_kernel<NT, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_rollout_tpg2_kernel<NT, CW><<<blocks, NT, smem, e->stream>>>(kp);
+    return SYN_OK;
+}
+
 static size_t nn_tc_smem_bytes(int gpb) { return sizeof(mlptc::Smem) + (size_t)gpb * 64 * sizeof(uint32_t); }
 static size_t nn_smem_bytes(int gpb) { return (size_t)(mlp::WEIGHT_FLOATS + 2 * gpb * mlp::XS + gpb * 64) * sizeof(float); }
 
@@ -187,7 +197,25 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         e->launches += 1;
         return SYN_OK;
     }
-    const int gl = e->group_lanes == 1 ? 16 : e->group_lanes; // rollout leaves: lane groups
+    if (!nn && e->group_lanes == 1) { // rollout leaves, thread per game (tpg2_rollout.cuh): one persistent CTA per SM
+        const uint32_t gpb = (uint32_t)e->rollout_threads;
+        uint32_t max_blocks = e->max_games / gpb;
+        if (max_blocks == 0) return fail(SYN_ERR_CAPACITY, "max_games_in_flight %u is smaller than one CTA's %u games", e->max_games, gpb);
+        // spread the games over the SMs first (whole warps), then fill the CTAs
+        uint32_t want_warps = (kp.num_games + 31u) / 32u;
+        uint32_t blocks = want_warps < (uint32_t)e->sm_count ? want_warps : (uint32_t)e->sm_count;
+        if (blocks > max_blocks) blocks = max_blocks;
+        if (blocks == 0) blocks = 1;
+        CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
+        int rc = e->rollout_threads == 1024 ? launch_rollout_tpg<1024, 3>(e, kp, blocks)
+                 : e->rollout_threads == 768 ? launch_rollout_tpg<768, 3>(e, kp, blocks)
+                 : e->rollout_threads == 640 ? launch_rollout_tpg<640, 5>(e, kp, blocks) : launch_rollout_tpg<512, 5>(e, kp, blocks);
+        if (rc) return rc;
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        return SYN_OK;
+    }
+    const int gl = e->group_lanes == 1 ? 16 : e->group_lanes; // lane groups (NN leaves without tensor cores land here too)
     const int threads = nn ? NN_THREADS : ROLLOUT_THREADS;
     const int gpb = threads / gl;
     uint32_t max_blocks = e->max_games / gpb;
@@ -362,6 +390,8 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     const char* penv = std::getenv("SYN_TPG_PROF");
     e->tpg_prof = penv && std::atoi(penv) == 1;
     if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 5 || std::atoi(tenv) == 6 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
+    const char* renv = std::getenv("SYN_ROLLOUT_THREADS");
+    if (renv && (std::atoi(renv) == 512 || std::atoi(renv) == 640 || std::atoi(renv) == 768 || std::atoi(renv) == 1024)) e->rollout_threads = std::atoi(renv);
     // round the in-flight game count up to whole CTAs of every kernel
     uint32_t unit = 1024;
     e->max_games = ((max_games_in_flight + unit - 1) / unit) * unit;

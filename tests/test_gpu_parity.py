@@ -223,8 +223,26 @@ def test_group_lanes_do_not_change_results(engine, leaf):
     for gl in (16, 1):
         assert_rows_equal(res[gl][0], res[32][0], f"GL{gl} vs GL32 experience")
         assert_rows_equal(res[gl][2], res[32][2], f"GL{gl} vs GL32 trace")
-        for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels"):
+        for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels",
+                  "rollout_plies"):
             assert res[gl][1][k] == res[32][1][k], (gl, k)
+
+
+@pytest.mark.parametrize("threads", [640, 768, 1024])
+def test_rollout_threads_per_cta_do_not_change_results(threads):
+    """selfplay_rollout_tpg2_kernel is instantiated for 512 (default), 640, 768 and 1024 games per CTA (different ring
+    sizes, path-table depths and child batches): identical rows, traces and counters."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=150, sample_actions_until=12)
+    def run():
+        with s.Engine(0, 2048, 150) as e:
+            return e.gather(cfg, L.LEAF_ROLLOUT, 5, 300, 9, trace=True)
+    a = run()
+    b = _with_env("SYN_ROLLOUT_THREADS", str(threads), run)
+    assert_rows_equal(a[0], b[0], "experience")
+    assert_rows_equal(a[2], b[2], "trace")
+    for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels",
+              "rollout_plies"):
+        assert a[1][k] == b[1][k], k
 
 
 def test_sharding_is_invisible(engine):
@@ -567,12 +585,14 @@ def _with_env(name, value, fn):
             os.environ[name] = old
 
 
-def test_backprop_reductions_equal_load_add_store(engine):
-    """The thread-per-game kernel adds a leaf's value into the path's nodes with one REDG.ADD.F32x4 per level; with
-    SYN_TPG_NO_RED=1 it loads, adds and stores like the CPU.  Same trees, same rows, same counters."""
+@pytest.mark.parametrize("leaf", ["nn", "rollout"])
+def test_backprop_reductions_equal_load_add_store(engine, leaf):
+    """The thread-per-game kernels add a leaf's value into the path's nodes with one REDG.ADD.F32x4 per level; with
+    SYN_TPG_NO_RED=1 they load, add and store like the CPU.  Same trees, same rows, same counters."""
     engine.set_weights(s.Connect4Net.new(4).blob())
     cfg = _config3(explores=300)
-    run = lambda: engine.gather(cfg, L.LEAF_NN, 0, 700, 2, trace=True)
+    kind = L.LEAF_NN if leaf == "nn" else L.LEAF_ROLLOUT
+    run = lambda: engine.gather(cfg, kind, 0, 700, 2, trace=True)
     a, st, tr = run()
     b, st2, tr2 = _with_env("SYN_TPG_NO_RED", "1", run)
     assert_rows_equal(a, b, "experience")
