@@ -55,7 +55,7 @@ def size_workload(args):
     elif args.leaf == "nn":
         in_flight = 148 * (512 // args.group_lanes)
     elif args.group_lanes == 1:
-        in_flight = 148 * int(os.environ.get("SYN_ROLLOUT_THREADS", "512"))  # one CTA per SM, a thread per game
+        in_flight = 148 * int(os.environ.get("SYN_ROLLOUT_THREADS", "1024"))  # one CTA per SM, a thread per game
     else:
         in_flight = 148 * 8 * (256 // args.group_lanes)
     args.in_flight = in_flight

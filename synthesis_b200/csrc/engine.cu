@@ -70,7 +70,8 @@ struct syn_engine {
     uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
     int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
     int tpg_teams = 4;     // teams of 128 threads per CTA in thread-per-game mode (512 threads, 128 registers each)
-    int rollout_threads = 512; // threads (= games) per CTA of the thread-per-game rollout kernel: 512, 640, 768 or 1024
+    int rollout_threads = 1024; // threads (= games) per CTA of the thread-per-game rollout kernel: 512, 640, 768, 896 or 1024
+    int rollout_cw = 3;         // child records per memory round trip at 896 / 1024 threads (SYN_ROLLOUT_CW = 3 or 5)
     bool tpg_prof = false; // SYN_TPG_PROF=1: the instantiation with per-warp phase clocks
    // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
     DevBuf<uint32_t> slot_state;
@@ -207,7 +208,9 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         if (blocks > max_blocks) blocks = max_blocks;
         if (blocks == 0) blocks = 1;
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-        int rc = e->rollout_threads == 1024 ? launch_rollout_tpg<1024, 3>(e, kp, blocks)
+        const bool cw5 = e->rollout_cw == 5;
+        int rc = e->rollout_threads == 1024 ? (cw5 ? launch_rollout_tpg<1024, 5>(e, kp, blocks) : launch_rollout_tpg<1024, 3>(e, kp, blocks))
+                 : e->rollout_threads == 896 ? (cw5 ? launch_rollout_tpg<896, 5>(e, kp, blocks) : launch_rollout_tpg<896, 3>(e, kp, blocks))
                  : e->rollout_threads == 768 ? launch_rollout_tpg<768, 3>(e, kp, blocks)
                  : e->rollout_threads == 640 ? launch_rollout_tpg<640, 5>(e, kp, blocks) : launch_rollout_tpg<512, 5>(e, kp, blocks);
         if (rc) return rc;
@@ -391,7 +394,9 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     e->tpg_prof = penv && std::atoi(penv) == 1;
     if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 5 || std::atoi(tenv) == 6 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
     const char* renv = std::getenv("SYN_ROLLOUT_THREADS");
-    if (renv && (std::atoi(renv) == 512 || std::atoi(renv) == 640 || std::atoi(renv) == 768 || std::atoi(renv) == 1024)) e->rollout_threads = std::atoi(renv);
+    if (renv && (std::atoi(renv) == 512 || std::atoi(renv) == 640 || std::atoi(renv) == 768 || std::atoi(renv) == 896 || std::atoi(renv) == 1024)) e->rollout_threads = std::atoi(renv);
+    const char* cwenv = std::getenv("SYN_ROLLOUT_CW");
+    if (cwenv && std::atoi(cwenv) == 5) e->rollout_cw = 5;
     // round the in-flight game count up to whole CTAs of every kernel
     uint32_t unit = 1024;
     e->max_games = ((max_games_in_flight + unit - 1) / unit) * unit;

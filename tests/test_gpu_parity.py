@@ -228,9 +228,9 @@ def test_group_lanes_do_not_change_results(engine, leaf):
             assert res[gl][1][k] == res[32][1][k], (gl, k)
 
 
-@pytest.mark.parametrize("threads", [640, 768, 1024])
+@pytest.mark.parametrize("threads", [512, 640, 768, 896])
 def test_rollout_threads_per_cta_do_not_change_results(threads):
-    """selfplay_rollout_tpg2_kernel is instantiated for 512 (default), 640, 768 and 1024 games per CTA (different ring
+    """selfplay_rollout_tpg2_kernel is instantiated for 1024 (default), 896, 768, 640 and 512 games per CTA (different ring
     sizes, path-table depths and child batches): identical rows, traces and counters."""
     cfg = s.study_connect4_rollout_cfg(num_explores=150, sample_actions_until=12)
     def run():
