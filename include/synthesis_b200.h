@@ -201,8 +201,14 @@ typedef struct {
     syn_mcts_cfg mcts;
 } syn_player_cfg;
 
+/* eval_against_old(p1, p2) with two DIFFERENT networks (evaluator.rs:131-161, called per older model at
+ * :87-94): players[1] of the following syn_engine_match calls evaluates its leaves with this blob (same
+ * layout as syn_engine_set_weights, host or device) when BOTH players use leaf_eval_kind = NN; players[0]
+ * keeps syn_engine_set_weights' network.  blob = NULL returns to one network for both. */
+int syn_engine_set_opponent_weights(syn_engine* e, const float* blob, size_t n_floats);
+
 /* Replaces the evaluator's game loops eval_against_rollout_mcts (evaluator.rs:163-198), mcts_vs_mcts
- * (:200-228) and eval_against_old (:129-160, one network) on a batch of independent matches: match i
+ * (:200-228) and eval_against_old (:129-160; p1 != p2 after syn_engine_set_opponent_weights) on a batch of independent matches: match i
  * starts from Connect4::new(), players[0] moves first, every move is `exploit` of the mover's player
  * (a fresh tree per move), and the game ends when Game::step reports is_over.  All RolloutPolicy
  * draws of match i — by either player — come from ONE stream StdRng::seed_from_u64(seeds[i]), as in
@@ -293,8 +299,9 @@ int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, f
 
 /* Lanes per game: 1 (default; a thread per game, 128 games = one tensor-core tile of leaves), 32 (a
  * warp per game) or 16 (two games per warp).  The SYN_GROUP_LANES environment variable overrides the
- * default at syn_engine_create.  Rollout leaves use lane groups (1 means 16 there).  Results do not
- * depend on it. */
+ * default at syn_engine_create.  With rollout leaves 1 is a thread per game too (the thread plays the
+ * rollout itself; SYN_ROLLOUT_THREADS = 512 / 640 / 768 / 896 / 1024 games per CTA, default 1024).
+ * Results do not depend on any of these. */
 int syn_engine_set_group_lanes(syn_engine* e, int lanes);
 
 /* Which kernel evaluates Connect4Net: 1 (default) = fp16-operand / fp32-accumulate GEMM chain on the

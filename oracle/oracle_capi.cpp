@@ -221,9 +221,12 @@ int orc_search(const syn_rollout_cfg* cfg, uint32_t tree_kind, uint64_t my_bb, u
 // player on a clone of the game; all RolloutPolicy draws of the match come from ONE
 // StdRng::seed_from_u64(seed) (evaluator.rs:172-173, 207-208).  Returns game.reward(first_player).
 // Trace per move: the column played, nodes.len() and the root's child visit counts by column.
-int orc_match(const syn_player_cfg* players, uint64_t seed, const uint32_t* explores2, const float* weights, orc_eval_fn callback,
-              void* ctx, uint32_t flags, float* result, uint8_t* n_moves, uint8_t* moves63, uint32_t* tree_nodes63,
-              float* child_visits63x9, syn_stats* stats) {
+// weights2 (optional): players[1]'s network when two different networks meet (eval_against_old, evaluator.rs:131-161);
+// mover_out (optional): set to the index of the player whose tree is being searched before every move, so that a
+// callback can tell whose leaf it is asked about.
+int orc_match2(const syn_player_cfg* players, uint64_t seed, const uint32_t* explores2, const float* weights, const float* weights2,
+               uint32_t* mover_out, orc_eval_fn callback, void* ctx, uint32_t flags, float* result, uint8_t* n_moves, uint8_t* moves63,
+               uint32_t* tree_nodes63, float* child_visits63x9, syn_stats* stats) {
     TreeOptions opt = opts_from(flags);
     Counters cnt;
     StdRng rng = StdRng::seed_from_u64(seed);
@@ -231,6 +234,7 @@ int orc_match(const syn_player_cfg* players, uint64_t seed, const uint32_t* expl
     StdRng fpu_rng = StdRng::seed_from_u64((seed ^ (1ull << 63)) + 1);
     RolloutPolicy<Connect4> rp(&rng, &cnt);
     Connect4Net net(weights, opt.libm);
+    Connect4Net net2(weights2 ? weights2 : weights, opt.libm);
     CallbackPolicy cb(callback, ctx);
     Connect4 game;
     int first_player = game.player();
@@ -239,8 +243,9 @@ int orc_match(const syn_player_cfg* players, uint64_t seed, const uint32_t* expl
     for (;;) {
         const syn_player_cfg& pl = players[ply & 1u];
         uint32_t E = explores2 ? explores2[ply & 1u] : pl.num_explores;
+        if (mover_out) *mover_out = ply & 1u;
         Policy<Connect4>* p = pl.leaf_eval_kind == SYN_LEAF_ROLLOUT ? (Policy<Connect4>*)&rp
-                              : (callback ? (Policy<Connect4>*)&cb : (Policy<Connect4>*)&net);
+                              : (callback ? (Policy<Connect4>*)&cb : ((ply & 1u) ? (Policy<Connect4>*)&net2 : (Policy<Connect4>*)&net));
         if (pl.leaf_eval_kind == SYN_LEAF_NN && !weights && !callback) return SYN_ERR_NO_WEIGHTS;
         int action;
         if (pl.tree_kind == SYN_TREE_MCTS) {
@@ -272,6 +277,13 @@ int orc_match(const syn_player_cfg* players, uint64_t seed, const uint32_t* expl
     if (n_moves) *n_moves = (uint8_t)ply;
     fill_stats(stats, cnt, ply, 1, 0);
     return 0;
+}
+
+int orc_match(const syn_player_cfg* players, uint64_t seed, const uint32_t* explores2, const float* weights, orc_eval_fn callback,
+              void* ctx, uint32_t flags, float* result, uint8_t* n_moves, uint8_t* moves63, uint32_t* tree_nodes63,
+              float* child_visits63x9, syn_stats* stats) {
+    return orc_match2(players, seed, explores2, weights, nullptr, nullptr, callback, ctx, flags, result, n_moves, moves63, tree_nodes63,
+                      child_visits63x9, stats);
 }
 
 // ---- gather with the engine's per-game streams.  trace_* (optional, one entry per row):

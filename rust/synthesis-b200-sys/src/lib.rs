@@ -150,6 +150,7 @@ extern "C" {
     pub fn syn_engine_create(cuda_device: c_int, max_games_in_flight: u32, max_explores: u32, out: *mut *mut syn_engine) -> c_int;
     pub fn syn_engine_destroy(e: *mut syn_engine);
     pub fn syn_engine_set_weights(e: *mut syn_engine, blob: *const f32, n_floats: usize) -> c_int;
+    pub fn syn_engine_set_opponent_weights(e: *mut syn_engine, blob: *const f32, n_floats: usize) -> c_int;
     pub fn syn_engine_gather(e: *mut syn_engine, cfg: *const syn_rollout_cfg, first_game_index: u64, num_games: u32, seed: u64,
                              out: *mut syn_experience, stats: *mut syn_stats) -> c_int;
     pub fn syn_engine_gather_launch(e: *mut syn_engine, cfg: *const syn_rollout_cfg, first_game_index: u64, num_games: u32, seed: u64) -> c_int;

@@ -7,7 +7,13 @@ for v in "1024 3" "1024 5" "896 3" "896 5"; do set -- $v
   SYN_ROLLOUT_THREADS=$1 SYN_ROLLOUT_CW=$2 timeout 300 python bench.py --leaf rollout $q > gpurun_out/rb_$1_$2.json 2> gpurun_out/rb_$1_$2.err
   echo "rollout threads $1 cw $2: $(python -c "import json;d=json.load(open('gpurun_out/rb_$1_$2.json'));print(round(d['value']/1e6,1))")"
 done
-for t in 5 6 8; do
+SYN_TPG_FAST_SELECT=1 timeout 300 python bench.py --leaf rollout $q > gpurun_out/rb_fast.json 2> gpurun_out/rb_fast.err
+echo "rollout 1024/3 fast select: $(python -c "import json;d=json.load(open('gpurun_out/rb_fast.json'));print(round(d['value']/1e6,1))")"
+for f in 0 1; do
+  SYN_TPG_FAST_SELECT=$f timeout 300 python bench.py $q > gpurun_out/nn_fast_$f.json 2> gpurun_out/nn_fast_$f.err
+  echo "nn teams 4 fast select $f: $(python -c "import json;d=json.load(open('gpurun_out/nn_fast_$f.json'));print(round(d['value']/1e6,1))")"
+done
+for t in 5 8; do
   SYN_TPG_TEAMS=$t timeout 300 python bench.py $q > gpurun_out/nn_teams_$t.json 2> gpurun_out/nn_teams_$t.err
   echo "nn teams $t: $(python -c "import json;d=json.load(open('gpurun_out/nn_teams_$t.json'));print(round(d['value']/1e6,1))")"
 done

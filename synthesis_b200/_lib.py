@@ -92,7 +92,7 @@ class SynStats(C.Structure):
 # every symbol include/synthesis_b200.h declares
 EXPORTED_SYMBOLS = (
     "syn_abi_version", "syn_build_info", "syn_last_error", "syn_engine_create", "syn_engine_destroy",
-    "syn_engine_set_weights", "syn_engine_gather", "syn_engine_gather_launch", "syn_engine_gather_wait",
+    "syn_engine_set_weights", "syn_engine_set_opponent_weights", "syn_engine_gather", "syn_engine_gather_launch", "syn_engine_gather_wait",
     "syn_engine_search", "syn_engine_match", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode", "syn_engine_debug_counters",
     "syn_engine_deduplicate", "syn_engine_train", "syn_engine_reset_optimizer", "syn_engine_get_weights",
 )
@@ -124,6 +124,7 @@ def load():
     lib.syn_engine_destroy.argtypes = [vp]
     lib.syn_engine_destroy.restype = None
     lib.syn_engine_set_weights.argtypes = [vp, vp, C.c_size_t]
+    lib.syn_engine_set_opponent_weights.argtypes = [vp, vp, C.c_size_t]
     lib.syn_engine_gather.argtypes = [vp, C.POINTER(SynRolloutCfg), u64, u32, u64, C.POINTER(SynExperience), C.POINTER(SynStats)]
     lib.syn_engine_gather_launch.argtypes = [vp, C.POINTER(SynRolloutCfg), u64, u32, u64]
     lib.syn_engine_gather_wait.argtypes = [vp, C.POINTER(SynExperience), C.POINTER(SynStats)]

@@ -78,6 +78,9 @@ struct syn_engine {
     DevBuf<uint4> nodes; // 2 x uint4 = one 32-byte record per tree node
     DevBuf<float> weights;
     DevBuf<uint8_t> weight_image; // mlptc layout (fp16 weights + fp32 biases)
+    DevBuf<float> weights2;        // players[1]'s network in a match between two different networks (syn_engine_set_opponent_weights)
+    DevBuf<uint8_t> weight_image2;
+    bool has_weights2 = false;
     bool has_weights = false;
     bool use_tc = true;           // Connect4Net on tcgen05 tensor cores (false: fp32 CUDA-core kernel)
     DevBuf<unsigned int> next_game;
@@ -271,6 +274,8 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.weight_image = e->weight_image.p;
     const char* nored = std::getenv("SYN_TPG_NO_RED"); // read per launch so that one test process can run both forms
     kp.no_reductions = (nored && std::atoi(nored) == 1) ? 1u : 0u;
+    const char* fsel = std::getenv("SYN_TPG_FAST_SELECT"); // likewise: the filter pass of tp2::descend, off unless asked for
+    kp.fast_select = (fsel && std::atoi(fsel) == 1) ? 1u : 0u;
 }
 
 static int read_stats(syn_engine* e, syn_stats* stats, float ms) {
@@ -345,10 +350,22 @@ static int launch_match(syn_engine* e, KParams& kp, mtc::MParams& mp) {
     if (active > per_cta) active = per_cta;
     if ((uint64_t)blocks * active > e->max_games) active = e->max_games / blocks;
     if (active == 0) { blocks = e->max_games; active = 1; }
+    if (mp.weight_image2) { // two resident weight images leave room for two teams' activation tiles
+        constexpr int T2 = 2;
+        const uint32_t per_cta2 = 128u * T2;
+        if (active > per_cta2) active = per_cta2;
+        mp.active_per_block = active;
+        size_t smem2 = sizeof(mlpteam::Smem<T2, T2>) + mlptc::IMG_BYTES;
+        CUDA_TRY(cudaFuncSetAttribute(match_tpg_kernel<T2, T2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        match_tpg_kernel<T2, T2, true><<<blocks, per_cta2, smem2, e->stream>>>(kp, mp);
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        return SYN_OK;
+    }
     mp.active_per_block = active;
     size_t smem = sizeof(mlpteam::Smem<MATCH_TEAMS, MATCH_TEAMS>);
-    CUDA_TRY(cudaFuncSetAttribute(match_tpg_kernel<MATCH_TEAMS, MATCH_TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    match_tpg_kernel<MATCH_TEAMS, MATCH_TEAMS><<<blocks, per_cta, smem, e->stream>>>(kp, mp);
+    CUDA_TRY(cudaFuncSetAttribute(match_tpg_kernel<MATCH_TEAMS, MATCH_TEAMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    match_tpg_kernel<MATCH_TEAMS, MATCH_TEAMS, false><<<blocks, per_cta, smem, e->stream>>>(kp, mp);
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
     return SYN_OK;
@@ -424,7 +441,7 @@ void syn_engine_destroy(syn_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->nodes.release(); e->slot_state.release(); e->weights.release(); e->weight_image.release(); e->next_game.release(); e->counters.release(); e->error.release();
+    e->nodes.release(); e->slot_state.release(); e->weights.release(); e->weight_image.release(); e->weights2.release(); e->weight_image2.release(); e->next_game.release(); e->counters.release(); e->error.release();
     e->row_my.release(); e->row_op.release(); e->row_off.release(); e->row_pi.release(); e->row_v.release(); e->row_visits.release();
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();
@@ -469,6 +486,23 @@ int syn_engine_set_weights(syn_engine* e, const float* blob, size_t n_floats) {
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (!dev) e->h2d += n_floats * sizeof(float);
     e->has_weights = true;
+    return SYN_OK;
+}
+
+int syn_engine_set_opponent_weights(syn_engine* e, const float* blob, size_t n_floats) {
+    if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    if (!blob) { e->has_weights2 = false; return SYN_OK; } // back to one network for both players
+    if (n_floats != SYN_N_WEIGHTS) return fail(SYN_ERR_INVALID_ARGUMENT, "expected %d floats (63-128-96-64-48-12 MLP), got %zu", SYN_N_WEIGHTS, n_floats);
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(e->weights2.reserve(SYN_N_WEIGHTS));
+    CUDA_TRY(e->weight_image2.reserve(mlptc::IMG_BYTES));
+    bool dev = is_device_ptr(blob);
+    CUDA_TRY(cudaMemcpyAsync(e->weights2.p, blob, n_floats * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights2.p, e->weight_image2.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (!dev) e->h2d += n_floats * sizeof(float);
+    e->has_weights2 = true;
     return SYN_OK;
 }
 
@@ -691,6 +725,8 @@ int syn_engine_match(syn_engine* e, const syn_player_cfg players[2], const uint6
     mp.players[0] = players[0]; mp.players[1] = players[1];
     mp.explores = explores ? e->s_nodes.p : nullptr;
     mp.result = e->s_q.p; mp.n_moves = e->s_rsol.p;
+    // two different networks (syn_engine_set_opponent_weights): only when both players ask for Connect4Net
+    if (e->has_weights2 && players[0].leaf_eval_kind == SYN_LEAF_NN && players[1].leaf_eval_kind == SYN_LEAF_NN) mp.weight_image2 = e->weight_image2.p;
     CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_ALL * sizeof(unsigned long long), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->error.p, 0, sizeof(int), e->stream));
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));

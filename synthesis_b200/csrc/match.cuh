@@ -78,17 +78,28 @@ __device__ __forceinline__ bool descend(const syn_mcts_cfg& cfg, uint32_t cap, G
         const float pterm = __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
         uint32_t b = 0u, bfc = 0u, bpk = 0u;
         float bval = 0.0f, bvis = 0.0f;
-        for (uint32_t k = 0; k < nch; ++k) {
-            Rec ch = load_rec(nodes, cfc + k);
-            uint32_t csol = (ch.pk >> 8) & 0xffu, cn = ch.pk & 0xffu;
-            float value;
-            if (csol == 0u && cn == 0u) {
-                value = __fadd_rn(cfg.fpu_a, __uint_as_float(ch.prior));
-            } else {
-                float q = csol ? sol_value(sol_reversed(csol)) : -__fdiv_rn(ch.o0, ch.vis);
-                value = __fadd_rn(q, __fdiv_rn(pterm, __fsqrt_rn(ch.vis)));
+        // five children per trip: their records are requested together (a level costs ceil(nch / 5) memory round trips
+        // instead of nch), scored in child order like the reference's loop
+        for (uint32_t k0 = 0; k0 < nch; k0 += 5u) {
+            Rec chs[5];
+#pragma unroll
+            for (uint32_t j = 0; j < 5u; ++j) chs[j] = load_rec(nodes, cfc + (k0 + j < nch ? k0 + j : nch - 1u));
+#pragma unroll
+            for (uint32_t j = 0; j < 5u; ++j) {
+                const uint32_t k = k0 + j;
+                if (k < nch) {
+                    const Rec& ch = chs[j];
+                    uint32_t csol = (ch.pk >> 8) & 0xffu, cn = ch.pk & 0xffu;
+                    float value;
+                    if (csol == 0u && cn == 0u) {
+                        value = __fadd_rn(cfg.fpu_a, __uint_as_float(ch.prior));
+                    } else {
+                        float q = csol ? sol_value(sol_reversed(csol)) : -__fdiv_rn(ch.o0, ch.vis);
+                        value = __fadd_rn(q, __fdiv_rn(pterm, __fsqrt_rn(ch.vis)));
+                    }
+                    if (k == 0u || value > bval) { b = k; bval = value; bvis = ch.vis; bfc = ch.fc; bpk = ch.pk; }
+                }
             }
-            if (k == 0u || value > bval) { b = k; bval = value; bvis = ch.vis; bfc = ch.fc; bpk = ch.pk; }
         }
         g.cnt[CNT_SELECT_LEVELS] += 1u;
         g.cnt[CNT_CHILDREN_SCANNED] += nch;
@@ -206,7 +217,7 @@ __device__ __noinline__ int rollout(rng::Stream& st, uint64_t my, uint64_t op, u
         uint64_t occ = my | op;
         uint64_t legal = (~(occ >> 6)) & c4::ROW0; // bit 7c set <=> column c has room
         uint32_t n = (uint32_t)__popcll(legal);
-        uint32_t hi = st.gen_range_u8(n);
+        uint32_t hi = st.gen_range_1to9(n);
         for (uint32_t t = 0; t < hi; ++t) legal &= legal - 1; // hi-th legal column, ascending
         int p7 = __ffsll((long long)legal) - 1;
         uint64_t bit = (occ + (1ull << p7)) & (0x7full << p7);
@@ -225,6 +236,7 @@ struct MParams { // what a match launch adds to KParams
     float* result;            // [n]
     uint8_t* n_moves;         // [n]
     uint32_t active_per_block; // threads of a CTA that play (arena slot = block * active + thread)
+    const uint8_t* weight_image2; // players[1]'s network when it differs from players[0]'s (eval_against_old), else null
 };
 
 __device__ __forceinline__ const syn_player_cfg& mover(const MParams& m, const Game& g) { return m.players[g.ply & 1u]; }
@@ -358,12 +370,16 @@ __device__ __forceinline__ void finish_nn(const KParams& p, const MParams& m, Ga
 namespace eng {
 
 // One persistent CTA per SM, TEAMS teams of 128 threads; thread = match (or search root).
-template <int TEAMS, int SLOTS>
+// TWO: players[1] evaluates its leaves with a second network (eval_against_old, evaluator.rs:129-160, with p1 != p2):
+// both images stay resident, and a round in which a team holds leaves of both players runs the forward once per image.
+template <int TEAMS, int SLOTS, bool TWO>
 __global__ void __launch_bounds__(128 * TEAMS, 1) match_tpg_kernel(const __grid_constant__ KParams p, const __grid_constant__ mtc::MParams m) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     mlpteam::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS, SLOTS>*>(smem_raw);
+    uint8_t* const img2 = smem_raw + sizeof(mlpteam::Smem<TEAMS, SLOTS>);
     const bool any_nn = m.players[0].leaf_eval_kind == SYN_LEAF_NN || m.players[1].leaf_eval_kind == SYN_LEAF_NN;
     if (any_nn) mlpteam::setup<TEAMS, SLOTS>(ms, p.weight_image);
+    if (TWO) mlpteam::load_second_image<TEAMS, SLOTS>(ms, img2, m.weight_image2);
     const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
     tpg::Game g;
     tpg::init_game(p, g, (size_t)blockIdx.x * m.active_per_block + (threadIdx.x < m.active_per_block ? threadIdx.x : 0u));
@@ -378,12 +394,26 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) match_tpg_kernel(const __grid_
         __syncwarp();
         if (!mlpteam::team_any(team, st != 0)) break; // no thread of this team has a match left
         if (!any_nn) continue;
-        if (!mlpteam::team_any(team, st == 1)) continue; // nobody needs the network this round
+        const bool second = TWO && st == 1 && (g.ply & 1u) != 0u; // this leaf belongs to players[1]'s tree
+        const bool any1 = mlpteam::team_any(team, st == 1 && !second);
+        const bool any2 = TWO && mlpteam::team_any(team, second);
+        if (!any1 && !any2) continue; // nobody needs a network this round
         uint32_t mma_phase;
         const int slot = mlpteam::acquire_slot<TEAMS, SLOTS>(ms, team, r, mma_phase);
-        if (st == 1) mlpteam::write_features(ms.a[slot], ms.col_lut, r, my, op);
         float y[12];
-        mlpteam::forward<TEAMS, SLOTS>(ms, team, slot, r, mma_phase, y);
+        if (any1) {
+            if (st == 1) mlpteam::write_features(ms.a[slot], ms.col_lut, r, my, op);
+            mlpteam::forward<TEAMS, SLOTS>(ms, team, slot, r, mma_phase, y);
+        }
+        if (any2) { // the chain overwrites its A tile in place, so the features are written again
+            float y2[12];
+            if (st == 1) mlpteam::write_features(ms.a[slot], ms.col_lut, r, my, op);
+            mlpteam::forward_img<TEAMS, SLOTS>(ms, img2, team, slot, r, mma_phase, y2);
+            if (second) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) y[k] = y2[k];
+            }
+        }
         mlpteam::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
         if (st == 1) mtc::finish_nn(p, m, g, lf, y);
         __syncwarp();

@@ -174,8 +174,9 @@ __device__ __forceinline__ void release_slot(Smem<TEAMS, SLOTS>& s, int team, in
 // already in the slot's A tile (generic-proxy stores); `phase` is the running parity of the slot's
 // mbarrier (acquire_slot / release_slot carry it).  On return y[0..8] are the row's policy logits and
 // y[9..11] its value logits.
+// `img` = the resident weight image to use (s.img, or a second image of the same layout elsewhere in shared memory).
 template <int TEAMS, int SLOTS>
-__device__ __forceinline__ void forward(Smem<TEAMS, SLOTS>& s, int team, int slot, int r, uint32_t& phase, float (&y)[12]) {
+__device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t* img, int team, int slot, int r, uint32_t& phase, float (&y)[12]) {
     uint8_t* a_tile = s.a[slot];
     const uint32_t tmem = s.tmem_base + (uint32_t)(slot * 128);           // the slot's 128 accumulator columns
     const uint32_t tlane = tmem + ((uint32_t)((r >> 5) * 32) << 16);       // this warp's 32 TMEM lanes
@@ -187,7 +188,7 @@ __device__ __forceinline__ void forward(Smem<TEAMS, SLOTS>& s, int team, int slo
         team_sync(team);
         if (r == 0) {
             tc_fence_after();
-            const uint32_t a_base = smem_u32(a_tile), b_base = smem_u32(s.img + w_off(l));
+            const uint32_t a_base = smem_u32(a_tile), b_base = smem_u32(img + w_off(l));
 #pragma unroll
             for (int kk = 0; kk < K / 16; ++kk) {
                 uint64_t ad = make_desc(a_base + kk * 2 * (M_TILE * 16), M_TILE * 16, 128);
@@ -199,7 +200,7 @@ __device__ __forceinline__ void forward(Smem<TEAMS, SLOTS>& s, int team, int slo
         mbar_wait(&s.bar_mma[slot], phase);
         phase ^= 1u;
         tc_fence_after();
-        const float* bias = reinterpret_cast<const float*>(s.img + BIAS_OFF) + b_off(l);
+        const float* bias = reinterpret_cast<const float*>(img + BIAS_OFF) + b_off(l);
 #pragma unroll
         for (int c16 = 0; c16 < N / 16; ++c16) {
             uint32_t v[16];
@@ -227,6 +228,24 @@ __device__ __forceinline__ void forward(Smem<TEAMS, SLOTS>& s, int team, int slo
     }
     // the next forward()'s first team_sync orders these TMEM reads before the next MMA overwrites D
     tc_fence_before();
+}
+
+template <int TEAMS, int SLOTS>
+__device__ __forceinline__ void forward(Smem<TEAMS, SLOTS>& s, int team, int slot, int r, uint32_t& phase, float (&y)[12]) {
+    forward_img<TEAMS, SLOTS>(s, s.img, team, slot, r, phase, y);
+}
+
+// A second resident image (evaluation matches between two different networks): bulk-copied behind the first on the
+// same mbarrier.  All threads of the CTA call, after setup().
+template <int TEAMS, int SLOTS>
+__device__ __forceinline__ void load_second_image(Smem<TEAMS, SLOTS>& s, uint8_t* dst, const uint8_t* __restrict__ weight_image) {
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s.bar_w, IMG_BYTES);
+        bulk_g2s(dst, weight_image, IMG_BYTES, &s.bar_w);
+    }
+    mbar_wait(&s.bar_w, 1);
+    fence_proxy_async();
+    __syncthreads();
 }
 
 } // namespace mlpteam

@@ -73,6 +73,15 @@ struct Stream {
             if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
         }
     }
+    // the same for n in 1..9 (a Connect4 move count) without the modulo: 2^32 mod n comes from a packed table
+    __device__ uint32_t gen_range_1to9(uint32_t n) {
+        const uint32_t zone = 0xffffffffu - (uint32_t)((0x4044101000ull >> (4u * n)) & 15ull);
+        for (;;) {
+            uint32_t v = next_u32();
+            uint64_t m = (uint64_t)v * (uint64_t)n;
+            if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
+        }
+    }
     __device__ float next_f32_01() { return __uint_as_float((next_u32() >> 9) | 0x3f800000u) - 1.0f; }
 };
 

@@ -50,6 +50,15 @@ class Engine:
         b = np.ascontiguousarray(blob, dtype=np.float32).reshape(-1)
         L.check(self._lib.syn_engine_set_weights(self._h, _ptr(b), b.size))
 
+    def set_opponent_weights(self, blob):
+        """players[1]'s network in matches between two Connect4Net players (eval_against_old with p1 != p2,
+        evaluator.rs:129-160); None: both players use set_weights' network again."""
+        if blob is None:
+            L.check(self._lib.syn_engine_set_opponent_weights(self._h, None, 0))
+            return
+        b = np.ascontiguousarray(blob, dtype=np.float32).reshape(-1)
+        L.check(self._lib.syn_engine_set_opponent_weights(self._h, _ptr(b), b.size))
+
     def set_mlp_mode(self, tensor_cores: bool):
         """True (default): Connect4Net on the tcgen05 tensor cores; False: the fp32 CUDA-core kernel."""
         L.check(self._lib.syn_engine_set_mlp_mode(self._h, int(bool(tensor_cores))))

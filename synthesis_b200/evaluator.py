@@ -80,13 +80,31 @@ def mcts_vs_mcts(engine: Engine, cfg: EvaluationConfig, player: int, p1_explores
     return (out["result"], out, stats) if trace else out["result"]
 
 
-def eval_against_old(engine: Engine, cfg: EvaluationConfig, p1: Connect4Net, n_games: int = 1, trace: bool = False):
-    """evaluator.rs:129-160 with p1 == p2 (self-match of one network; two different networks in one
-    launch need two resident weight images and are not supported yet)."""
+def eval_against_old(engine: Engine, cfg: EvaluationConfig, p1: Connect4Net, p2: Connect4Net = None, n_games: int = 1, trace: bool = False):
+    """evaluator.rs:129-160: p1 (moves first) against p2, both `MCTS::exploit` with the policy's settings; returns
+    game.reward(first_player) per game (the game is deterministic: the reference plays it once per colour,
+    evaluator.rs:87-94).  p2 = None plays p1 against itself.  Both weight images stay resident in the kernel."""
     engine.set_weights(p1.blob())
-    nn = _policy_player(cfg)
-    out, stats = engine.match((nn, nn), np.zeros(n_games, np.uint64), None, trace=trace)
+    engine.set_opponent_weights(None if p2 is None else p2.blob())
+    try:
+        nn = _policy_player(cfg)
+        out, stats = engine.match((nn, nn), np.zeros(n_games, np.uint64), None, trace=trace)
+    finally:
+        engine.set_opponent_weights(None)
     return (out["result"], out, stats) if trace else out["result"]
+
+
+def evaluate_against_old_models(engine: Engine, cfg: EvaluationConfig, policy: Connect4Net, name: str, old, pgn=None):
+    """evaluator.rs:87-94: the newest model against each of the best older ones, once as each colour.  `old` = [(name, net)].
+    Returns [(white, black, reward)] in the reference's order and writes the PGN records."""
+    records = []
+    for old_name, old_net in old:
+        records.append((name, old_name, float(eval_against_old(engine, cfg, policy, old_net)[0])))
+        records.append((old_name, name, float(eval_against_old(engine, cfg, old_net, policy)[0])))
+    if pgn is not None:
+        for w, b, r in records:
+            add_pgn_result(pgn, w, b, r)
+    return records
 
 
 def add_pgn_result(pgn, white_name: str, black_name: str, white_reward: float) -> None:

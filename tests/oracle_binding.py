@@ -39,6 +39,8 @@ class Oracle:
                                            C.POINTER(L.SynExperience), C.POINTER(L.SynStats), C.c_void_p, C.c_void_p]
         l.orc_match.argtypes = [C.POINTER(L.SynPlayerCfg), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32] + \
                                [C.c_void_p] * 5 + [C.POINTER(L.SynStats)]
+        l.orc_match2.argtypes = [C.POINTER(L.SynPlayerCfg), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_uint32] + [C.c_void_p] * 5 + [C.POINTER(L.SynStats)]
         l.orc_mlp_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         l.orc_c4_play.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8
         l.orc_c4_won.argtypes = [C.c_uint64]
@@ -110,17 +112,21 @@ class Oracle:
         assert rc == 0, rc
         return dict(child_visits=cv, child_solution=cs, root_q=rq, root_solution=rs.value, best_action=ba.value, num_nodes=nn.value), st.as_dict()
 
-    def match(self, players, seed, explores2=None, weights=None, callback=None, flags=0):
-        """One evaluation match (evaluator.rs:129-228); players = two objects with .to_c() -> SynPlayerCfg."""
+    def match(self, players, seed, explores2=None, weights=None, callback=None, flags=0, weights2=None, mover=None):
+        """One evaluation match (evaluator.rs:129-228); players = two objects with .to_c() -> SynPlayerCfg.
+        weights2 = players[1]'s network (two-network eval_against_old); mover = a ctypes.c_uint32 the oracle sets to the
+        index of the player to move before every search (for callbacks that stand in for two networks)."""
         pc = (L.SynPlayerCfg * 2)(players[0].to_c(), players[1].to_c())
         res, nm = C.c_float(), C.c_uint8()
         moves, nodes, cv = np.zeros(63, np.uint8), np.zeros(63, np.uint32), np.zeros((63, 9), np.float32)
         ex = None if explores2 is None else np.ascontiguousarray(explores2, np.uint32)
         w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        w2 = None if weights2 is None else np.ascontiguousarray(weights2, np.float32)
         cb = EVAL_FN(callback) if callback else None
         st = L.SynStats()
-        rc = self.lib.orc_match(pc, int(seed), _p(ex), _p(w), C.cast(cb, C.c_void_p) if cb else None, None, flags,
-                                C.cast(C.byref(res), C.c_void_p), C.cast(C.byref(nm), C.c_void_p), _p(moves), _p(nodes), _p(cv), C.byref(st))
+        rc = self.lib.orc_match2(pc, int(seed), _p(ex), _p(w), _p(w2), C.cast(C.byref(mover), C.c_void_p) if mover is not None else None,
+                                 C.cast(cb, C.c_void_p) if cb else None, None, flags,
+                                 C.cast(C.byref(res), C.c_void_p), C.cast(C.byref(nm), C.c_void_p), _p(moves), _p(nodes), _p(cv), C.byref(st))
         assert rc == 0, rc
         return dict(result=res.value, n_moves=nm.value, moves=moves, tree_nodes=nodes, child_visits=cv), st.as_dict()
 

@@ -490,6 +490,50 @@ def test_match_nn_mcts_vs_rollout_frozen_bit_exact(engine, oracle):
             _assert_match_equal(out, i, ref, what)
 
 
+def test_match_two_networks_bit_exact(engine, oracle):
+    """eval_against_old(p1, p2) with p1 != p2 (evaluator.rs:131-161, called at :87-94): both weight images resident, a
+    forward per image in rounds where a team holds leaves of both players.  The oracle is fed each side's GPU leaf
+    outputs (a second small engine holds p2), so moves, per-move visit counts and tree sizes must be identical; and the
+    result must change sides correctly when the two networks swap colours."""
+    import ctypes
+    import synthesis_b200.evaluator as ev
+    p1, p2 = s.Connect4Net.new(21), s.Connect4Net.new(22)
+    nn = ev.Player(L.TREE_MCTS, L.LEAF_NN, 150, s.study_connect4_mcts_cfg(), s.ActionSelection.NumVisits)
+    mover = ctypes.c_uint32(0)
+    with s.Engine(0, 1024, 8) as e2:
+        for first, second, what in ((p1, p2, "p1 first"), (p2, p1, "p2 first")):
+            engine.set_weights(first.blob())
+            engine.set_opponent_weights(second.blob())
+            e2.set_weights(second.blob())
+            try:
+                out, st = engine.match((nn, nn), np.zeros(3, np.uint64))
+            finally:
+                engine.set_opponent_weights(None)
+
+            def cb(ctx, my, op, logits, probs):
+                lg, pr = (e2 if mover.value else engine).eval([my], [op])
+                for i in range(9):
+                    logits[i] = float(lg[0, i])
+                for i in range(3):
+                    probs[i] = float(pr[0, i])
+            ref, rst = oracle.match((nn, nn), 0, callback=cb, mover=mover)
+            for i in range(3):  # the game is deterministic: every copy is the same game
+                _assert_match_equal(out, i, ref, what)
+            assert st["explores"] == 3 * rst["explores"]
+    # the host mirror: same games through eval_against_old, and one network against itself is unchanged by the detour
+    cfg = s.EvaluationConfig(policy_num_explores=150, policy_action=s.ActionSelection.NumVisits, policy_mcts_cfg=s.study_connect4_mcts_cfg(),
+                             rollout_action=s.ActionSelection.Q, rollout_num_explores=[100], rollout_mcts_cfg=s.study_connect4_rollout_mcts_cfg(),
+                             num_games_against_rollout=1)
+    r12, o12, _ = ev.eval_against_old(engine, cfg, p1, p2, trace=True)
+    r21, o21, _ = ev.eval_against_old(engine, cfg, p2, p1, trace=True)
+    assert np.array_equal(o21["moves"][0][:int(o21["n_moves"][0])], out["moves"][0][:int(out["n_moves"][0])]) and float(r21[0]) == float(out["result"][0])
+    r11a = ev.eval_against_old(engine, cfg, p1)
+    r11b = ev.eval_against_old(engine, cfg, p1, p1)
+    assert float(r11a[0]) == float(r11b[0])
+    recs = ev.evaluate_against_old_models(engine, cfg, p1, "model_1.ot", [("model_0.ot", p2)])
+    assert recs == [("model_1.ot", "model_0.ot", float(r12[0])), ("model_0.ot", "model_1.ot", float(r21[0]))]
+
+
 def test_evaluator_sweep_and_pgn(engine):
     """configs[4] through the host mirror of evaluator.rs:65-82: results are +-1/0 and the PGN text is the reference's."""
     import io
@@ -599,6 +643,31 @@ def test_backprop_reductions_equal_load_add_store(engine, leaf):
     assert_rows_equal(tr, tr2, "trace")
     for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels"):
         assert st[k] == st2[k], k
+
+
+@pytest.mark.parametrize("leaf", ["nn", "rollout"])
+def test_fast_select_equals_exact_select(engine, oracle, leaf):
+    """SYN_TPG_FAST_SELECT=1: select_best_child first scores the children with approximate reciprocals and error bounds
+    and only falls back to the reference's IEEE divisions when the bounds overlap.  The chosen child must be the same
+    every time: identical trees, rows and counters — and identical to the oracle where it can replay the games."""
+    engine.set_weights(s.Connect4Net.new(5).blob())
+    kind = L.LEAF_NN if leaf == "nn" else L.LEAF_ROLLOUT
+    for cfg, games in ((_config3(explores=300), 700), (s.study_connect4_rollout_cfg(num_explores=800, sample_actions_until=30), 300)):
+        run = lambda: engine.gather(cfg, kind, 0, games, 3, trace=True)
+        a, st, tr = run()
+        b, st2, tr2 = _with_env("SYN_TPG_FAST_SELECT", "1", run)
+        assert_rows_equal(a, b, "experience")
+        assert_rows_equal(tr, tr2, "trace")
+        for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels",
+                  "rollout_plies"):
+            assert st[k] == st2[k], k
+    if leaf == "rollout":
+        cfg = s.study_connect4_rollout_cfg(num_explores=200, sample_actions_until=20)
+        cfg.mcts_cfg.fpu = s.Fpu.ParentQ()
+        b, st2, tr2 = _with_env("SYN_TPG_FAST_SELECT", "1", lambda: engine.gather(cfg, kind, 0, 24, 1, trace=True))
+        ra, rst, rtr = oracle.gather(cfg.to_c(kind), 1, 0, 24, threads=8)
+        assert_rows_equal(tr2, rtr, "trace vs oracle")
+        assert_rows_equal(b, ra, "experience vs oracle")
 
 
 def test_backprop_with_subnormal_values_is_bit_exact(engine, oracle):
