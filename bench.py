@@ -203,7 +203,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    cpu_games = args.cpu_games or 96 * cores
+    cpu_games = args.cpu_games or (96 if args.leaf == "nn" else 768) * cores  # rollout leaves are ~8x cheaper on the CPU
     size_workload(args)  # the same `config` as our arm; every step times a bounded sample of that workload
     games = cpu_games
     for w in range(args.warmup):
@@ -385,7 +385,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cgames = args.cpu_games or 96 * cores
+            cgames = args.cpu_games or (96 if args.leaf == "nn" else 768) * cores
             cst, cdt, cores = cpu_reference_run(args, cgames, 0)
             cpu = {"value": cst["explores"] / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d games (%d explores, %.1f s), reference schedule: %d worker threads, per-worker memo cache"

@@ -60,3 +60,32 @@ pub fn eval_against_rollout_sweep_b200(
     }
     Ok(())
 }
+
+/// Replaces evaluator.rs:87-94 + eval_against_old (:131-161): the new model against one of the best older models,
+/// once as each colour.  Both networks stay resident in the match kernel; the game is deterministic, one match each.
+pub fn eval_against_old_b200(
+    engine: *mut ffi::syn_engine,
+    cfg: &EvaluationConfig,
+    name: &String,
+    weights: &[f32],
+    prev_name: &String,
+    prev_weights: &[f32],
+    pgn: &mut std::fs::File,
+) -> std::io::Result<()> {
+    let nn = player(0, 0, cfg.policy_num_explores, cfg.policy_action, &cfg.policy_mcts_cfg);
+    let players = [nn, nn];
+    let seed = [0u64];
+    for (first, second, white, black) in [(weights, prev_weights, name, prev_name), (prev_weights, weights, prev_name, name)].iter() {
+        let mut result = [0f32];
+        unsafe {
+            assert_eq!(ffi::syn_engine_set_weights(engine, first.as_ptr(), first.len()), 0);
+            assert_eq!(ffi::syn_engine_set_opponent_weights(engine, second.as_ptr(), second.len()), 0);
+            let rc = ffi::syn_engine_match(engine, players.as_ptr(), seed.as_ptr(), std::ptr::null(), 1, result.as_mut_ptr(),
+                                           std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut());
+            assert_eq!(rc, 0, "syn_engine_match failed");
+            assert_eq!(ffi::syn_engine_set_opponent_weights(engine, std::ptr::null(), 0), 0);
+        }
+        add_pgn_result(pgn, white, black, result[0])?;
+    }
+    Ok(())
+}

@@ -274,8 +274,6 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.weight_image = e->weight_image.p;
     const char* nored = std::getenv("SYN_TPG_NO_RED"); // read per launch so that one test process can run both forms
     kp.no_reductions = (nored && std::atoi(nored) == 1) ? 1u : 0u;
-    const char* fsel = std::getenv("SYN_TPG_FAST_SELECT"); // likewise: the filter pass of tp2::descend, off unless asked for
-    kp.fast_select = (fsel && std::atoi(fsel) == 1) ? 1u : 0u;
 }
 
 static int read_stats(syn_engine* e, syn_stats* stats, float ms) {

@@ -28,7 +28,6 @@ struct KParams {
     uint32_t num_games;
     uint32_t search_mode; // 1: one tree per given position, no game loop (syn_engine_search)
     uint32_t no_reductions; // tpg2.cuh: 1 = backprop by load / add / store only (SYN_TPG_NO_RED=1; the parity suite runs both)
-    uint32_t fast_select;   // tpg2.cuh: 1 = select_best_child tries the division-free filter pass first (SYN_TPG_FAST_SELECT)
     uint32_t arena_nodes;
     uint4* nodes; // tree arenas: arena_nodes 32-byte records per game slot (tree.cuh)
     unsigned int* next_game;

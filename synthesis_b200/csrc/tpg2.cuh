@@ -64,11 +64,6 @@ __device__ __forceinline__ void red_stat(uint4* nodes, uint32_t i, float v0, flo
 // so the flushing adder and the IEEE adder agree bit for bit.  The first value that fails makes the tree
 // "slow" (Game::slow) until it is reset: it then only uses load / FADD / store.
 __device__ __forceinline__ bool red_exact(float x) { return ((__float_as_uint(x) << 1) >= (27u << 24)) || ((__float_as_uint(x) << 1) == 0u); }
-__device__ __forceinline__ float rcp_approx(float x) { // MUFU.RCP: relative error <= 2^-23
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 __device__ __forceinline__ void prefetch_l2(const uint4* nodes, uint32_t i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + 2 * (size_t)i)); }
 __device__ __forceinline__ uint32_t* meta_words(uint4* nodes, uint32_t i) { return reinterpret_cast<uint32_t*>(nodes + 2 * (size_t)i + 1); }
 enum { MW_PRIOR = 0, MW_PARENT = 1, MW_FC = 2, MW_PK = 3 };
@@ -137,8 +132,6 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
     uint32_t cfc = root.fc, cpk = root.pk;
     uint32_t depth = 0;
     const bool puct = cfg.exploration_kind == SYN_EXPLORATION_POLYNOMIAL_UCT;
-    // the filter pass below covers the shipped configuration; everything else is scored exactly right away
-    const bool fast_ok = p.fast_select != 0u && puct && FPU != SYN_FPU_NORMAL && cfg.select_solved_nodes != 0u;
     for (;;) {
         uint32_t sol = (cpk >> 8) & 0xffu, nch = cpk & 0xffu;
         if (sol) { rc.levels = depth; pd.kind = K_TERMINAL; pd.id = cur; pd.fc = sol; pd.depth = depth; return 0; } // mcts.rs:314-316
@@ -150,56 +143,7 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
         const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
         const float fpu_q = PQ ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : cfg.fpu_a; // Fpu::ParentQ = parent.q() (mcts.rs:353), once per level
         uint32_t b = 0u, bfc = 0u, bpk = 0u;
-        float bvis = 0.0f, bo0 = 0.0f, bo2 = 0.0f;
-        bool exact_pass = !fast_ok;
-        if (fast_ok) {
-            // ---- filter pass: the same scores with MUFU.RCP instead of the two IEEE divisions, each with a bound on
-            // its distance from the exact score.  When one child's interval lies above everybody else's (or ties are
-            // between children with identical inputs, which the later one loses) it IS the first strict maximum and no
-            // division was needed; otherwise the level is rescored exactly below.
-            float blo = 0.0f, bhi = 0.0f, bd = 0.0f;
-            uint32_t bprior = 0u;
-            for (uint32_t k0 = 0; k0 < nch && !exact_pass; k0 += (uint32_t)CW) {
-                Rec chs[CW];
-#pragma unroll
-                for (uint32_t j = 0; j < (uint32_t)CW; ++j) chs[j] = load_rec(nodes, cfc + min(k0 + j, nch - 1u));
-#pragma unroll
-                for (uint32_t j = 0; j < (uint32_t)CW; ++j) {
-                    const uint32_t k = k0 + j;
-                    const Rec& ch = chs[j];
-                    const uint32_t csol = (ch.pk >> 8) & 0xffu, cn = ch.pk & 0xffu;
-                    const float cp = __fmul_rn(__fmul_rn(cfg.c, __uint_as_float(ch.prior)), pterm);
-                    const bool visited = ch.vis != 0.0f;
-                    const float r = rcp_approx(visited ? ch.vis : 1.0f), r1 = rcp_approx(__fadd_rn(1.0f, ch.vis));
-                    float q, d = __uint_as_float(0x7fc00000u); // d: o2 - o0 of a visited unsolved child, else NaN (never equal)
-                    bool inexact = visited; // u = cp / (1 + 0) is exact for an unvisited child
-                    if (csol) {
-                        uint32_t kd = sol_kind(csol);
-                        q = kd == SYN_KIND_WIN ? -1.0f : (kd == SYN_KIND_LOSE ? 1.0f : 0.0f);
-                    } else if (cn == 0u) {
-                        q = fpu_q;
-                    } else {
-                        d = __fsub_rn(ch.o2, ch.o0);
-                        q = -__fmul_rn(d, r);
-                        inexact = true;
-                    }
-                    const float u = visited ? __fmul_rn(cp, r1) : cp;
-                    const float a = __fadd_rn(q, u);
-                    const float eps = inexact ? __fmaf_rn(__fadd_rn(fabsf(q), fabsf(u)), 9.5367431640625e-07f, 1e-30f) : 0.0f; // 2^-20 relative
-                    const float lo = __fsub_rn(a, eps), hi = __fadd_rn(a, eps);
-                    if (k < nch) {
-                        if (k == 0u || lo > bhi) { // strictly above every earlier child
-                            b = k; blo = lo; bhi = hi; bd = d; bprior = ch.prior; bvis = ch.vis; bfc = ch.fc; bpk = ch.pk;
-                            if (PQ) { bo0 = ch.o0; bo2 = ch.o2; }
-                        } else if (!(hi <= blo) && !(d == bd && ch.vis == bvis && ch.prior == bprior)) {
-                            exact_pass = true; // overlapping intervals (or a NaN): decide with the reference's arithmetic
-                        }
-                    }
-                }
-            }
-        }
-        if (exact_pass) {
-        float bval = 0.0f;
+        float bval = 0.0f, bvis = 0.0f, bo0 = 0.0f, bo2 = 0.0f;
         for (uint32_t k0 = 0; k0 < nch; k0 += (uint32_t)CW) { // CW records per memory round trip
             Rec chs[CW];
 #pragma unroll
@@ -229,7 +173,6 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
                     if (PQ) { bo0 = ch.o0; bo2 = ch.o2; }
                 }
             }
-        }
         }
         rc.scanned += nch;
         cur = cfc + b;

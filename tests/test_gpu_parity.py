@@ -645,31 +645,6 @@ def test_backprop_reductions_equal_load_add_store(engine, leaf):
         assert st[k] == st2[k], k
 
 
-@pytest.mark.parametrize("leaf", ["nn", "rollout"])
-def test_fast_select_equals_exact_select(engine, oracle, leaf):
-    """SYN_TPG_FAST_SELECT=1: select_best_child first scores the children with approximate reciprocals and error bounds
-    and only falls back to the reference's IEEE divisions when the bounds overlap.  The chosen child must be the same
-    every time: identical trees, rows and counters — and identical to the oracle where it can replay the games."""
-    engine.set_weights(s.Connect4Net.new(5).blob())
-    kind = L.LEAF_NN if leaf == "nn" else L.LEAF_ROLLOUT
-    for cfg, games in ((_config3(explores=300), 700), (s.study_connect4_rollout_cfg(num_explores=800, sample_actions_until=30), 300)):
-        run = lambda: engine.gather(cfg, kind, 0, games, 3, trace=True)
-        a, st, tr = run()
-        b, st2, tr2 = _with_env("SYN_TPG_FAST_SELECT", "1", run)
-        assert_rows_equal(a, b, "experience")
-        assert_rows_equal(tr, tr2, "trace")
-        for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels",
-                  "rollout_plies"):
-            assert st[k] == st2[k], k
-    if leaf == "rollout":
-        cfg = s.study_connect4_rollout_cfg(num_explores=200, sample_actions_until=20)
-        cfg.mcts_cfg.fpu = s.Fpu.ParentQ()
-        b, st2, tr2 = _with_env("SYN_TPG_FAST_SELECT", "1", lambda: engine.gather(cfg, kind, 0, 24, 1, trace=True))
-        ra, rst, rtr = oracle.gather(cfg.to_c(kind), 1, 0, 24, threads=8)
-        assert_rows_equal(tr2, rtr, "trace vs oracle")
-        assert_rows_equal(b, ra, "experience vs oracle")
-
-
 def test_backprop_with_subnormal_values_is_bit_exact(engine, oracle):
     """The L2's adder flushes subnormals, the CPU's does not.  A net whose value head yields a subnormal draw probability
     (zero weights, l_5.bias = [.., 0, -95, -60]) must still give the oracle's outcome sums bit for bit: the kernel notices
