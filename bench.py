@@ -51,7 +51,7 @@ def parse_args():
 def size_workload(args):
     """Games one GPU holds in flight and games per step; identical for both arms so their `config` matches."""
     if args.leaf == "nn" and args.group_lanes == 1:
-        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "4"))  # one CTA per SM, teams of 128 games
+        in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "5"))  # one CTA per SM, teams of 128 games
     elif args.leaf == "nn":
         in_flight = 148 * (512 // args.group_lanes)
     elif args.group_lanes == 1:

@@ -21,4 +21,4 @@ for m in modes:
         tot = max(1, d["t_total"])
         print("   phase share of warp time: advance %.1f%% teamwait %.1f%% mlp %.1f%% finish %.1f%% | rounds/warp %.0f leaves/round/warp %.1f | cycles/round %.0f"
               % (100 * d["t_advance"] / tot, 100 * d["t_teamwait"] / tot, 100 * d["t_mlp"] / tot, 100 * d["t_finish"] / tot,
-                 d["rounds"] / (148 * 4 * int(os.environ.get("SYN_TPG_TEAMS", "4"))), d["leaves"] / max(1, d["rounds"]), (d["t_advance"] + d["t_teamwait"] + d["t_mlp"] + d["t_finish"]) / max(1, d["rounds"])))
+                 d["rounds"] / (148 * 4 * int(os.environ.get("SYN_TPG_TEAMS", "5"))), d["leaves"] / max(1, d["rounds"]), (d["t_advance"] + d["t_teamwait"] + d["t_mlp"] + d["t_finish"]) / max(1, d["rounds"])))

@@ -69,7 +69,7 @@ struct syn_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
     int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
-    int tpg_teams = 4;     // teams of 128 threads per CTA in thread-per-game mode (512 threads, 128 registers each)
+    int tpg_teams = 5;     // teams of 128 threads per CTA in thread-per-game mode (640 threads, 96 registers each; SYN_TPG_TEAMS)
     int rollout_threads = 1024; // threads (= games) per CTA of the thread-per-game rollout kernel: 512, 640, 768, 896 or 1024
     int rollout_cw = 3;         // child records per memory round trip at 896 / 1024 threads (SYN_ROLLOUT_CW = 3 or 5)
     bool tpg_prof = false; // SYN_TPG_PROF=1: the instantiation with per-warp phase clocks

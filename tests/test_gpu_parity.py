@@ -245,6 +245,25 @@ def test_rollout_threads_per_cta_do_not_change_results(threads):
         assert a[1][k] == b[1][k], k
 
 
+@pytest.mark.parametrize("teams", [4, 6])
+def test_nn_teams_per_cta_do_not_change_results(teams):
+    """selfplay_nn_tpg2_kernel runs 5 teams of 128 games per CTA by default (96 registers, three children per trip, a
+    10-level path table); 4 teams (128 registers, five per trip, 12 levels) and 6 teams sharing 4 MLP slots must give
+    identical rows, traces and counters."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=150, sample_actions_until=12)
+    blob = s.Connect4Net.new(8).blob()
+    def run():
+        with s.Engine(0, 2048, 150) as e:
+            e.set_weights(blob)
+            return e.gather(cfg, L.LEAF_NN, 5, 900, 9, trace=True)
+    a = run()
+    b = _with_env("SYN_TPG_TEAMS", str(teams), run)
+    assert_rows_equal(a[0], b[0], "experience")
+    assert_rows_equal(a[2], b[2], "trace")
+    for k in ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels"):
+        assert a[1][k] == b[1][k], k
+
+
 def test_sharding_is_invisible(engine):
     """Games are seeded by their global index: two shards concatenated == one call."""
     cfg = s.study_connect4_rollout_cfg(num_explores=60)
