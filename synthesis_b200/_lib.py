@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsynthesis_b200.so")
+# SYN_B200_LIB: another build of the same library (A/B experiments: scripts/gpu_*.sh); never a different implementation
+LIB_PATH = os.environ.get("SYN_B200_LIB") or os.path.join(_HERE, "libsynthesis_b200.so")
 
 SYN_OK = 0
 SYN_ERR_INVALID_ARGUMENT = -1

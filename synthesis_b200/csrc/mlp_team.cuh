@@ -170,6 +170,26 @@ __device__ __forceinline__ void release_slot(Smem<TEAMS, SLOTS>& s, int team, in
     }
 }
 
+#ifndef SYN_TMEM_PAIR
+#define SYN_TMEM_PAIR 0
+#endif
+// Hidden-layer epilogue for 16 accumulator columns of this thread's row: bias (two lanes per FADD2), then ReLU + saturate to
+// the fp16 range + round + pack in ONE instruction, stored as the row's next-layer A operand (K chunks 2*c16, 2*c16+1).
+__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], const float* bias, uint8_t* a_tile, int r, int c16) {
+    uint32_t h[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 b4 = *reinterpret_cast<const float4*>(bias + c16 * 16 + 4 * j);
+        float x0, x1, x2, x3;
+        add2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), b4.x, b4.y, x0, x1);
+        add2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), b4.z, b4.w, x2, x3);
+        h[2 * j] = cvt_relu_sat_f16x2(x0, x1);
+        h[2 * j + 1] = cvt_relu_sat_f16x2(x2, x3);
+    }
+    *reinterpret_cast<uint4*>(a_tile + (2 * c16) * (M_TILE * 16) + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_tile + (2 * c16 + 1) * (M_TILE * 16) + r * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
 // Forward pass of the team's 128 rows.  Every thread of the team calls with its row's features
 // already in the slot's A tile (generic-proxy stores); `phase` is the running parity of the slot's
 // mbarrier (acquire_slot / release_slot carry it).  On return y[0..8] are the row's policy logits and
@@ -201,30 +221,42 @@ __device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t
         phase ^= 1u;
         tc_fence_after();
         const float* bias = reinterpret_cast<const float*>(img + BIAS_OFF) + b_off(l);
+#if SYN_TMEM_PAIR
+        // two 16-column reads in flight per wait: halves the tcgen05.wait::ld round trips of the epilogue (22 -> 12 per forward)
+#pragma unroll
+        for (int c32 = 0; c32 < N / 32; ++c32) {
+            uint32_t va[16], vb[16];
+            tmem_ld16(tlane + (uint32_t)(c32 * 32), va);
+            tmem_ld16(tlane + (uint32_t)(c32 * 32 + 16), vb);
+            tmem_ld_wait();
+            epilogue16(va, bias, a_tile, r, 2 * c32);
+            epilogue16(vb, bias, a_tile, r, 2 * c32 + 1);
+        }
+        if (N % 32) {
+            uint32_t v[16];
+            tmem_ld16(tlane + (uint32_t)((N / 32) * 32), v);
+            tmem_ld_wait();
+            if (l < NL - 1) {
+                epilogue16(v, bias, a_tile, r, 2 * (N / 32));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) y[j] = __uint_as_float(v[j]) + bias[j];
+            }
+        }
+#else
 #pragma unroll
         for (int c16 = 0; c16 < N / 16; ++c16) {
             uint32_t v[16];
             tmem_ld16(tlane + (uint32_t)(c16 * 16), v);
             tmem_ld_wait();
             if (l < NL - 1) {
-                uint32_t h[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float4 b4 = *reinterpret_cast<const float4*>(bias + c16 * 16 + 4 * j);
-                    // bias (two lanes per FADD2), then ReLU + saturate to the fp16 range + round + pack in ONE instruction
-                    float x0, x1, x2, x3;
-                    add2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), b4.x, b4.y, x0, x1);
-                    add2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), b4.z, b4.w, x2, x3);
-                    h[2 * j] = cvt_relu_sat_f16x2(x0, x1);
-                    h[2 * j + 1] = cvt_relu_sat_f16x2(x2, x3);
-                }
-                *reinterpret_cast<uint4*>(a_tile + (2 * c16) * (M_TILE * 16) + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(a_tile + (2 * c16 + 1) * (M_TILE * 16) + r * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+                epilogue16(v, bias, a_tile, r, c16);
             } else {
 #pragma unroll
                 for (int j = 0; j < 12; ++j) y[j] = __uint_as_float(v[j]) + bias[j];
             }
         }
+#endif
     }
     // the next forward()'s first team_sync orders these TMEM reads before the next MMA overwrites D
     tc_fence_before();

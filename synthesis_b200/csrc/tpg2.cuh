@@ -95,6 +95,13 @@ struct Pend { // what descend leaves for finish
 // Levels of the path table per thread: what fits beside the MLP state in 227 KB of shared memory.
 __host__ __device__ constexpr int path_cap(int teams) { return teams <= 4 ? 12 : teams == 5 ? 10 : teams == 6 ? 8 : 6; }
 
+// Per-warp statistics rows in shared memory (see the kernels) and the global counter each column belongs to.
+enum { WC_LEVELS = 0, WC_SCANNED, WC_EXPANSIONS, WC_CREATED, WC_BACKPROP, WC_LEAF_EVALS, WC_ROLLOUT_PLIES, WC_N };
+__device__ __forceinline__ int wc_counter(int i) {
+    return i == WC_LEVELS ? CNT_SELECT_LEVELS : i == WC_SCANNED ? CNT_CHILDREN_SCANNED : i == WC_EXPANSIONS ? CNT_EXPANSIONS
+           : i == WC_CREATED ? CNT_CHILDREN_CREATED : i == WC_BACKPROP ? CNT_BACKPROP_LEVELS : i == WC_LEAF_EVALS ? CNT_LEAF_EVALS : CNT_ROLLOUT_PLIES;
+}
+
 struct RoundCnt { uint32_t levels, scanned, expansions, created, bp_levels, leaf_evals, explores; };
 
 __device__ __forceinline__ uint64_t stream_seed(const KParams& p, uint32_t gi, unsigned k) {
@@ -512,10 +519,15 @@ template <int TEAMS, int SLOTS, bool PROF>
 __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ unsigned long long s_cnt[CNT_ALL];
+    // the six per-round statistics are kept per WARP (plain 64-bit adds by lane 0, nobody else touches the row): shared-memory
+    // 64-bit atomics on six CTA-wide counters were 3.8 % of the stall samples (profiles/r1s_*)
+    __shared__ unsigned long long s_wcnt[4 * TEAMS][tp2::WC_N];
     mlpteam::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS, SLOTS>*>(smem_raw);
     constexpr int NT = 128 * TEAMS, PATH_CAP = tp2::path_cap(TEAMS);
     uint32_t* const path = reinterpret_cast<uint32_t*>(smem_raw + sizeof(mlpteam::Smem<TEAMS, SLOTS>)) + threadIdx.x; // [PATH_CAP][NT] after the MLP state
     if (threadIdx.x < CNT_ALL) s_cnt[threadIdx.x] = 0ull;
+    for (int i = threadIdx.x; i < 4 * TEAMS * tp2::WC_N; i += 128 * TEAMS) (&s_wcnt[0][0])[i] = 0ull;
+    unsigned long long* const wc = s_wcnt[threadIdx.x >> 5];
     mlpteam::setup<TEAMS, SLOTS>(ms, p.weight_image);
     const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
     const size_t slot_id = (size_t)blockIdx.x * (128 * TEAMS) + threadIdx.x;
@@ -576,10 +588,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
         { // statistics of the descent (summed per warp here so that they are not live across the forward)
             uint32_t a0 = __reduce_add_sync(0xffffffffu, rc.levels), a1 = __reduce_add_sync(0xffffffffu, rc.scanned);
             uint32_t a2 = __reduce_add_sync(0xffffffffu, rc.expansions), a3 = __reduce_add_sync(0xffffffffu, rc.created);
-            if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&s_cnt[CNT_SELECT_LEVELS], (unsigned long long)a0); atomicAdd(&s_cnt[CNT_CHILDREN_SCANNED], (unsigned long long)a1);
-                atomicAdd(&s_cnt[CNT_EXPANSIONS], (unsigned long long)a2); atomicAdd(&s_cnt[CNT_CHILDREN_CREATED], (unsigned long long)a3);
-            }
+            if ((threadIdx.x & 31) == 0) { wc[tp2::WC_LEVELS] += a0; wc[tp2::WC_SCANNED] += a1; wc[tp2::WC_EXPANSIONS] += a2; wc[tp2::WC_CREATED] += a3; }
             rc.bp_levels = 0u; rc.leaf_evals = 0u;
         }
         long long t1 = PROF ? clock64() : 0;
@@ -621,9 +630,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
         __syncwarp();
         { // statistics of the finish: one shared-memory atomic per warp and counter
             uint32_t a4 = __reduce_add_sync(0xffffffffu, rc.bp_levels), a5 = __reduce_add_sync(0xffffffffu, rc.leaf_evals);
-            if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&s_cnt[CNT_BACKPROP_LEVELS], (unsigned long long)a4); atomicAdd(&s_cnt[CNT_LEAF_EVALS], (unsigned long long)a5);
-            }
+            if ((threadIdx.x & 31) == 0) { wc[tp2::WC_BACKPROP] += a4; wc[tp2::WC_LEAF_EVALS] += a5; }
         }
         if (PROF) {
             long long t4 = clock64();
@@ -639,9 +646,14 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
         atomicAdd(&s_cnt[DBG_LEAVES], (unsigned long long)leaves);
         atomicAdd(&s_cnt[DBG_T_TOTAL], (unsigned long long)(clock64() - t_start));
     }
-    mlpteam::teardown<TEAMS, SLOTS>(ms); // ends with a CTA barrier: every warp's counters are in s_cnt
+    mlpteam::teardown<TEAMS, SLOTS>(ms); // ends with a CTA barrier: every warp's counters are in s_cnt / s_wcnt
     __syncthreads();
     if (threadIdx.x < CNT_ALL && s_cnt[threadIdx.x]) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
+    if (threadIdx.x < tp2::WC_N) {
+        unsigned long long t = 0ull;
+        for (int w = 0; w < 4 * TEAMS; ++w) t += s_wcnt[w][threadIdx.x];
+        if (t) atomicAdd(p.counters + tp2::wc_counter(threadIdx.x), t);
+    }
 }
 
 } // namespace eng

@@ -125,10 +125,13 @@ template <int NT, int CW>
 __global__ void __launch_bounds__(NT, 1) selfplay_rollout_tpg2_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ unsigned long long s_cnt[CNT_N];
+    __shared__ unsigned long long s_wcnt[NT / 32][tp2::WC_N]; // per-warp statistics rows: plain adds by lane 0, no atomics
     constexpr int RING = tp2r::ring_words(NT), PATH_CAP = tp2r::path_cap(NT);
     uint32_t* const ring = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;      // [RING][NT]
     uint32_t* const path = reinterpret_cast<uint32_t*>(smem_raw) + RING * NT + threadIdx.x; // [PATH_CAP][NT]
     if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0ull;
+    for (int i = threadIdx.x; i < (NT / 32) * tp2::WC_N; i += NT) (&s_wcnt[0][0])[i] = 0ull;
+    unsigned long long* const wc = s_wcnt[threadIdx.x >> 5];
     __syncthreads();
     const size_t slot_id = (size_t)blockIdx.x * NT + threadIdx.x;
     uint32_t* const ss = p.slot_state + tp2::SS_WORDS * slot_id;
@@ -188,10 +191,7 @@ __global__ void __launch_bounds__(NT, 1) selfplay_rollout_tpg2_kernel(const __gr
         { // statistics of the descent
             uint32_t a0 = __reduce_add_sync(0xffffffffu, rc.levels), a1 = __reduce_add_sync(0xffffffffu, rc.scanned);
             uint32_t a2 = __reduce_add_sync(0xffffffffu, rc.expansions), a3 = __reduce_add_sync(0xffffffffu, rc.created);
-            if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&s_cnt[CNT_SELECT_LEVELS], (unsigned long long)a0); atomicAdd(&s_cnt[CNT_CHILDREN_SCANNED], (unsigned long long)a1);
-                atomicAdd(&s_cnt[CNT_EXPANSIONS], (unsigned long long)a2); atomicAdd(&s_cnt[CNT_CHILDREN_CREATED], (unsigned long long)a3);
-            }
+            if ((threadIdx.x & 31) == 0) { wc[tp2::WC_LEVELS] += a0; wc[tp2::WC_SCANNED] += a1; wc[tp2::WC_EXPANSIONS] += a2; wc[tp2::WC_CREATED] += a3; }
         }
         const bool need = (pd.kind & tp2::K_LEAF) != 0u;
         // ---- RolloutPolicy::eval: top up the stream at one place, then play the position out
@@ -229,14 +229,16 @@ __global__ void __launch_bounds__(NT, 1) selfplay_rollout_tpg2_kernel(const __gr
         { // statistics of the finish: one shared-memory atomic per warp and counter
             uint32_t a4 = __reduce_add_sync(0xffffffffu, bp_levels), a5 = __reduce_add_sync(0xffffffffu, need ? 1u : 0u);
             uint32_t a6 = __reduce_add_sync(0xffffffffu, plies);
-            if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&s_cnt[CNT_BACKPROP_LEVELS], (unsigned long long)a4); atomicAdd(&s_cnt[CNT_LEAF_EVALS], (unsigned long long)a5);
-                atomicAdd(&s_cnt[CNT_ROLLOUT_PLIES], (unsigned long long)a6);
-            }
+            if ((threadIdx.x & 31) == 0) { wc[tp2::WC_BACKPROP] += a4; wc[tp2::WC_LEAF_EVALS] += a5; wc[tp2::WC_ROLLOUT_PLIES] += a6; }
         }
     }
     __syncthreads();
     if (threadIdx.x < CNT_N && s_cnt[threadIdx.x]) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
+    if (threadIdx.x < tp2::WC_N) {
+        unsigned long long t = 0ull;
+        for (int w = 0; w < NT / 32; ++w) t += s_wcnt[w][threadIdx.x];
+        if (t) atomicAdd(p.counters + tp2::wc_counter(threadIdx.x), t);
+    }
 }
 
 } // namespace eng
