@@ -170,9 +170,6 @@ __device__ __forceinline__ void release_slot(Smem<TEAMS, SLOTS>& s, int team, in
     }
 }
 
-#ifndef SYN_TMEM_PAIR
-#define SYN_TMEM_PAIR 0
-#endif
 // Hidden-layer epilogue for 16 accumulator columns of this thread's row: bias (two lanes per FADD2), then ReLU + saturate to
 // the fp16 range + round + pack in ONE instruction, stored as the row's next-layer A operand (K chunks 2*c16, 2*c16+1).
 __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], const float* bias, uint8_t* a_tile, int r, int c16) {
@@ -221,29 +218,7 @@ __device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t
         phase ^= 1u;
         tc_fence_after();
         const float* bias = reinterpret_cast<const float*>(img + BIAS_OFF) + b_off(l);
-#if SYN_TMEM_PAIR
-        // two 16-column reads in flight per wait: halves the tcgen05.wait::ld round trips of the epilogue (22 -> 12 per forward)
-#pragma unroll
-        for (int c32 = 0; c32 < N / 32; ++c32) {
-            uint32_t va[16], vb[16];
-            tmem_ld16(tlane + (uint32_t)(c32 * 32), va);
-            tmem_ld16(tlane + (uint32_t)(c32 * 32 + 16), vb);
-            tmem_ld_wait();
-            epilogue16(va, bias, a_tile, r, 2 * c32);
-            epilogue16(vb, bias, a_tile, r, 2 * c32 + 1);
-        }
-        if (N % 32) {
-            uint32_t v[16];
-            tmem_ld16(tlane + (uint32_t)((N / 32) * 32), v);
-            tmem_ld_wait();
-            if (l < NL - 1) {
-                epilogue16(v, bias, a_tile, r, 2 * (N / 32));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 12; ++j) y[j] = __uint_as_float(v[j]) + bias[j];
-            }
-        }
-#else
+        // (two 16-column reads in flight per wait were measured: -0.4 %, profiles/r1_tmem_pair_ab.txt)
 #pragma unroll
         for (int c16 = 0; c16 < N / 16; ++c16) {
             uint32_t v[16];
@@ -256,7 +231,6 @@ __device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t
                 for (int j = 0; j < 12; ++j) y[j] = __uint_as_float(v[j]) + bias[j];
             }
         }
-#endif
     }
     // the next forward()'s first team_sync orders these TMEM reads before the next MMA overwrites D
     tc_fence_before();
