@@ -155,14 +155,14 @@ __device__ __forceinline__ bool descend(const Ctx& c, Game& g, uint64_t& my, uin
         const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
         uint32_t b = 0u, bfc = 0u, bpk = 0u;
         float bval = 0.0f, bvis = 0.0f, bo0 = 0.0f, bo2 = 0.0f;
-        // three children per trip: their records are requested together, so a level costs
-        // ceil(nch / 3) memory round trips instead of nch
-        for (uint32_t k0 = 0; k0 < nch; k0 += 3u) {
-            Rec chs[3];
+        // five children per trip: their records are requested together, so a level costs
+        // ceil(nch / 5) memory round trips instead of nch (the match kernel runs at 128 registers per thread)
+        for (uint32_t k0 = 0; k0 < nch; k0 += 5u) {
+            Rec chs[5];
 #pragma unroll
-            for (uint32_t j = 0; j < 3u; ++j) chs[j] = load_rec(nodes, cfc + (k0 + j < nch ? k0 + j : nch - 1u));
+            for (uint32_t j = 0; j < 5u; ++j) chs[j] = load_rec(nodes, cfc + (k0 + j < nch ? k0 + j : nch - 1u));
 #pragma unroll
-            for (uint32_t j = 0; j < 3u; ++j) {
+            for (uint32_t j = 0; j < 5u; ++j) {
                 const uint32_t k = k0 + j;
                 if (k < nch) {
                     const Rec& ch = chs[j];
