@@ -239,6 +239,30 @@ def test_stream_seeds(oracle):
     assert len(seen) == 3 * 50 * 4
 
 
+def test_two_shift_won_equals_the_reference_form():
+    """csrc/c4.cuh won(): `t = bb & bb>>s; t & t>>2s & MASK` per direction is the reference's
+    `bb & bb>>s & bb>>2s & bb>>3s & MASK` (connect4.rs:77-83) for every 64-bit pattern — checked on random boards, on
+    boards built from played games, and on all single lines of four."""
+    import random
+    ROW0 = sum(1 << (7 * c) for c in range(9)); C05 = (1 << 42) - 1
+    masks = {1: ROW0 * 0x0F, 7: C05, 8: C05 & (ROW0 * 0x0F), 6: C05 & (ROW0 * 0x78)}
+    ref = lambda bb: any(bb & (bb >> s) & (bb >> 2 * s) & (bb >> 3 * s) & m for s, m in masks.items())
+
+    def two(bb):
+        out = 0
+        for s, m in masks.items():
+            t = bb & (bb >> s)
+            out |= t & (t >> 2 * s) & m
+        return out != 0
+    rnd = random.Random(5)
+    boards = [rnd.getrandbits(63) & rnd.getrandbits(63) for _ in range(20000)] + [rnd.getrandbits(63) for _ in range(5000)]
+    for s in masks:
+        for start in range(63):
+            boards.append(sum(1 << (start + k * s) for k in range(4) if start + k * s < 63))
+    assert all(ref(b) == two(b) for b in boards)
+    assert any(ref(b) for b in boards) and not all(ref(b) for b in boards)
+
+
 def test_winning_cells_algebra_equals_won_per_column():
     """csrc/c4.cuh winning_cells(): the mover's winning cells for all nine columns from one pass of masked
     neighbour shifts.  Mirrored here in Python integers and checked against Connect4::won (connect4.rs:77-83)
