@@ -361,7 +361,9 @@ static int launch_match(syn_engine* e, KParams& kp, mtc::MParams& mp) {
         return SYN_OK;
     }
     mp.active_per_block = active;
-    size_t smem = sizeof(mlpteam::Smem<MATCH_TEAMS, MATCH_TEAMS>);
+    // no Connect4Net player: the kernel never touches the MLP state, and the shared memory it would take comes out of the L1
+    const bool any_nn = mp.players[0].leaf_eval_kind == SYN_LEAF_NN || mp.players[1].leaf_eval_kind == SYN_LEAF_NN;
+    size_t smem = any_nn ? sizeof(mlpteam::Smem<MATCH_TEAMS, MATCH_TEAMS>) : 0;
     CUDA_TRY(cudaFuncSetAttribute(match_tpg_kernel<MATCH_TEAMS, MATCH_TEAMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     match_tpg_kernel<MATCH_TEAMS, MATCH_TEAMS, false><<<blocks, per_cta, smem, e->stream>>>(kp, mp);
     CUDA_TRY(cudaGetLastError());

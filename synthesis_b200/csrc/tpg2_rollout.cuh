@@ -112,7 +112,10 @@ __device__ __forceinline__ void write_children_uniform(uint4* nodes, const tp2::
     }
 }
 
-__host__ __device__ constexpr int ring_words(int nt) { return nt <= 768 ? 64 : 32; } // what fits in 227 KB beside the path table
+// 32 words (two blocks) per game at every thread count: a 64-word ring tops up less often, but the shared memory it takes
+// comes out of the L1 (the SM's carve-out goes up in steps), where this kernel keeps its spills and hottest nodes
+// (profiles/r1_rollout_keys_smem_ab.txt, r1_rollout_variants.txt).
+__host__ __device__ constexpr int ring_words(int nt) { return 32; }
 __host__ __device__ constexpr int path_cap(int nt) { return nt <= 512 ? 12 : 8; }
 __host__ __device__ constexpr size_t smem_bytes(int nt) { return (size_t)nt * (size_t)(ring_words(nt) + path_cap(nt)) * sizeof(uint32_t); }
 
