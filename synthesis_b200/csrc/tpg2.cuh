@@ -146,6 +146,8 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
         // the children are read CW at a time; DRAM hands out whole 128-byte lines, so asking for the last child's line now
         // makes the second batch an L2 hit instead of a second trip to HBM
         if (nch > (uint32_t)CW) prefetch_l2(nodes, cfc + nch - 1u);
+        // three batches (CW = 3, seven or more children): nine records span three or four lines, so the middle one is asked for too
+        if (CW < 5 && nch > 2u * (uint32_t)CW) prefetch_l2(nodes, cfc + (uint32_t)CW + 1u);
         // ---- select_best_child (mcts.rs:327-372): first strict maximum in child order
         const float pterm = puct ? __fsqrt_rn(cvis) : __fsqrt_rn(__fmul_rn(cfg.c, syn_logf(cvis)));
         const float fpu_q = PQ ? __fdiv_rn(__fsub_rn(cop2, cop0), cvis) : cfg.fpu_a; // Fpu::ParentQ = parent.q() (mcts.rs:353), once per level
