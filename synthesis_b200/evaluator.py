@@ -6,7 +6,7 @@ The reference plays these games one at a time on one thread; here a whole sweep 
 
     eval_against_rollout_mcts  evaluator.rs:163-198   NN `MCTS::exploit` vs rollout `FrozenMCTS::exploit`
     mcts_vs_mcts               evaluator.rs:200-228   rollout `FrozenMCTS` vs rollout `FrozenMCTS`
-    eval_against_old           evaluator.rs:129-160   NN `MCTS` vs NN `MCTS` (one network per engine call)
+    eval_against_old           evaluator.rs:131-161   NN `MCTS` vs NN `MCTS`, two networks resident (called at :87-94)
     add_pgn_result             utils.rs:32-53         results.pgn in the exact text bayeselo reads
 
 Names, argument meaning and return values follow the reference: every function returns

@@ -239,6 +239,22 @@ def test_stream_seeds(oracle):
     assert len(seen) == 3 * 50 * 4
 
 
+def test_add_pgn_result_text_is_the_reference_s():
+    """utils.rs:32-53: three tag lines and the result line per game, '1-0' / '0-1' / '1/2-1/2' by white's reward; any other
+    reward trips the reference's assert_eq!."""
+    import io
+    import synthesis_b200.evaluator as ev
+    out = io.StringIO()
+    ev.add_pgn_result(out, "model_3.ot", "VanillaMCTS800", 1.0)
+    ev.add_pgn_result(out, "VanillaMCTS800", "model_3.ot", -1.0)
+    ev.add_pgn_result(out, "model_3.ot", "model_2.ot", 0.0)
+    assert out.getvalue() == ('[White "model_3.ot"]\n[Black "VanillaMCTS800"]\n[Result "1-0"]\n1-0\n'
+                              '[White "VanillaMCTS800"]\n[Black "model_3.ot"]\n[Result "0-1"]\n0-1\n'
+                              '[White "model_3.ot"]\n[Black "model_2.ot"]\n[Result "1/2-1/2"]\n1/2-1/2\n')
+    with pytest.raises(AssertionError):
+        ev.add_pgn_result(io.StringIO(), "a", "b", 0.5)
+
+
 def test_two_shift_won_equals_the_reference_form():
     """csrc/c4.cuh won(): `t = bb & bb>>s; t & t>>2s & MASK` per direction is the reference's
     `bb & bb>>s & bb>>2s & bb>>3s & MASK` (connect4.rs:77-83) for every 64-bit pattern — checked on random boards, on
