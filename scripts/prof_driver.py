@@ -7,15 +7,16 @@ games = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 explores = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 gl = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 modes = sys.argv[4].split(",") if len(sys.argv) > 4 else ["rollout", "nn"]
+in_flight = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # games in flight (default: as many as the GPU seats)
 cfg = s.study_connect4_rollout_cfg(num_explores=explores)
-eng = s.Engine(0, max(148 * 32, min(games, 148 * 1024)), explores)
+eng = s.Engine(0, in_flight or max(148 * 32, min(games, 148 * 1024)), explores)
 eng.set_group_lanes(gl)
 eng.set_weights(s.Connect4Net.new(0).blob())
 for m in modes:
     leaf = L.LEAF_ROLLOUT if m == "rollout" else L.LEAF_NN
     eng.gather_launch(cfg, leaf, 0, games, 0)
     st = eng.gather_wait(None)
-    print(m, st["explores"], st["device_ns"] / 1e6, "ms", st["explores"] / st["device_ns"] * 1e3, "M explores/s")
+    print(m, "in flight", in_flight or "max", st["explores"], st["device_ns"] / 1e6, "ms", st["explores"] / st["device_ns"] * 1e3, "M explores/s")
     if gl == 1 and m == "nn":
         d = eng.debug_counters()
         tot = max(1, d["t_total"])

@@ -7,6 +7,7 @@
 // to move is the parity of the stone count, so a position is 16 bytes in registers.
 #pragma once
 #include <stdint.h>
+#include "devport.cuh"
 
 namespace c4 {
 

@@ -20,6 +20,8 @@
 #include "match.cuh"
 #include "tpg2.cuh"
 #include "tpg2_rollout.cuh"
+#include "tpg4.cuh"
+#include "tpg4_rollout.cuh"
 #include "dedup.cuh"
 #include "train.cuh"
 #include "train_cluster.cuh"
@@ -67,7 +69,9 @@ struct syn_engine {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint32_t max_games = 0, max_explores = 0, arena_nodes = 0;
+    uint32_t max_games = 0, max_explores = 0, arena_nodes = 0; // max_games = arena slots allocated (>= req_games)
+    uint32_t req_games = 0; // max_games_in_flight as the caller asked for it
+    int tpg_ver = 2;        // thread-per-game tree layout: 2 = tpg2.cuh (32-byte records, the product path), 4 = tpg4.cuh (family blocks; SYN_TPG_VER=4)
     int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
     int tpg_teams = 5;     // teams of 128 threads per CTA in thread-per-game mode (640 threads, 96 registers each; SYN_TPG_TEAMS)
     int rollout_threads = 1024; // threads (= games) per CTA of the thread-per-game rollout kernel: 512, 640, 768, 896 or 1024
@@ -82,6 +86,7 @@ struct syn_engine {
     DevBuf<uint8_t> weight_image2;
     bool has_weights2 = false;
     bool has_weights = false;
+    float bias_host[mlptc::BIAS_FLOATS] = {}; // the weight image's biases, for KParams::mlp_bias
     bool use_tc = true;           // Connect4Net on tcgen05 tensor cores (false: fp32 CUDA-core kernel)
     DevBuf<unsigned int> next_game;
     DevBuf<unsigned long long> counters;
@@ -172,6 +177,59 @@ static int launch_rollout_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     return SYN_OK;
 }
 
+template <int TEAMS, int SLOTS, bool PROF, int FPU>
+static int launch_tpg4_k(syn_engine* e, KParams& kp, uint32_t blocks) {
+    size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>) + (size_t)tp2::path_cap(TEAMS) * 128 * TEAMS * sizeof(uint32_t);
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg4_kernel<TEAMS, SLOTS, PROF, FPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_nn_tpg4_kernel<TEAMS, SLOTS, PROF, FPU><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+    return SYN_OK;
+}
+template <int TEAMS, int SLOTS>
+static int launch_tpg4(syn_engine* e, KParams& kp, uint32_t blocks) {
+    const uint32_t fpu = kp.cfg.mcts.fpu_kind;
+    if (fpu == SYN_FPU_PARENT_Q) return launch_tpg4_k<TEAMS, SLOTS, false, SYN_FPU_PARENT_Q>(e, kp, blocks);
+    if (fpu == SYN_FPU_NORMAL) return launch_tpg4_k<TEAMS, SLOTS, false, SYN_FPU_NORMAL>(e, kp, blocks);
+    if (e->tpg_prof) return launch_tpg4_k<TEAMS, SLOTS, true, SYN_FPU_CONST>(e, kp, blocks); // per-warp phase clocks (syn_engine_debug_counters)
+    return launch_tpg4_k<TEAMS, SLOTS, false, SYN_FPU_CONST>(e, kp, blocks);
+}
+
+template <int NT, int FPU>
+static int launch_rollout_tpg4_k(syn_engine* e, KParams& kp, uint32_t blocks) {
+    const size_t smem = tp2r::smem_bytes(NT);
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_rollout_tpg4_kernel<NT, FPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_rollout_tpg4_kernel<NT, FPU><<<blocks, NT, smem, e->stream>>>(kp);
+    return SYN_OK;
+}
+template <int NT>
+static int launch_rollout_tpg4(syn_engine* e, KParams& kp, uint32_t blocks) {
+    const uint32_t fpu = kp.cfg.mcts.fpu_kind;
+    if (fpu == SYN_FPU_PARENT_Q) return launch_rollout_tpg4_k<NT, SYN_FPU_PARENT_Q>(e, kp, blocks);
+    if (fpu == SYN_FPU_NORMAL) return launch_rollout_tpg4_k<NT, SYN_FPU_NORMAL>(e, kp, blocks);
+    return launch_rollout_tpg4_k<NT, SYN_FPU_CONST>(e, kp, blocks);
+}
+
+// Seating of a thread-per-game launch (tp2::seat_of): `want` games in flight spread over all SMs, at most team_size * teams seats per
+// CTA.  Returns the grid size.
+static uint32_t seat_games(const syn_engine* e, KParams& kp, uint32_t team_size, uint32_t teams) {
+    uint32_t want = kp.num_games < e->req_games ? kp.num_games : e->req_games;
+    if (want == 0) want = 1;
+    uint32_t blocks = want < (uint32_t)e->sm_count ? want : (uint32_t)e->sm_count;
+    const uint32_t cta_cap = team_size * teams;
+    if ((uint64_t)blocks * cta_cap < want) want = blocks * cta_cap;
+    kp.seats_q = want / blocks;
+    kp.seats_rem = want % blocks;
+    const uint32_t per_cta = kp.seats_q + (kp.seats_rem ? 1u : 0u);
+    kp.teams_used = (per_cta + team_size - 1) / team_size;
+    kp.per_team = (per_cta + kp.teams_used - 1) / kp.teams_used;
+    // the arena slots of a CTA are teams_used * per_team apart: never more than the engine allocated
+    while ((uint64_t)blocks * kp.teams_used * kp.per_team > e->max_games && kp.per_team > 1) {
+        kp.per_team -= 1;
+        const uint32_t cap = kp.teams_used * kp.per_team;
+        if (kp.seats_q >= cap) { kp.seats_q = cap; kp.seats_rem = 0; }
+    }
+    return blocks;
+}
+
 static size_t nn_tc_smem_bytes(int gpb) { return sizeof(mlptc::Smem) + (size_t)gpb * 64 * sizeof(uint32_t); }
 static size_t nn_smem_bytes(int gpb) { return (size_t)(mlp::WEIGHT_FLOATS + 2 * gpb * mlp::XS + gpb * 64) * sizeof(float); }
 
@@ -181,15 +239,31 @@ constexpr int NN_THREADS = 512;
 // Launches the self-play kernel for `n` games/positions.  Rows/search buffers must be set in kp.
 static int launch_selfplay(syn_engine* e, KParams& kp) {
     const bool nn = kp.cfg.leaf_eval_kind == SYN_LEAF_NN;
-    if (nn && e->group_lanes == 1 && e->use_tc) { // thread per game: one persistent CTA per SM
-        const uint32_t gpb = 128u * (uint32_t)e->tpg_teams;
-        uint32_t max_blocks = e->max_games / gpb;
-        if (max_blocks == 0) return fail(SYN_ERR_CAPACITY, "max_games_in_flight %u is smaller than one CTA's %u games", e->max_games, gpb);
-        // spread the games over the SMs first (whole teams), then fill the CTAs
-        uint32_t want_teams = (kp.num_games + 127u) / 128u;
-        uint32_t blocks = want_teams < (uint32_t)e->sm_count ? want_teams : (uint32_t)e->sm_count;
-        if (blocks > max_blocks) blocks = max_blocks;
-        if (blocks == 0) blocks = 1;
+    const bool tpg4_teams = e->tpg_teams == 4 || e->tpg_teams == 5 || e->tpg_teams == 6;
+    const bool tpg4_nt = e->rollout_threads == 512 || e->rollout_threads == 768 || e->rollout_threads == 1024;
+    const bool tpg4_ok = e->tpg_ver == 4 && e->max_explores <= tp4::MAX_EXPLORES && (e->arena_nodes >> 2) <= tp4::MAX_LINES;
+    if (nn && e->group_lanes == 1 && e->use_tc && tpg4_ok && tpg4_teams) { // thread per game on family blocks (tpg4.cuh), SYN_TPG_VER=4
+        const uint32_t blocks = seat_games(e, kp, 128u, (uint32_t)e->tpg_teams);
+        CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
+        int rc = e->tpg_teams == 6 ? launch_tpg4<6, 4>(e, kp, blocks)
+                 : e->tpg_teams == 5 ? launch_tpg4<5, 4>(e, kp, blocks) : launch_tpg4<4, 4>(e, kp, blocks);
+        if (rc) return rc;
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        return SYN_OK;
+    }
+    if (!nn && e->group_lanes == 1 && tpg4_ok && tpg4_nt) { // rollout leaves on family blocks (tpg4_rollout.cuh), SYN_TPG_VER=4
+        const uint32_t blocks = seat_games(e, kp, (uint32_t)e->rollout_threads, 1u);
+        CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
+        int rc = e->rollout_threads == 1024 ? launch_rollout_tpg4<1024>(e, kp, blocks)
+                 : e->rollout_threads == 768 ? launch_rollout_tpg4<768>(e, kp, blocks) : launch_rollout_tpg4<512>(e, kp, blocks);
+        if (rc) return rc;
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        return SYN_OK;
+    }
+    if (nn && e->group_lanes == 1 && e->use_tc) { // thread per game (tpg2.cuh): one persistent CTA per SM, games seated over all SMs
+        const uint32_t blocks = seat_games(e, kp, 128u, (uint32_t)e->tpg_teams);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         int rc = e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
                  : e->tpg_teams == 6 ? launch_tpg<6, 4>(e, kp, blocks)
@@ -202,14 +276,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         return SYN_OK;
     }
     if (!nn && e->group_lanes == 1) { // rollout leaves, thread per game (tpg2_rollout.cuh): one persistent CTA per SM
-        const uint32_t gpb = (uint32_t)e->rollout_threads;
-        uint32_t max_blocks = e->max_games / gpb;
-        if (max_blocks == 0) return fail(SYN_ERR_CAPACITY, "max_games_in_flight %u is smaller than one CTA's %u games", e->max_games, gpb);
-        // spread the games over the SMs first (whole warps), then fill the CTAs
-        uint32_t want_warps = (kp.num_games + 31u) / 32u;
-        uint32_t blocks = want_warps < (uint32_t)e->sm_count ? want_warps : (uint32_t)e->sm_count;
-        if (blocks > max_blocks) blocks = max_blocks;
-        if (blocks == 0) blocks = 1;
+        const uint32_t blocks = seat_games(e, kp, (uint32_t)e->rollout_threads, 1u);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         const bool cw5 = e->rollout_cw == 5;
         int rc = e->rollout_threads == 1024 ? (cw5 ? launch_rollout_tpg<1024, 5>(e, kp, blocks) : launch_rollout_tpg<1024, 3>(e, kp, blocks))
@@ -272,6 +339,7 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.error = e->error.p;
     kp.weights = e->weights.p;
     kp.weight_image = e->weight_image.p;
+    std::memcpy(kp.mlp_bias, e->bias_host, sizeof(kp.mlp_bias));
     const char* nored = std::getenv("SYN_TPG_NO_RED"); // read per launch so that one test process can run both forms
     kp.no_reductions = (nored && std::atoi(nored) == 1) ? 1u : 0u;
 }
@@ -410,16 +478,23 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     const char* penv = std::getenv("SYN_TPG_PROF");
     e->tpg_prof = penv && std::atoi(penv) == 1;
     if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 5 || std::atoi(tenv) == 6 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
+    const char* venv = std::getenv("SYN_TPG_VER");
+    if (venv && std::atoi(venv) == 4) e->tpg_ver = 4;
     const char* renv = std::getenv("SYN_ROLLOUT_THREADS");
     if (renv && (std::atoi(renv) == 512 || std::atoi(renv) == 640 || std::atoi(renv) == 768 || std::atoi(renv) == 896 || std::atoi(renv) == 1024)) e->rollout_threads = std::atoi(renv);
     const char* cwenv = std::getenv("SYN_ROLLOUT_CW");
     if (cwenv && std::atoi(cwenv) == 5) e->rollout_cw = 5;
-    // round the in-flight game count up to whole CTAs of every kernel
+    // round the in-flight game count up to whole CTAs of every kernel, plus the slack of the even seating (tp2::seat_of)
+    // (teams_used * per_team slots per CTA: at most 8 more than the CTA's share of the games)
     uint32_t unit = 1024;
-    e->max_games = ((max_games_in_flight + unit - 1) / unit) * unit;
+    e->req_games = max_games_in_flight;
+    e->max_games = (uint32_t)((((uint64_t)max_games_in_flight + 8ull * (uint64_t)prop.multiProcessorCount + unit - 1) / unit) * unit);
     e->max_explores = max_explores;
     // nodes.len() <= 1 + 9 * (explores + 1): every visit pushes at most 9 nodes (mcts.rs:384-397)
     e->arena_nodes = 1u + 9u * (max_explores + 1u) + 7u;
+    // tpg4 cuts the arena into 128-byte lines: an expansion takes three (two or more children) or one (an only child: every
+    // step of an auto-extended chain), so 768 bytes per explore leave room for a chain of three behind every expansion
+    if (e->tpg_ver == 4 && e->arena_nodes < 24u * (max_explores + 1u) + 256u) e->arena_nodes = 24u * (max_explores + 1u) + 256u;
     e->arena_nodes = (e->arena_nodes + 7u) & ~7u;
     cudaError_t ce;
     size_t total = (size_t)e->max_games * e->arena_nodes;
@@ -483,6 +558,7 @@ int syn_engine_set_weights(syn_engine* e, const float* blob, size_t n_floats) {
     CUDA_TRY(cudaMemcpyAsync(e->weights.p, blob, n_floats * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
     mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(e->bias_host, e->weight_image.p + mlptc::BIAS_OFF, sizeof(e->bias_host), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (!dev) e->h2d += n_floats * sizeof(float);
     e->has_weights = true;
@@ -1045,6 +1121,7 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
     CUDA_TRY(cudaGetLastError());
     mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p); // the search kernels see the new weights
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(e->bias_host, e->weight_image.p + mlptc::BIAS_OFF, sizeof(e->bias_host), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
     e->launches += 2;
     e->adam_t += n_batches;

@@ -187,13 +187,30 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], const float*
     *reinterpret_cast<uint4*>(a_tile + (2 * c16 + 1) * (M_TILE * 16) + r * 16) = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
+// epilogue16 with the biases in the kernel's parameter space (constant bank: an operand of the FADD, no load at all).
+// The shared-memory form waits for four LDS.128 per 16 columns on the short scoreboard — 24 % of all stall samples of
+// a kernel whose tree code waited less (profiles/r2_tpg3_t5_source_summary.txt).
+__device__ __forceinline__ void epilogue16_cb(const uint32_t (&v)[16], const float* __restrict__ bias, uint8_t* a_tile, int r, int c16) {
+    uint32_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float x0 = __fadd_rn(__uint_as_float(v[2 * j]), bias[c16 * 16 + 2 * j]);
+        const float x1 = __fadd_rn(__uint_as_float(v[2 * j + 1]), bias[c16 * 16 + 2 * j + 1]);
+        h[j] = cvt_relu_sat_f16x2(x0, x1);
+    }
+    *reinterpret_cast<uint4*>(a_tile + (2 * c16) * (M_TILE * 16) + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_tile + (2 * c16 + 1) * (M_TILE * 16) + r * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
 // Forward pass of the team's 128 rows.  Every thread of the team calls with its row's features
 // already in the slot's A tile (generic-proxy stores); `phase` is the running parity of the slot's
 // mbarrier (acquire_slot / release_slot carry it).  On return y[0..8] are the row's policy logits and
 // y[9..11] its value logits.
 // `img` = the resident weight image to use (s.img, or a second image of the same layout elsewhere in shared memory).
-template <int TEAMS, int SLOTS>
-__device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t* img, int team, int slot, int r, uint32_t& phase, float (&y)[12]) {
+// `cbias` = the image's 352 padded biases in the kernel's parameter space, or nullptr to read them from the image.
+template <int TEAMS, int SLOTS, bool CB = false>
+__device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t* img, int team, int slot, int r, uint32_t& phase, float (&y)[12],
+                                            const float* __restrict__ cbias = nullptr) {
     uint8_t* a_tile = s.a[slot];
     const uint32_t tmem = s.tmem_base + (uint32_t)(slot * 128);           // the slot's 128 accumulator columns
     const uint32_t tlane = tmem + ((uint32_t)((r >> 5) * 32) << 16);       // this warp's 32 TMEM lanes
@@ -217,7 +234,7 @@ __device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t
         mbar_wait(&s.bar_mma[slot], phase);
         phase ^= 1u;
         tc_fence_after();
-        const float* bias = reinterpret_cast<const float*>(img + BIAS_OFF) + b_off(l);
+        const float* bias = (CB ? cbias : reinterpret_cast<const float*>(img + BIAS_OFF)) + b_off(l);
         // (two 16-column reads in flight per wait were measured: -0.4 %, profiles/r1_tmem_pair_ab.txt)
 #pragma unroll
         for (int c16 = 0; c16 < N / 16; ++c16) {
@@ -225,7 +242,8 @@ __device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t
             tmem_ld16(tlane + (uint32_t)(c16 * 16), v);
             tmem_ld_wait();
             if (l < NL - 1) {
-                epilogue16(v, bias, a_tile, r, c16);
+                if (CB) epilogue16_cb(v, bias, a_tile, r, c16);
+                else epilogue16(v, bias, a_tile, r, c16);
             } else {
 #pragma unroll
                 for (int j = 0; j < 12; ++j) y[j] = __uint_as_float(v[j]) + bias[j];
@@ -239,6 +257,11 @@ __device__ __forceinline__ void forward_img(Smem<TEAMS, SLOTS>& s, const uint8_t
 template <int TEAMS, int SLOTS>
 __device__ __forceinline__ void forward(Smem<TEAMS, SLOTS>& s, int team, int slot, int r, uint32_t& phase, float (&y)[12]) {
     forward_img<TEAMS, SLOTS>(s, s.img, team, slot, r, phase, y);
+}
+// The same with the biases read from the kernel's parameter space (KParams::mlp_bias).
+template <int TEAMS, int SLOTS>
+__device__ __forceinline__ void forward_cb(Smem<TEAMS, SLOTS>& s, const float* __restrict__ cbias, int team, int slot, int r, uint32_t& phase, float (&y)[12]) {
+    forward_img<TEAMS, SLOTS, true>(s, s.img, team, slot, r, phase, y, cbias);
 }
 
 // A second resident image (evaluation matches between two different networks): bulk-copied behind the first on the

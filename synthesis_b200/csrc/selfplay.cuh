@@ -28,6 +28,9 @@ struct KParams {
     uint32_t num_games;
     uint32_t search_mode; // 1: one tree per given position, no game loop (syn_engine_search)
     uint32_t no_reductions; // tpg2.cuh: 1 = backprop by load / add / store only (SYN_TPG_NO_RED=1; the parity suite runs both)
+    // seating (tp2::seat_of): CTA b plays seats_q + (b < seats_rem) games, dealt round-robin to teams_used teams of at most
+    // per_team seats each (rollout kernel: one "team" = the CTA), so that few games still occupy every SM
+    uint32_t teams_used, per_team, seats_q, seats_rem;
     uint32_t arena_nodes;
     uint4* nodes; // tree arenas: arena_nodes 32-byte records per game slot (tree.cuh)
     unsigned int* next_game;
@@ -55,6 +58,7 @@ struct KParams {
     int* error;
     const float* weights; // device blob, NN mode
     const uint8_t* weight_image; // mlptc image (fp16 UMMA layout), NN mode on tensor cores
+    float mlp_bias[mlptc::BIAS_FLOATS]; // the image's padded fp32 biases again, in the parameter space: constant-bank operands (mlp_team.cuh forward_cb)
 };
 
 enum Phase { PH_NEED_GAME = 0, PH_NEW_TREE = 1, PH_EXPLORE = 2, PH_DONE = 3 };

@@ -27,6 +27,8 @@
 namespace tp2 {
 
 using namespace eng;
+using tpx::K_NONE; using tpx::K_LEAF; using tpx::K_TERMINAL; using tpx::K_INIT;
+using tpx::Pend; using tpx::RoundCnt; using tpx::RootOut;
 
 struct Rec {
     float vis, o0, o1, o2;
@@ -72,7 +74,6 @@ enum { MW_PRIOR = 0, MW_PARENT = 1, MW_FC = 2, MW_PK = 3 };
 // the current tree (read once per round next to the root record) and what only changes once per move.
 enum { SS_MY = 0, SS_OP = 2, SS_GI = 4, SS_PLY = 5, SS_APOS = 6, SS_FPU_POS = 7, SS_NOISE_POS = 8, SS_WORDS = 16 };
 
-enum { K_NONE = 0, K_LEAF = 1, K_TERMINAL = 2, K_INIT = 4 /* flag: the construction visit of MCTS::with_capacity */ };
 
 // Hot per-thread state is three registers: the arena pointer is recomputed from the slot index, and
 // the explore count of the current tree IS the root's visit count (every backprop ends at the root:
@@ -84,13 +85,6 @@ struct Game {
     bool slow;   // this tree has seen a value the L2's flushing adder would treat differently: no reductions (red_exact)
 };
 
-struct Pend { // what descend leaves for finish
-    uint32_t kind;  // K_*
-    uint32_t id;    // K_LEAF: the expanded node; K_TERMINAL: the proven node
-    uint32_t fc;    // K_LEAF: first child; K_TERMINAL: the node's packed solution
-    uint32_t lc;    // K_LEAF: legal mask | csol2 << 9 (2 bits per column: 0 none / 1 Lose(0) / 2 Draw(0))
-    uint32_t depth; // level of `id` (root = 0): path[0 .. depth-1] holds the ids of levels 1 .. depth
-};
 
 // Levels of the path table per thread: what fits beside the MLP state in 227 KB of shared memory.
 __host__ __device__ constexpr int path_cap(int teams) { return teams <= 4 ? 12 : teams == 5 ? 10 : teams == 6 ? 8 : 6; }
@@ -102,7 +96,6 @@ __device__ __forceinline__ int wc_counter(int i) {
            : i == WC_CREATED ? CNT_CHILDREN_CREATED : i == WC_BACKPROP ? CNT_BACKPROP_LEVELS : i == WC_LEAF_EVALS ? CNT_LEAF_EVALS : CNT_ROLLOUT_PLIES;
 }
 
-struct RoundCnt { uint32_t levels, scanned, expansions, created, bp_levels, leaf_evals, explores; };
 
 __device__ __forceinline__ uint64_t stream_seed(const KParams& p, uint32_t gi, unsigned k) {
     if (!p.search_mode) return syn_stream_seed(p.seed, p.first_game + gi, k);
@@ -119,6 +112,28 @@ __device__ __noinline__ float fpu_normal_draw(const KParams& p, uint32_t* ss) { 
     ss[SS_FPU_POS] = (uint32_t)st.pos;
     return v;
 }
+
+// Which arena slot a thread of a team-structured CTA plays in, and whether it plays at all: a launch that holds fewer
+// games than the GPU has thread slots spreads them over ALL SMs instead of filling the first CTAs (the reference plays
+// 1,000 games per iteration, study-connect4/src/main.rs:26: 6-7 per SM instead of 640 on two).  CTA b seats
+// seats_q + (b < seats_rem) games; seat order runs round-robin over the teams in use and, inside a team, over its
+// warps (seat li of a team = lane li / W of warp li % W), so that the warps of a CTA carry equal numbers of games.
+struct Seat { bool active; size_t slot; };
+__device__ __forceinline__ Seat seat_of(const KParams& p, int team, int r, int warps_per_team) {
+    const uint32_t li = (uint32_t)(r & 31) * (uint32_t)warps_per_team + (uint32_t)(r >> 5);
+    const uint32_t n_b = p.seats_q + (blockIdx.x < p.seats_rem ? 1u : 0u);
+    Seat s;
+    s.active = (uint32_t)team < p.teams_used && li < p.per_team && li * p.teams_used + (uint32_t)team < n_b;
+    s.slot = ((size_t)blockIdx.x * p.teams_used + (size_t)team) * p.per_team + li;
+    return s;
+}
+
+// mcts.rs:354 with the shipped closure, on the game's seeded FPU stream (a functor for tpg4_tree.cuh's descend)
+struct FpuDraw {
+    const KParams& p;
+    uint32_t* ss;
+    __device__ __forceinline__ float operator()() const { return fpu_normal_draw(p, ss); }
+};
 
 // One explore from the (already loaded) root up to the point where the policy is needed
 // (mcts.rs:310-325, 327-372, 374-406).  `my`/`op` enter as the root position and leave as the
@@ -352,13 +367,6 @@ __device__ __noinline__ void add_root_noise(const KParams& p, uint32_t* ss, uint
     }
 }
 
-struct RootOut {
-    float pi[9], visits[9];
-    uint32_t child_sol[9];
-    float q0, q1, q2;
-    uint32_t root_sol, legal;
-    int best_action;
-};
 
 // What the driver reads from a finished tree (mcts.rs:174-225, 273-306), by COLUMN.
 __device__ __noinline__ void read_root(const uint4* nodes, uint32_t action_selection, RootOut& r) {
@@ -408,7 +416,7 @@ __device__ __noinline__ void read_root(const uint4* nodes, uint32_t action_selec
 __device__ __forceinline__ uint64_t ss_load64(const uint32_t* ss, int w) { return *reinterpret_cast<const uint64_t*>(ss + w); }
 __device__ __forceinline__ void ss_store64(uint32_t* ss, int w, uint64_t v) { *reinterpret_cast<uint64_t*>(ss + w) = v; }
 
-struct ReadRoot2 { // the node layout of this file; tpg3.cuh passes its own reader
+struct ReadRoot2 { // the node layout of this file; tpg4.cuh passes its own reader
     __device__ __forceinline__ void operator()(const uint4* nodes, uint32_t cap, uint32_t action_selection, RootOut& r) const { read_root(nodes, action_selection, r); }
 };
 
@@ -532,14 +540,15 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
     unsigned long long* const wc = s_wcnt[threadIdx.x >> 5];
     mlpteam::setup<TEAMS, SLOTS>(ms, p.weight_image);
     const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
-    const size_t slot_id = (size_t)blockIdx.x * (128 * TEAMS) + threadIdx.x;
+    const tp2::Seat seat = tp2::seat_of(p, team, r, 4);
+    const size_t slot_id = seat.slot;
     uint32_t* const ss = p.slot_state + tp2::SS_WORDS * slot_id;
     const syn_mcts_cfg& cfg = p.cfg.mcts;
     const float stop_vis = (float)(p.cfg.num_explores + 1u); // explore_n is over when the root has 1 + num_explores visits
     constexpr int CW = TEAMS >= 5 ? 3 : 5;
     tp2::Game g;
     g.nodes = p.nodes + 2 * slot_id * p.arena_nodes;
-    g.nn = 1u; g.phase = PH_NEED_GAME; g.slow = p.no_reductions != 0u;
+    g.nn = 1u; g.phase = seat.active ? PH_NEED_GAME : PH_DONE; g.slow = p.no_reductions != 0u;
     // per-warp phase clocks (syn_engine_debug_counters): only in the PROF instantiation, they cost 14 registers
     long long t_adv = 0, t_wait = 0, t_mlp = 0, t_fin = 0, t_start = PROF ? clock64() : 0;
     uint32_t rounds = 0, leaves = 0;

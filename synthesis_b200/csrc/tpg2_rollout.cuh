@@ -136,13 +136,14 @@ __global__ void __launch_bounds__(NT, 1) selfplay_rollout_tpg2_kernel(const __gr
     for (int i = threadIdx.x; i < (NT / 32) * tp2::WC_N; i += NT) (&s_wcnt[0][0])[i] = 0ull;
     unsigned long long* const wc = s_wcnt[threadIdx.x >> 5];
     __syncthreads();
-    const size_t slot_id = (size_t)blockIdx.x * NT + threadIdx.x;
+    const tp2::Seat seat = tp2::seat_of(p, 0, (int)threadIdx.x, NT / 32); // few games: spread over all SMs and warps
+    const size_t slot_id = seat.slot;
     uint32_t* const ss = p.slot_state + tp2::SS_WORDS * slot_id;
     const syn_mcts_cfg& cfg = p.cfg.mcts;
     const float stop_vis = (float)(p.cfg.num_explores + 1u); // explore_n is over when the root has 1 + num_explores visits
     tp2::Game g;
     g.nodes = p.nodes + 2 * slot_id * p.arena_nodes;
-    g.nn = 1u; g.phase = PH_NEED_GAME; g.slow = p.no_reductions != 0u;
+    g.nn = 1u; g.phase = seat.active ? PH_NEED_GAME : PH_DONE; g.slow = p.no_reductions != 0u;
     tp2r::RStream rs = {0u, 0u};
     for (;;) {
         // ---- cold bookkeeping, then at most one descent (as selfplay_nn_tpg2_kernel)

@@ -26,6 +26,7 @@
 #include "../../include/syn_streams.h"
 #include "../../include/synthesis_b200.h"
 #include "c4.cuh"
+#include "treedefs.cuh"
 #include "rng.cuh"
 
 namespace eng {
@@ -37,7 +38,6 @@ enum Counter {
     DBG_T_ADVANCE = CNT_N, DBG_T_TEAMWAIT, DBG_T_MLP, DBG_T_FINISH, DBG_ROUNDS, DBG_LEAVES, DBG_T_TOTAL, CNT_ALL
 };
 
-enum DeviceError { DERR_NONE = 0, DERR_ARENA_OVERFLOW = 1, DERR_DEPTH_OVERFLOW = 2, DERR_BAD_WEIGHTS = 3, DERR_NO_BEST_ACTION = 4 };
 
 // ------------------------------------------------------------------ lane groups
 template <int GL>
@@ -65,24 +65,6 @@ struct Grp {
     __device__ __forceinline__ uint32_t rmax(uint32_t v) const { return __reduce_max_sync(mask, v); }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
-
-// ------------------------------------------------------------------ packed Option<Outcome> (game.rs:9-66)
-// 0 = None, else kind<<6 | turns, kind 1 = Lose, 2 = Draw, 3 = Win.
-__device__ __forceinline__ uint32_t sol_kind(uint32_t s) { return s >> 6; }
-__device__ __forceinline__ uint32_t sol_reversed(uint32_t s) { // game.rs:28-35; s != 0
-    return ((4u - (s >> 6)) << 6) | (((s & 63u) + 1u) & 63u);
-}
-// Monotone key of the Ord impl (game.rs:46-60) extended to Option (None lowest): Win prefers FEWER
-// turns, Draw and Lose prefer MORE.
-__device__ __forceinline__ uint32_t sol_key(uint32_t s) {
-    if (s == 0u) return 0u;
-    return (s >> 6) == SYN_KIND_WIN ? ((3u << 6) | (63u - (s & 63u))) : s;
-}
-__device__ __forceinline__ uint32_t sol_from_key(uint32_t k) {
-    if (k == 0u) return 0u;
-    return (k >> 6) == SYN_KIND_WIN ? ((3u << 6) | (63u - (k & 63u))) : k;
-}
-__device__ __forceinline__ int sol_index(uint32_t s) { return (int)(s >> 6) - 1; } // Lose 0, Draw 1, Win 2 (mcts.rs:10-18)
 
 __device__ __forceinline__ uint32_t float_sort_key(float f) { // monotone for non-NaN floats, -0 == +0
     uint32_t u = __float_as_uint(f);

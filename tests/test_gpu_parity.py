@@ -892,3 +892,63 @@ def test_alpha_zero_distributed_world_of_one_equals_local(engine):
     finally:
         dist.destroy_process_group()
     assert net.blob().tobytes() == local.blob().tobytes()
+
+
+# ---------------------------------------------------------------- tpg2 (32-byte records, the product kernels) vs tpg4 (family blocks), and seating
+_COUNTERS = ("explores", "leaf_evals", "rows", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels")
+
+
+@pytest.mark.parametrize("leaf", ["nn", "rollout"])
+@pytest.mark.parametrize("variant", ["default", "parent_q", "fpu_normal", "uct"])
+def test_node_layouts_do_not_change_results(leaf, variant):
+    """The product kernels (tpg2.cuh: 32-byte node records, three children per memory trip, q divided at selection time,
+    backprop by L2 reductions or, with SYN_TPG_NO_RED=1, by load/add/store) and the family-block layout (tpg4.cuh,
+    SYN_TPG_VER=4: select_best_child reads one 128-byte line per level, -child.q() memoised, u16 visit counts, children in
+    column slots, backprop that reads what it updates) are layouts of the same serial per-tree algorithm: identical rows,
+    per-move visit counts, tree sizes and counters."""
+    cfg = _config3(explores=300)
+    if variant == "parent_q":
+        cfg.mcts_cfg.fpu = s.Fpu.ParentQ()
+    elif variant == "fpu_normal":
+        cfg.mcts_cfg.fpu = s.Fpu.Normal(1.0, 0.1)
+    elif variant == "uct":
+        cfg.mcts_cfg.exploration = s.Exploration.Uct(2.0)
+        cfg.mcts_cfg.fpu = s.Fpu.Const(float("inf"))
+        cfg.mcts_cfg.auto_extend = False
+    kind = L.LEAF_NN if leaf == "nn" else L.LEAF_ROLLOUT
+    blob = s.Connect4Net.new(4).blob()
+
+    def run():
+        with s.Engine(0, 2048, 300) as e:
+            e.set_weights(blob)
+            return e.gather(cfg, kind, 3, 700, 2, trace=True)
+    a = run()
+    b = _with_env("SYN_TPG_NO_RED", "1", run)
+    c = _with_env("SYN_TPG_VER", "4", run)
+    for other, name in ((b, "tpg2 load/add/store"), (c, "tpg4")):
+        assert_rows_equal(a[0], other[0], f"experience vs {name}")
+        assert_rows_equal(a[2], other[2], f"trace vs {name}")
+        for k in _COUNTERS:
+            assert a[1][k] == other[1][k], (name, k)
+
+
+@pytest.mark.parametrize("leaf", ["nn", "rollout"])
+@pytest.mark.parametrize("in_flight", [1, 37, 1000, 4096])
+def test_games_in_flight_do_not_change_results(leaf, in_flight):
+    """A launch that holds fewer games than the GPU has thread slots seats them over ALL SMs (tp2::seat_of): 1000 games
+    (the reference's games_per_train, study-connect4/src/main.rs:26) run as 6-7 games on each of 148 SMs instead of 1000
+    on two.  Results do not depend on the seating: games are seeded by their global index."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=80, sample_actions_until=12)
+    kind = L.LEAF_NN if leaf == "nn" else L.LEAF_ROLLOUT
+    blob = s.Connect4Net.new(5).blob()
+
+    def run(n):
+        with s.Engine(0, n, 80) as e:
+            e.set_weights(blob)
+            return e.gather(cfg, kind, 11, 1200, 4, trace=True)
+    a = run(148 * 640)
+    b = run(in_flight)
+    assert_rows_equal(a[0], b[0], "experience")
+    assert_rows_equal(a[2], b[2], "trace")
+    for k in _COUNTERS:
+        assert a[1][k] == b[1][k], k
