@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — self-play MCTS explores/sec (Connect4 9x7, 800 explores/move), the metric of BASELINE.json.
+"""bench.py — self-play MCTS explores/sec (Connect4 9x7), the metric of BASELINE.json.
 
-A "step" is one gather_experience pass: `--games` whole self-play games per GPU, every move an MCTS of
-`--explores` explores whose leaves are evaluated by the reference's Connect4Net MLP (random-init
-weights, synthetic: no dataset or checkpoint exists offline).  Workload = BASELINE.json configs[1].
+A "step" is one pass of the hot path over one batch of synthetic input (random-init weights, seeded games: no
+dataset or checkpoint exists offline).  `--config` picks the workload, all of them BASELINE.json's own:
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA engine through the C ABI)
-  python bench.py --impl reference [...]                          the reference's CPU path (C++ oracle,
-                                                                  reference thread schedule, all host cores)
+  1 (default)  configs[1]: AlphaZero self-play, study-connect4 policy/value net, 800 explores/move — one
+               gather_experience pass of `--games` games per GPU (default 6 x the games a GPU holds in flight)
+  0            configs[0]: rollout-only MCTS with MCTS-Solver, 800 explores/move, 256 games — the reference's CPU-sized case
+  2            configs[2]: 4,096 concurrent games per GPU, 1,600 explores/move, Dirichlet root noise + sample_actions_until
+  4            configs[4]: the evaluator's sweep — NN MCTS::exploit (800 explores) against rollout FrozenMCTS::exploit at
+               explores in {100 .. 10,000}, seeds 0..4, both colours (80 matches, study-connect4/src/main.rs:68-82)
+  (--leaf rollout without --config: configs[0] scaled up to fill the GPU, as in round 1)
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C]      our arm (CUDA engine through the C ABI)
+  python bench.py --impl reference [...]                                 the reference's CPU path (C++ oracle,
+                                                                         reference thread schedule, all host cores)
 Under torchrun (N > 1) every rank drives one GPU; rank 0 prints ONE JSON line.
 
-Keys beyond the base contract: `roofline` (dominant kernel vs the measured HBM peak), `cpu_baseline`
-(the oracle on this box's host cores, bounded sample), `e2e` (the same metric through the public API
-with pinned host buffers, H2D of the weights and D2H of the experience inside the timed region),
-`clocks`, `gpu_launches`, `positions_per_s`, `leaf_evals_per_s`.
+Keys beyond the base contract: `roofline` (dominant kernel vs the measured HBM peak; `frac_tree_only` leaves out the
+64 B per leaf that never leave the SM), `cpu_baseline` (the oracle on this box's host cores, bounded sample), `e2e` (the
+same metric through the public API with pinned host buffers: weights H2D — at N > 1 ONE NCCL broadcast inside the
+library — and experience rows D2H — at N > 1 ONE gather of 72-byte rows to rank 0 inside the library — within the
+timed region), `clocks`, `gpu_launches`, `positions_per_s`, `leaf_evals_per_s`.
 """
 import argparse
 import json
@@ -26,8 +34,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "self-play MCTS explores/sec (Connect4 9x7, 800 explores/move)"
 UNIT = "explores/s"
+SWEEP = [100, 200, 400, 800, 1600, 3200, 6400, 10000]  # study-connect4/src/main.rs:72 capped at BASELINE.json's 10,000
 
 
 def parse_args():
@@ -36,20 +44,38 @@ def parse_args():
     p.add_argument("--steps", type=int, default=2)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--games", type=int, default=0, help="self-play games per GPU per step (default: --games-mult x games in flight)")
+    p.add_argument("--config", type=int, default=-1, choices=[-1, 0, 1, 2, 4], help="BASELINE.json configs[k]; default configs[1]")
+    p.add_argument("--games", type=int, default=0, help="self-play games per GPU per step (configs 1: default --games-mult x games in flight)")
     p.add_argument("--games-mult", type=int, default=6,
                    help="games per step as a multiple of the games one GPU holds in flight (amortises the end-of-step tail)")
-    p.add_argument("--explores", type=int, default=800)
-    p.add_argument("--leaf", default="nn", choices=["nn", "rollout"])
+    p.add_argument("--explores", type=int, default=0)
+    p.add_argument("--leaf", default="", choices=["", "nn", "rollout"])
     p.add_argument("--group-lanes", type=int, default=int(os.environ.get("SYN_GROUP_LANES", "1")),
                    help="lanes per game: 1 = thread per game (default), 16 / 32 = lane group per game")
-    p.add_argument("--cpu-games", type=int, default=0, help="games in the CPU sample (default 96 per host thread, ~10-20 s)")
+    p.add_argument("--cpu-games", type=int, default=0, help="games in the CPU sample (default sized for ~10-20 s)")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.config < 0:
+        a.config = 0 if a.leaf == "rollout" else 1
+        a.scaled_up = a.leaf == "rollout"
+    else:
+        a.scaled_up = False
+    a.leaf = "rollout" if a.config == 0 else "nn"
+    a.explores = a.explores or (1600 if a.config == 2 else 800)
+    return a
 
 
 def size_workload(args):
     """Games one GPU holds in flight and games per step; identical for both arms so their `config` matches."""
+    if args.config == 4:
+        args.in_flight, args.games = 80, 80
+        return args.in_flight, args.games
+    if args.config == 0 and not args.scaled_up:
+        args.in_flight, args.games = 256, args.games or 256
+        return args.in_flight, args.games
+    if args.config == 2:
+        args.in_flight, args.games = 4096, args.games or 4096
+        return args.in_flight, args.games
     if args.leaf == "nn" and args.group_lanes == 1:
         in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "5"))  # one CTA per SM, teams of 128 games
     elif args.leaf == "nn":
@@ -63,27 +89,60 @@ def size_workload(args):
     return in_flight, args.games
 
 
+def metric_name(args):
+    if args.config == 4:
+        return "evaluation MCTS explores/sec (Connect4 9x7, NN MCTS 800 explores vs rollout FrozenMCTS sweep 100..10000)"
+    return "self-play MCTS explores/sec (Connect4 9x7, %d explores/move)" % args.explores
+
+
 def workload_cfg(args):
     import synthesis_b200 as s
-    # study-connect4/src/main.rs:28-36 with the reproducible MCTS config of main.rs:58-66 and 800 explores
+    if args.config == 2:  # Dirichlet{alpha 1.0, weight 0.25}, sample_actions_until = 30
+        m = s.study_connect4_mcts_cfg()
+        m.root_policy_noise = s.PolicyNoise.Dirichlet(1.0, 0.25)
+        return s.study_connect4_rollout_cfg(num_explores=args.explores, mcts_cfg=m, sample_actions_until=30)
+    # study-connect4/src/main.rs:28-36 with the reproducible MCTS config of main.rs:58-66
     return s.study_connect4_rollout_cfg(num_explores=args.explores, sample_actions_until=30)
 
 
+def eval_cfg():
+    import synthesis_b200 as s
+    return s.EvaluationConfig(policy_num_explores=800, policy_action=s.ActionSelection.NumVisits, policy_mcts_cfg=s.study_connect4_mcts_cfg(),
+                              rollout_action=s.ActionSelection.Q, rollout_num_explores=SWEEP, rollout_mcts_cfg=s.study_connect4_rollout_mcts_cfg(),
+                              num_games_against_rollout=5)
+
+
 def config_dict(args, n_gpus):
-    return {
-        "workload": ("BASELINE.json configs[1]: Connect4 9x7 AlphaZero self-play, study-connect4 policy/value net "
-                     "(MLP 63-128-96-64-48-12, random-init weights), %d explores/move" % args.explores) if args.leaf == "nn" else
-                    ("BASELINE.json configs[0] scaled up: Connect4 9x7 rollout-only MCTS with MCTS-Solver, %d explores/move" % args.explores),
+    names = {
+        0: "BASELINE.json configs[0]%s: Connect4 9x7 rollout-only MCTS (no NN) with MCTS-Solver, %d explores/move, %d games" %
+           (" scaled up to fill the GPU" if args.scaled_up else "", args.explores, args.games),
+        1: "BASELINE.json configs[1]: Connect4 9x7 AlphaZero self-play, study-connect4 policy/value net (MLP 63-128-96-64-48-12, "
+           "random-init weights), %d explores/move" % args.explores,
+        2: "BASELINE.json configs[2]: Connect4 9x7 self-play, 4096 concurrent games per GPU, %d explores/move, Dirichlet(1.0, 0.25) root noise + "
+           "sample_actions_until=30, study-connect4 policy/value net" % args.explores,
+        4: "BASELINE.json configs[4]: evaluation sweep, NN MCTS::exploit (800 explores) vs rollout FrozenMCTS::exploit at explores "
+           "100..10000, seeds 0..4, both colours = 80 matches (study-connect4/src/main.rs:68-82, synthesis/src/evaluator.rs:65-82)",
+    }
+    d = {
+        "workload": names[args.config],
         "games_per_gpu_per_step": args.games,
-        "explores_per_move": args.explores,
+        "explores_per_move": args.explores if args.config != 4 else "800 vs " + "/".join(map(str, SWEEP)),
         "leaf_eval": "Connect4Net" if args.leaf == "nn" else "RolloutPolicy",
-        "mcts": "PUCT c=3, Fpu::Const(1.0), solve+correct_values+select_solved+auto_extend, no root noise (study-connect4/src/main.rs:58-66)",
+        "mcts": "PUCT c=3, Fpu::Const(1.0), solve+correct_values+select_solved+auto_extend%s (study-connect4/src/main.rs:58-66)"
+                % (", Dirichlet(1.0, 0.25) root noise" if args.config == 2 else ", no root noise"),
         "driver": "random_actions_until=1, sample_actions_until=30, ValueTarget::Q, ActionSelection::NumVisits (main.rs:31-35)",
-        "parallelism": "game-sharded x%d (no data-path collective)" % n_gpus,
+        "parallelism": "game-sharded x%d; no collective on the search path; e2e leg: one NCCL broadcast of the weights + one gather of 72-byte rows "
+                       "per step inside the library (syn_engine_broadcast_weights / syn_engine_gather_experience)" % n_gpus,
         "games_in_flight_per_gpu": getattr(args, "in_flight", None),
-        "l2": "inputs larger than L2: the tree arenas of the games in flight (%.2f MB/game at %d explores) total ~%.0f GB per GPU vs 126 MB L2; a new seed per step"
+        "host_rows": "72 B per row reach the host (game id, bitboards, pi, v); height / player / the 63 features are functions of the bitboards "
+                     "and are rebuilt where they are consumed (synthesis_b200.data.ReplayBuffer on the host, the learner kernel on the device)",
+        "l2": "inputs larger than L2: the tree arenas of the games in flight (%.2f MB/game at %d explores) total ~%.1f GB per GPU vs 126 MB L2; a new seed per step"
               % ((9 * (args.explores + 1) + 8) * 32 / 1e6, args.explores, (getattr(args, "in_flight", 0) or 0) * (9 * (args.explores + 1) + 8) * 32 / 1e9),
     }
+    if args.config == 4:
+        d["driver"] = "policy ActionSelection::NumVisits, rollout ActionSelection::Q, UCT c=2 / FPU inf / no auto-extend on the rollout side (main.rs:74-82)"
+        d["l2"] = "a tree per move per match, up to 90,000 nodes (2.9 MB) at 10,000 explores; the match kernel is bound by the rounds of its longest match"
+    return d
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -144,14 +203,21 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def ncu_traffic(args):
+def ncu_traffic(args, kernel, launch_ms):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for ONE launch of this configuration, from the
-    committed ncu capture (profiles/traffic.json, written by scripts/ncu_traffic.py); None if no capture matches."""
+    committed ncu capture (profiles/traffic.json, written by scripts/ncu_traffic.py).  None if no capture matches the
+    configuration AND the kernel, or if this run's launch time differs from the capture's by more than 3 % (a capture
+    of another build says nothing about this one)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             for rec in json.load(f):
-                if (rec["leaf"], rec["explores"], rec["games"], rec["group_lanes"]) == (args.leaf, args.explores, args.games, args.group_lanes):
-                    return rec["dram_bytes"]
+                if (rec["leaf"], rec["explores"], rec["games"], rec["group_lanes"]) != (args.leaf, args.explores, args.games, args.group_lanes):
+                    continue
+                if rec.get("config", 1 if rec["leaf"] == "nn" else 0) != args.config or kernel not in rec["kernel"]:
+                    continue
+                if abs(rec["gpu_time_ns"] * 1e-6 - launch_ms) > 0.03 * launch_ms:
+                    continue
+                return rec["dram_bytes"]
     except Exception:
         pass
     return None
@@ -159,32 +225,66 @@ def ncu_traffic(args):
 
 def algorithmic_bytes_per_explore(st):
     """B = d*(20 + 18*C) + x*C*47 + (d+1)*36 with d = select levels per explore, C = children
-    per selected parent, x = expansions per explore, all measured in this run."""
+    per selected parent, x = expansions per explore, all measured in this run; NN leaves add 64 B per leaf (16 B position in,
+    48 B logits + probabilities out) which in these kernels never leave the SM — reported separately."""
     e = max(1, st["explores"])
     d = st["select_levels"] / e
     c = st["children_scanned"] / max(1, st["select_levels"])
     x = st["expansions"] / e
     cpx = st["children_created"] / max(1, st["expansions"])
-    b = d * (20 + 18 * c) + x * cpx * 47 + (d + 1) * 36
-    if st.get("leaf_evals") and st.get("nn"):
-        b += (st["leaf_evals"] / e) * 64  # NN mode: 16 B position in + 48 B (logits, probs) out per leaf
-    return b, {"select_depth": round(d, 3), "children_per_parent": round(c, 3), "expansions_per_explore": round(x, 3)}
+    tree = d * (20 + 18 * c) + x * cpx * 47 + (d + 1) * 36
+    nn = (st["leaf_evals"] / e) * 64 if (st.get("leaf_evals") and st.get("nn")) else 0.0
+    return tree + nn, tree, {"select_depth": round(d, 3), "children_per_parent": round(c, 3), "expansions_per_explore": round(x, 3)}
 
 
 # ------------------------------------------------------------------------------- CPU baseline (oracle)
-def cpu_reference_run(args, games, seed):
-    """The reference's CPU path as the reference schedules it (alpha_zero.rs:120-209): num_workers+1 = all host
-    threads, one StdRng + one weight copy + one memo cache per worker.  C++ oracle (the Rust original cannot be
-    built in this image)."""
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import build as oracle_build
     oracle_build.build()
     import oracle_binding
+    return oracle_binding.Oracle()
+
+
+def default_cpu_games(args, cores):
+    if args.cpu_games:
+        return args.cpu_games
+    if args.config == 4:
+        return 2 * cores  # matches
+    if args.config == 0 and not args.scaled_up:
+        return 256        # the literal configuration is CPU-sized
+    per_core = 768 if args.leaf == "rollout" else (48 if args.explores > 800 else 96)  # rollout leaves are ~8x cheaper on the CPU
+    return per_core * cores
+
+
+def cpu_reference_run(args, games, seed):
+    """The reference's CPU path as the reference schedules it (alpha_zero.rs:120-209): num_workers+1 = all host
+    threads, one StdRng + one weight copy + one memo cache per worker.  C++ oracle (the Rust original cannot be
+    built in this image).  Returns (stats, seconds, cores)."""
+    import numpy as np
     import synthesis_b200 as s
     from synthesis_b200 import _lib as L
-    orc = oracle_binding.Oracle()
+    orc = _oracle()
     cores = os.cpu_count() or 1
+    if args.config == 4:
+        import synthesis_b200.evaluator as ev
+        from concurrent.futures import ThreadPoolExecutor
+        ecfg = eval_cfg()
+        net = s.Connect4Net.new(0)
+        ex = [e for e in SWEEP for _ in range(5)]
+        sd = [k for _ in SWEEP for k in range(5)]
+        pick = np.linspace(0, len(ex) - 1, games).astype(int)  # matches spread over the sweep, one per thread at a time
+        players = (ev._policy_player(ecfg), ev._rollout_player(ecfg, max(SWEEP)))
+
+        def one(i):
+            out, st = orc.match(players, sd[i] + seed, explores2=[800, ex[i]], weights=net.blob())
+            return st["explores"], int(out["n_moves"])
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as pool:
+            r = list(pool.map(one, pick))
+        dt = time.perf_counter() - t0
+        return {"explores": sum(a for a, _ in r), "rows": sum(b for _, b in r)}, dt, cores
     cfg = workload_cfg(args)
     if args.leaf == "nn":
         net = s.Connect4Net.new(0)
@@ -198,28 +298,34 @@ def cpu_reference_run(args, games, seed):
     return st, dt, cores
 
 
+def cpu_sample_text(args, games, steps, explores, cores):
+    unit = "matches" if args.config == 4 else "games"
+    return "%d %s/step x %d step(s) of this workload (%d explores), %d worker threads%s" % (
+        games, unit, steps, explores, cores, ", per-worker memo cache" if args.leaf == "nn" and args.config != 4 else "")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    cpu_games = args.cpu_games or (96 if args.leaf == "nn" else 768) * cores  # rollout leaves are ~8x cheaper on the CPU
     size_workload(args)  # the same `config` as our arm; every step times a bounded sample of that workload
-    games = cpu_games
+    games = default_cpu_games(args, cores)
     for w in range(args.warmup):
-        cpu_reference_run(args, max(cores, games // 8), 1000 + w)
+        cpu_reference_run(args, max(cores if args.config != 4 else 4, games // 8), 1000 + w)
     tot_e = tot_rows = 0
     tot_t = 0.0
     for k in range(args.steps):
         st, dt, cores = cpu_reference_run(args, games, k)
         tot_e += st["explores"]; tot_rows += st["rows"]; tot_t += dt
     value = tot_e / tot_t
-    sample = "%d games/step x %d steps (%d explores), %d worker threads, per-worker memo cache" % (games, args.steps, tot_e, cores)
+    cfgd = config_dict(args, args.gpus)
+    cfgd["cpu_sample_per_step"] = "%d %s (a bounded sample of games_per_gpu_per_step; the metric is a rate)" % (games, "matches" if args.config == 4 else "games")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic (random-init weights, seeded games)", "config": config_dict(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic (random-init weights, seeded games)", "config": cfgd,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_text(args, games, args.steps, tot_e, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "positions_per_s": tot_rows / tot_t, "gpu_launches": 0,
         "note": "restated reference CPU path (C++ oracle, g++ -O3 -march=native -ffp-contract=off); the Rust reference cannot be built here",
@@ -228,12 +334,14 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------- our arm
+COMPACT = (("game_ids", "int64", ()), ("my_bb", "int64", ()), ("op_bb", "int64", ()), ("pis", "float32", (9,)), ("vs", "float32", (3,)))
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import synthesis_b200 as s
     from synthesis_b200 import _lib as L
-    from synthesis_b200 import distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,9 +351,11 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    comm = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        comm = s.Comm.from_torch(local_rank)  # the library's own communicator: torch only carries the 128-byte id
 
     def barrier():
         if dist is not None:
@@ -253,28 +363,26 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     leaf = L.LEAF_NN if args.leaf == "nn" else L.LEAF_ROLLOUT
-    cfg = workload_cfg(args)
     in_flight, games = size_workload(args)
+    net = s.Connect4Net.new(0)
+    blob_pinned = torch.from_numpy(net.blob()).pin_memory()
+
+    if args.config == 4:
+        return run_ours_matches(args, s, L, np, torch, dist, comm, world, rank, local_rank, dev, barrier, net)
+
+    cfg = workload_cfg(args)
     eng = s.Engine(local_rank, in_flight, args.explores)
     eng.set_group_lanes(args.group_lanes)
     first = rank * games  # weak scaling: every rank plays `games` games of the global index space
 
-    # weights: rank 0 owns them (the trainer); ONE broadcast per iteration when N > 1
-    net = s.Connect4Net.new(0)
-    blob_pinned = torch.from_numpy(net.blob()).pin_memory()
-
     def load_weights():
+        """rank 0 owns the weights (the trainer); N > 1: ONE NCCL broadcast inside the library per iteration."""
         if args.leaf != "nn":
             return 0
-        if dist is None:
+        if comm is None:
             eng.set_weights(blob_pinned.numpy())  # H2D from pinned host memory
-            return blob_pinned.numel() * 4
-        w = torch.empty(L.N_WEIGHTS, dtype=torch.float32, device=dev)
-        if rank == 0:
-            w.copy_(blob_pinned, non_blocking=True)
-        dist.broadcast(w, src=0)
-        torch.cuda.synchronize()
-        eng.set_weights(int(w.data_ptr()))
+        else:
+            eng.broadcast_weights(comm, blob_pinned.numpy() if rank == 0 else None, root=0)
         return blob_pinned.numel() * 4 if rank == 0 else 0
 
     load_weights()
@@ -319,46 +427,27 @@ def run_ours(args):
     launches_all = reduce(launches, "SUM")
     value = explores / t_dev
 
-    # ---- end-to-end leg: public API, pinned host buffers, H2D weights + D2H experience every step.
-    # N = 1: weights pinned-host -> HBM, experience HBM -> pinned host.  N > 1 adds the two collectives the
-    # path has per iteration: ONE broadcast of the weights from rank 0 and ONE gather of the rows to rank 0
-    # (NCCL over NVLink), rank 0 then copies everything to its pinned host buffers.
-    # rows per game: 63 always suffices (synthesis_b200.h); this workload's games last ~28 plies, so 44 per game bounds
+    # ---- end-to-end leg: the public API with pinned host buffers.  Every step: the weights travel pinned host -> HBM
+    # (N > 1: rank 0's copy, then ONE broadcast), every rank plays its shard, and the experience rows land in rank 0's
+    # pinned host memory (N > 1: ONE gather of 72-byte rows over NVLink inside the library, then rank 0's D2H).
+    # rows per game: 63 always suffices (synthesis_b200.h); these workloads' games last ~28 plies, so 44 per game bounds
     # the pinned buffers (the engine reports SYN_ERR_CAPACITY instead of overrunning if that were ever too small)
-    cap = min(L.MAX_TURNS, 44) * games
-    host = {n: torch.zeros((cap * (world if rank == 0 else 1),) + sh, dtype=D._torch_dtype(torch, dt)).pin_memory() for n, dt, sh in D.FIELDS}
-    dev_out = None
-    if dist is not None:
-        dev_out = {n: torch.zeros((cap,) + sh, dtype=D._torch_dtype(torch, dt), device=dev) for n, dt, sh in D.FIELDS}
+    cap = min(L.MAX_TURNS, 44) * games * (world if rank == 0 else 0)
+    host = {n: torch.zeros((max(cap, 1),) + sh, dtype=getattr(torch, dt)).pin_memory() for n, dt, sh in COMPACT} if rank == 0 else None
 
     def e2e_step(seed):
         h2d = load_weights()
-        exp = L.SynExperience()
-        exp.capacity = cap
-        for n, _, _ in D.FIELDS:
-            setattr(exp, n, host[n].data_ptr() if dist is None else dev_out[n].data_ptr())
-        st = eng.gather_into(cfg, leaf, first, games, seed, exp)
-        d2h = st["d2h_bytes"]
-        if dist is not None:
-            counts = torch.zeros(world, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(counts, torch.tensor([int(exp.len)], dtype=torch.int64, device=dev))
-            counts_h = counts.cpu().tolist()
-            mx = max(counts_h)
-            for n, _, _ in D.FIELDS:
-                t = dev_out[n][:mx]
-                if rank == 0:
-                    recv = [torch.empty_like(t) for _ in range(world)]
-                    dist.gather(t, recv, dst=0)
-                    off = 0
-                    for r in range(world):
-                        c = counts_h[r]
-                        host[n][off:off + c].copy_(recv[r][:c], non_blocking=True)
-                        d2h += c * recv[r][0].numel() * recv[r].element_size() if c else 0
-                        off += c
-                else:
-                    dist.gather(t, None, dst=0)
-            torch.cuda.synchronize()
-        return st, h2d + st["h2d_bytes"], d2h, int(exp.len)
+        exp = None
+        if rank == 0:
+            exp = L.SynExperience()
+            exp.capacity = cap
+            for n, _, _ in COMPACT:
+                setattr(exp, n, host[n].data_ptr())
+        if comm is None:
+            st = eng.gather_into(cfg, leaf, first, games, seed, exp)
+        else:
+            _, st = eng.gather_experience(comm, cfg, leaf, first, games, seed, root=0, exp=exp)
+        return st, h2d + st["h2d_bytes"], st["d2h_bytes"], int(exp.len) if exp is not None else 0
 
     e2e_step(2000)
     barrier()
@@ -370,38 +459,138 @@ def run_ours(args):
     barrier()
     e_wall = reduce(time.perf_counter() - t0, "MAX")
     e_value = reduce(e_expl, "SUM") / e_wall
+    e_h2d, e_d2h = reduce(e_h2d, "SUM"), reduce(e_d2h, "SUM")
 
     if rank == 0:
         acc["nn"] = args.leaf == "nn"
-        bpe, shape = algorithmic_bytes_per_explore(acc)
+        bpe, bpe_tree, shape = algorithmic_bytes_per_explore(acc)
         peak, peak_src = measured_peak_hbm()
         kernel_s = dev_ns * 1e-9 / max(1, args.steps)  # rank 0's kernel, average launch duration
-        achieved = bpe * (acc["explores"] / max(1, args.steps)) / kernel_s / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args),
-                    "kernel": ("selfplay_nn_tpg2_kernel" if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn" else ("selfplay_rollout_tpg2_kernel" if args.group_lanes == 1 else "selfplay_rollout_kernel"),
-                    "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": acc["explores"] / max(1, args.steps),
+        per_launch = acc["explores"] / max(1, args.steps)
+        achieved = bpe * per_launch / kernel_s / 1e9
+        kernel = (("selfplay_nn_tpg2_kernel" if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn"
+                  else ("selfplay_rollout_tpg2_kernel" if args.group_lanes == 1 else "selfplay_rollout_kernel"))
+        if os.environ.get("SYN_TPG_VER") == "4" and args.group_lanes == 1:
+            kernel = kernel.replace("tpg2", "tpg4")
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(args, kernel, 1e3 * kernel_s), "kernel": kernel,
+                    "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": per_launch,
+                    "tree_bytes_per_explore": round(bpe_tree, 1), "frac_tree_only": bpe_tree * per_launch / kernel_s / 1e9 / peak,
                     "launch_ms": 1e3 * kernel_s, "peak_source": peak_src, **shape,
+                    "second_roofline": {"what": "L2-miss sector rate of the memory system (scripts/probe/family_read_probe.cu, profiles/r2_family_read_probe.txt)",
+                                        "peak_sectors_per_s": 36.5e9,
+                                        "note": "a family of nine 32-byte child records is nine sector misses; at ~22 misses per explore (ncu DRAM read bytes / 64) "
+                                                "the kernel runs at 85-90 % of this rate while DRAM bytes stay at 30-40 % of the copy peak"},
                     "note": "latency-bound pointer chasing over per-game trees; see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cgames = args.cpu_games or (96 if args.leaf == "nn" else 768) * cores
+            cgames = default_cpu_games(args, cores)
             cst, cdt, cores = cpu_reference_run(args, cgames, 0)
             cpu = {"value": cst["explores"] / cdt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d games (%d explores, %.1f s), reference schedule: %d worker threads, per-worker memo cache"
-                             % (cgames, cst["explores"], cdt, cores)}
+                   "sample": cpu_sample_text(args, cgames, 1, cst["explores"], cores) + " in %.1f s" % cdt}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic (random-init weights, seeded games)", "config": config_dict(args, world),
+            "dtype": "f32 tree arithmetic; Connect4Net forward: f16 operands, f32 accumulate (tcgen05)" if args.leaf == "nn" else "f32 tree arithmetic, u64 bitboards",
+            "data": "synthetic (random-init weights, seeded games)", "config": config_dict(args, world),
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": e_h2d // max(1, args.steps), "d2h_bytes_per_step": e_d2h // max(1, args.steps)},
+            "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": int(e_h2d) // max(1, args.steps), "d2h_bytes_per_step": int(e_d2h) // max(1, args.steps)},
             "clocks": clocks, "gpu_launches": int(launches_all),
             "positions_per_s": rows / t_dev, "leaf_evals_per_s": leafs / t_dev, "wall_ms_per_step": 1e3 * t_wall / max(1, args.steps),
+            "value_excludes": "the row compaction kernel (compact_kernel, ~0.1 % of a step): `value` times the search kernel with the rows left in HBM at rows[game*63+ply]",
             "group_lanes": args.group_lanes,
         }
         emit(line)
     eng.close()
+    if comm is not None:
+        comm.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_ours_matches(args, s, L, np, torch, dist, comm, world, rank, local_rank, dev, barrier, net):
+    """configs[4]: every rank plays the evaluator's sweep (80 matches) with its own seeds; a step = both colours."""
+    import synthesis_b200.evaluator as ev
+    ecfg = eval_cfg()
+    ex = [e for e in SWEEP for _ in range(5)]
+    eng = s.Engine(local_rank, 256, max(SWEEP))
+    if comm is None:
+        eng.set_weights(net.blob())
+    else:
+        eng.broadcast_weights(comm, net.blob() if rank == 0 else None, root=0)
+
+    def step(seed):
+        sd = [seed * 1000 + rank * 100 + k for _ in SWEEP for k in range(5)]
+        tot = {}
+        moves = 0
+        for colour in (ev.RED, ev.BLACK):
+            r, out, st = ev.eval_against_rollout_mcts(eng, ecfg, net, colour, ex, sd, trace=True)
+            for k, v in st.items():
+                tot[k] = tot.get(k, 0) + v
+            moves += int(out["n_moves"].sum())
+        tot["rows"] = moves
+        return tot
+
+    for w in range(args.warmup):
+        step(1000 + w)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    acc = {}
+    for k in range(args.steps):
+        for key, v in step(k).items():
+            acc[key] = acc.get(key, 0) + v
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    def reduce(x, op):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
+
+    t_dev = reduce(acc["device_ns"] * 1e-9, "MAX")
+    t_wall = reduce(wall, "MAX")
+    explores = reduce(acc["explores"], "SUM")
+    rows = reduce(acc["rows"], "SUM")
+    if rank == 0:
+        acc["nn"] = False  # the 64 B-per-leaf term is left out: most leaves of this workload are rollouts
+        bpe, bpe_tree, shape = algorithmic_bytes_per_explore(acc)
+        peak, peak_src = measured_peak_hbm()
+        kernel_s = acc["device_ns"] * 1e-9 / max(1, 2 * args.steps)  # two launches (colours) per step
+        per_launch = acc["explores"] / max(1, 2 * args.steps)
+        achieved = bpe * per_launch / kernel_s / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel": "match_tpg_kernel",
+                    "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": per_launch, "launch_ms": 1e3 * kernel_s, "peak_source": peak_src, **shape,
+                    "note": "80 matches occupy 80 threads of the GPU: the launch lasts as long as its longest match (~250 k sequential rounds at 10,000 explores); latency-bound by construction"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cgames = default_cpu_games(args, cores)
+            cst, cdt, cores = cpu_reference_run(args, cgames, 0)
+            cpu = {"value": cst["explores"] / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": cpu_sample_text(args, cgames, 1, cst["explores"], cores) + " in %.1f s" % cdt}
+        line = {
+            "metric": metric_name(args), "value": explores / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 tree arithmetic; Connect4Net forward: f16 operands, f32 accumulate (tcgen05)", "data": "synthetic (random-init weights, seeded matches)",
+            "config": config_dict(args, world), "roofline": roofline, "cpu_baseline": cpu,
+            # the public API call (evaluator.eval_against_rollout_mcts) IS host-to-host: weights and seeds go in from host memory, results and moves come back
+            "e2e": {"value": explores / t_wall, "unit": UNIT, "h2d_bytes_per_step": int(acc.get("h2d_bytes", 0)) // max(1, args.steps) + 2 * L.N_WEIGHTS * 4,
+                    "d2h_bytes_per_step": int(acc.get("d2h_bytes", 0)) // max(1, args.steps)},
+            "clocks": clocks, "gpu_launches": int(reduce(acc.get("kernel_launches", 0), "SUM")), "positions_per_s": rows / t_dev,
+            "wall_ms_per_step": 1e3 * t_wall / max(1, args.steps),
+        }
+        emit(line)
+    eng.close()
+    if comm is not None:
+        comm.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -47,7 +47,8 @@ typedef enum {
     SYN_ERR_UNSUPPORTED = -4,    /* e.g. Fpu::Func — host code cannot run on the device */
     SYN_ERR_CAPACITY = -5,       /* caller buffer or engine arena too small */
     SYN_ERR_NO_WEIGHTS = -6,     /* leaf_eval = NN but syn_engine_set_weights was never called */
-    SYN_ERR_DEVICE_FAULT = -7    /* the kernel reported an internal inconsistency */
+    SYN_ERR_DEVICE_FAULT = -7,   /* the kernel reported an internal inconsistency */
+    SYN_ERR_COMM = -8            /* NCCL could not be loaded or a collective failed; see syn_last_error() */
 } syn_status;
 
 /* synthesis/src/config.rs:10-14  enum Exploration { Uct{c}, PolynomialUct{c} } */
@@ -290,6 +291,35 @@ int syn_engine_reset_optimizer(syn_engine* e);
 /* Replaces `vs.save` (alpha_zero.rs:37, 102) as far as the engine is concerned: the current fp32 weights in the blob
  * layout of syn_engine_set_weights (host or device destination). */
 int syn_engine_get_weights(syn_engine* e, float* blob, size_t n_floats);
+
+/* ---- multi-GPU: one process (or thread) per GPU, games sharded by contiguous ranges of the global game index --------
+ * The reference fans games out over num_workers+1 OS threads, each loading models/<name>.ot, and joins their
+ * ReplayBuffers in worker order (alpha_zero.rs:132-168, 192-194; data.rs:160-170).  Here a rank is a worker: ONE broadcast
+ * of the weight blob and ONE gather of experience rows per iteration, NCCL over NVLink inside the library (bound at run
+ * time by soname, so a host that already carries NCCL — PyTorch — shares its copy).  The search itself needs no
+ * collective.  The host only moves the 128-byte communicator id from rank 0 to the other ranks (any transport). */
+typedef struct syn_comm syn_comm;
+#define SYN_COMM_ID_BYTES 128
+int syn_comm_unique_id(uint8_t id[SYN_COMM_ID_BYTES]);  /* ncclGetUniqueId: call on ONE rank, hand the bytes to all */
+int syn_comm_create(const uint8_t id[SYN_COMM_ID_BYTES], int n_ranks, int rank, int cuda_device, syn_comm** out); /* collective */
+void syn_comm_destroy(syn_comm* c);
+int syn_comm_rank(const syn_comm* c);
+int syn_comm_size(const syn_comm* c);
+
+/* Replaces every worker's `vs.load(models/<name>.ot)` (alpha_zero.rs:192-194) across GPUs: rank `root` contributes
+ * `blob` (host or device, layout of syn_engine_set_weights; NULL = the root engine's current weights, e.g. fresh from
+ * syn_engine_train), every rank's engine ends up with them as if by syn_engine_set_weights.  Collective; blob is ignored
+ * on the other ranks. */
+int syn_engine_broadcast_weights(syn_engine* e, syn_comm* c, const float* blob, size_t n_floats, int root);
+
+/* Replaces gather_experience's fan-out and join (alpha_zero.rs:132-168) across GPUs: every rank plays games
+ * [first_game_index, first_game_index + num_games) (its shard: ranks must hold ascending contiguous ranges in rank order
+ * for the root's rows to come out in game order, like `extend` in worker order; num_games may be 0), the rows travel to
+ * rank `root` as 72 bytes each (game id, bitboards, pi, v) and the root rebuilds height / player / features from the
+ * bitboards.  On the root `out` receives all ranks' rows in rank order (capacity must cover the sum; len is set; games is
+ * not); elsewhere `out` is ignored and may be NULL.  stats (optional) are this rank's.  Collective. */
+int syn_engine_gather_experience(syn_engine* e, syn_comm* c, int root, const syn_rollout_cfg* cfg, uint64_t first_game_index,
+                                 uint32_t num_games, uint64_t seed, syn_experience* out, syn_stats* stats);
 
 /* Optional per-row trace of the NEXT gather (arrays of `capacity` rows like syn_experience, host or
  * device; NULL to disable): the action played from the row's state, nodes.len() of that ply's

@@ -10,10 +10,10 @@ from .config import (ActionSelection, EvaluationConfig, Exploration, Fpu, Learni
                      study_connect4_rollout_mcts_cfg)
 from .connect4 import Connect4
 from .data import BatchRandSampler, FlatBatch, ReplayBuffer
-from .engine import Engine
+from .engine import Comm, Engine
 from .policies import Connect4Net, RolloutPolicy
 
 __all__ = ["MCTS", "alpha_zero", "gather_experience", "engine_for", "lr_for_iteration", "train_on", "BatchRandSampler", "ActionSelection", "EvaluationConfig", "Exploration", "Fpu",
            "LearningConfig", "MCTSConfig", "PolicyNoise", "RolloutConfig", "ValueTarget", "Connect4", "FlatBatch", "ReplayBuffer",
-           "Engine", "Connect4Net", "RolloutPolicy", "study_connect4_mcts_cfg", "study_connect4_rollout_cfg",
+           "Engine", "Comm", "Connect4Net", "RolloutPolicy", "study_connect4_mcts_cfg", "study_connect4_rollout_cfg",
            "study_connect4_rollout_mcts_cfg"]

@@ -18,6 +18,7 @@ SYN_ERR_UNSUPPORTED = -4
 SYN_ERR_CAPACITY = -5
 SYN_ERR_NO_WEIGHTS = -6
 SYN_ERR_DEVICE_FAULT = -7
+SYN_ERR_COMM = -8
 
 N_ACTIONS = 9
 MAX_TURNS = 63
@@ -96,7 +97,10 @@ EXPORTED_SYMBOLS = (
     "syn_engine_set_weights", "syn_engine_set_opponent_weights", "syn_engine_gather", "syn_engine_gather_launch", "syn_engine_gather_wait",
     "syn_engine_search", "syn_engine_match", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode", "syn_engine_debug_counters",
     "syn_engine_deduplicate", "syn_engine_train", "syn_engine_reset_optimizer", "syn_engine_get_weights",
+    "syn_comm_unique_id", "syn_comm_create", "syn_comm_destroy", "syn_comm_rank", "syn_comm_size",
+    "syn_engine_broadcast_weights", "syn_engine_gather_experience",
 )
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -141,6 +145,14 @@ def load():
     lib.syn_engine_reset_optimizer.argtypes = [vp]
     lib.syn_engine_get_weights.argtypes = [vp, vp, C.c_size_t]
     lib.syn_engine_deduplicate.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(SynFlatBatch), C.POINTER(SynStats)]
+    lib.syn_comm_unique_id.argtypes = [vp]
+    lib.syn_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+    lib.syn_comm_destroy.argtypes = [vp]
+    lib.syn_comm_destroy.restype = None
+    lib.syn_comm_rank.argtypes = [vp]
+    lib.syn_comm_size.argtypes = [vp]
+    lib.syn_engine_broadcast_weights.argtypes = [vp, vp, vp, C.c_size_t, i32]
+    lib.syn_engine_gather_experience.argtypes = [vp, vp, i32, C.POINTER(SynRolloutCfg), u64, u32, u64, C.POINTER(SynExperience), C.POINTER(SynStats)]
     _lib = lib
     return lib
 

@@ -6,6 +6,8 @@
 // There is no CPU implementation behind any entry point: without a compute-capability-10.x device
 // syn_engine_create fails with SYN_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h> // types and prototypes only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
 #include <cmath>
@@ -14,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "selfplay.cuh"
@@ -109,6 +112,9 @@ struct syn_engine {
     uint64_t adam_t = 0;
     // deduplicate workspace (dedup.cuh)
     DevBuf<uint8_t> dd_ws, dd_io;
+    // multi-GPU gather (syn_engine_gather_experience): this rank's rows in wire format, the root's landing zone, row counts
+    DevBuf<uint8_t> gx_local, gx_all;
+    DevBuf<unsigned long long> gx_counts;
     // pending gather
     bool pending = false;
     uint32_t pend_games = 0;
@@ -439,6 +445,68 @@ static int launch_match(syn_engine* e, KParams& kp, mtc::MParams& mp) {
     return SYN_OK;
 }
 
+// ------------------------------------------------------------------ multi-GPU: one process (or thread) per GPU
+// NCCL is bound at run time by its soname: inside a process that already carries an NCCL (PyTorch's bundled copy) the same
+// library instance is used — two copies of NCCL in one process do not share their bootstrap state — and a plain C / Rust
+// host gets the system's libnccl.so.2.  Nothing else in this library depends on NCCL being present.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    const char* names[] = {std::getenv("SYN_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) return nullptr;
+    bool ok = true;
+    auto bind = [&](auto& fn, const char* name) {
+        fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(api.handle, name));
+        ok = ok && fn != nullptr;
+    };
+    bind(api.GetUniqueId, "ncclGetUniqueId"); bind(api.CommInitRank, "ncclCommInitRank"); bind(api.CommDestroy, "ncclCommDestroy");
+    bind(api.Broadcast, "ncclBroadcast"); bind(api.AllGather, "ncclAllGather"); bind(api.Send, "ncclSend"); bind(api.Recv, "ncclRecv");
+    bind(api.GroupStart, "ncclGroupStart"); bind(api.GroupEnd, "ncclGroupEnd"); bind(api.GetErrorString, "ncclGetErrorString");
+    if (!ok) { dlclose(api.handle); api.handle = nullptr; return nullptr; }
+    return &api;
+}
+#define NCCL_TRY(api, expr)                                                                                                   \
+    do {                                                                                                                      \
+        ncclResult_t _r = (expr);                                                                                             \
+        if (_r != ncclSuccess) return fail(SYN_ERR_COMM, "%s failed: %s (%s:%d)", #expr, (api)->GetErrorString(_r), __FILE__, __LINE__); \
+    } while (0)
+
+struct syn_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, size = 1, device = 0;
+};
+
+static_assert(SYN_COMM_ID_BYTES == sizeof(ncclUniqueId), "syn_comm id is an ncclUniqueId");
+
+// Wire format of one experience row between GPUs: game id, the two bitboards, pi[9], v[3] = 72 bytes in five arrays;
+// height, player and the 63 features are functions of the bitboards and are rebuilt on the root (expand_rows_kernel).
+static const size_t GX_ELT[5] = {8, 8, 8, 36, 12};
+static size_t gx_field_off(int f, size_t rows) { // 256-byte aligned arrays of `rows` elements each
+    size_t off = 0;
+    for (int i = 0; i < f; ++i) off += (GX_ELT[i] * rows + 255) / 256 * 256;
+    return off;
+}
+
 extern "C" {
 
 int syn_abi_version(void) { return SYN_ABI_VERSION; }
@@ -521,6 +589,7 @@ void syn_engine_destroy(syn_engine* e) {
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();
     e->s_csol.release(); e->s_rsol.release(); e->s_best.release(); e->s_nodes.release();
+    e->gx_local.release(); e->gx_all.release(); e->gx_counts.release();
     e->dd_ws.release(); e->dd_io.release(); e->adam_m.release(); e->adam_v.release(); e->tr_io.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -698,6 +767,189 @@ int syn_engine_gather(syn_engine* e, const syn_rollout_cfg* cfg, uint64_t first_
     int rc = syn_engine_gather_launch(e, cfg, first_game_index, num_games, seed);
     if (rc) return rc;
     return syn_engine_gather_wait(e, out, stats);
+}
+
+
+int syn_comm_unique_id(uint8_t id[SYN_COMM_ID_BYTES]) {
+    if (!id) return fail(SYN_ERR_INVALID_ARGUMENT, "id is NULL");
+    NcclApi* api = nccl_api();
+    if (!api) return fail(SYN_ERR_COMM, "libnccl.so.2 could not be loaded: %s", dlerror());
+    ncclUniqueId u;
+    NCCL_TRY(api, api->GetUniqueId(&u));
+    std::memcpy(id, &u, sizeof(u));
+    return SYN_OK;
+}
+
+int syn_comm_create(const uint8_t id[SYN_COMM_ID_BYTES], int n_ranks, int rank, int cuda_device, syn_comm** out) {
+    if (!out) return fail(SYN_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SYN_ERR_INVALID_ARGUMENT, "bad communicator arguments (n_ranks %d, rank %d)", n_ranks, rank);
+    NcclApi* api = nccl_api();
+    if (!api) return fail(SYN_ERR_COMM, "libnccl.so.2 could not be loaded: %s", dlerror());
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SYN_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+    }
+    if (cuda_device < 0 || cuda_device >= ndev) return fail(SYN_ERR_INVALID_ARGUMENT, "cuda_device %d out of range (%d devices)", cuda_device, ndev);
+    CUDA_TRY(cudaSetDevice(cuda_device));
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof(u));
+    syn_comm* c = new syn_comm();
+    c->rank = rank; c->size = n_ranks; c->device = cuda_device;
+    ncclResult_t r = api->CommInitRank(&c->comm, n_ranks, u, rank);
+    if (r != ncclSuccess) {
+        int rc = fail(SYN_ERR_COMM, "ncclCommInitRank failed: %s", api->GetErrorString(r));
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return SYN_OK;
+}
+
+void syn_comm_destroy(syn_comm* c) {
+    if (!c) return;
+    NcclApi* api = nccl_api();
+    if (api && c->comm) { cudaSetDevice(c->device); api->CommDestroy(c->comm); }
+    delete c;
+}
+
+int syn_comm_rank(const syn_comm* c) { return c ? c->rank : -1; }
+int syn_comm_size(const syn_comm* c) { return c ? c->size : 0; }
+
+int syn_engine_broadcast_weights(syn_engine* e, syn_comm* c, const float* blob, size_t n_floats, int root) {
+    if (!e || !c) return fail(SYN_ERR_INVALID_ARGUMENT, "engine or communicator is NULL");
+    if (root < 0 || root >= c->size) return fail(SYN_ERR_INVALID_ARGUMENT, "root %d out of range (%d ranks)", root, c->size);
+    if (c->device != e->device) return fail(SYN_ERR_INVALID_ARGUMENT, "communicator is on device %d, engine on %d", c->device, e->device);
+    if (n_floats != SYN_N_WEIGHTS) return fail(SYN_ERR_INVALID_ARGUMENT, "expected %d floats (63-128-96-64-48-12 MLP), got %zu", SYN_N_WEIGHTS, n_floats);
+    NcclApi* api = nccl_api();
+    if (!api) return fail(SYN_ERR_COMM, "libnccl.so.2 could not be loaded");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (c->rank == root) {
+        if (blob) { // NULL on the root: broadcast the engine's current weights (e.g. just trained by syn_engine_train)
+            const bool dev = is_device_ptr(blob);
+            CUDA_TRY(cudaMemcpyAsync(e->weights.p, blob, n_floats * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+            if (!dev) e->h2d += n_floats * sizeof(float);
+        } else if (!e->has_weights) {
+            return fail(SYN_ERR_NO_WEIGHTS, "the root has neither a blob nor weights of its own to broadcast");
+        }
+    }
+    NCCL_TRY(api, api->Broadcast(e->weights.p, e->weights.p, n_floats, ncclFloat32, root, c->comm, e->stream));
+    mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(e->bias_host, e->weight_image.p + mlptc::BIAS_OFF, sizeof(e->bias_host), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->has_weights = true;
+    return SYN_OK;
+}
+
+int syn_engine_gather_experience(syn_engine* e, syn_comm* c, int root, const syn_rollout_cfg* cfg, uint64_t first_game_index, uint32_t num_games,
+                                 uint64_t seed, syn_experience* out, syn_stats* stats) {
+    if (!e || !c) return fail(SYN_ERR_INVALID_ARGUMENT, "engine or communicator is NULL");
+    if (root < 0 || root >= c->size) return fail(SYN_ERR_INVALID_ARGUMENT, "root %d out of range (%d ranks)", root, c->size);
+    if (c->device != e->device) return fail(SYN_ERR_INVALID_ARGUMENT, "communicator is on device %d, engine on %d", c->device, e->device);
+    if (c->rank == root && !out) return fail(SYN_ERR_INVALID_ARGUMENT, "out is NULL on the root");
+    NcclApi* api = nccl_api();
+    if (!api) return fail(SYN_ERR_COMM, "libnccl.so.2 could not be loaded");
+    e->h2d = 0; e->d2h = 0;
+    // ---- this rank's shard: search, then compact the rows into wire format on the device
+    uint64_t my_rows = 0;
+    float ms = 0.0f;
+    int rc = SYN_OK;
+    if (num_games > 0) {
+        if ((rc = syn_engine_gather_launch(e, cfg, first_game_index, num_games, seed))) return rc;
+        e->pending = false;
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        if ((rc = check_device_error(e))) return rc;
+        std::vector<uint32_t> len(num_games);
+        CUDA_TRY(cudaMemcpyAsync(len.data(), e->game_len.p, (size_t)num_games * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        e->d2h += (uint64_t)num_games * sizeof(uint32_t);
+        std::vector<uint64_t> off(num_games);
+        for (uint32_t i = 0; i < num_games; ++i) { off[i] = my_rows; my_rows += len[i]; }
+        CUDA_TRY(cudaMemcpyAsync(e->row_off.p, off.data(), (size_t)num_games * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+        e->h2d += (uint64_t)num_games * sizeof(uint64_t);
+        CUDA_TRY(e->gx_local.reserve(gx_field_off(5, my_rows) + 256));
+        CompactParams cp;
+        std::memset(&cp, 0, sizeof(cp));
+        cp.num_games = num_games; cp.first_game = first_game_index; cp.game_len = e->game_len.p; cp.row_off = e->row_off.p;
+        cp.row_my = e->row_my.p; cp.row_op = e->row_op.p; cp.row_pi = e->row_pi.p; cp.row_v = e->row_v.p;
+        cp.row_action = e->row_action.p; cp.row_nodes = e->row_nodes.p; cp.row_visits = e->row_visits.p;
+        uint8_t* b = e->gx_local.p;
+        cp.game_ids = (uint64_t*)(b + gx_field_off(0, my_rows)); cp.my_bb = (uint64_t*)(b + gx_field_off(1, my_rows));
+        cp.op_bb = (uint64_t*)(b + gx_field_off(2, my_rows)); cp.pis = (float*)(b + gx_field_off(3, my_rows)); cp.vs = (float*)(b + gx_field_off(4, my_rows));
+        const uint64_t threads = (uint64_t)num_games * 63 * 32;
+        compact_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, e->stream>>>(cp);
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+    } else {
+        CUDA_TRY(cudaSetDevice(e->device));
+        e->launches = 0;
+        CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, CNT_ALL * sizeof(unsigned long long), e->stream));
+    }
+    // ---- how many rows every rank holds (ONE small all-gather), then ONE grouped send/recv of the five arrays to the root
+    const int n = c->size;
+    CUDA_TRY(e->gx_counts.reserve((size_t)n + 1));
+    unsigned long long mine = my_rows;
+    CUDA_TRY(cudaMemcpyAsync(e->gx_counts.p + n, &mine, sizeof(mine), cudaMemcpyHostToDevice, e->stream));
+    NCCL_TRY(api, api->AllGather(e->gx_counts.p + n, e->gx_counts.p, 1, ncclUint64, c->comm, e->stream));
+    std::vector<unsigned long long> counts(n);
+    CUDA_TRY(cudaMemcpyAsync(counts.data(), e->gx_counts.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    uint64_t total = 0;
+    std::vector<uint64_t> first_row(n);
+    for (int r = 0; r < n; ++r) { first_row[r] = total; total += counts[r]; }
+    if (c->rank == root) {
+        out->len = (size_t)total;
+        // every rank must take part in the exchange even if the root cannot hold the result: the capacity error is reported afterwards
+        CUDA_TRY(e->gx_all.reserve(gx_field_off(5, total) + 256));
+    }
+    NCCL_TRY(api, api->GroupStart());
+    for (int f = 0; f < 5; ++f) {
+        if (c->rank == root) {
+            uint8_t* dst = e->gx_all.p + gx_field_off(f, total);
+            for (int r = 0; r < n; ++r) {
+                if (counts[r] == 0) continue;
+                if (r == root) CUDA_TRY(cudaMemcpyAsync(dst + GX_ELT[f] * first_row[r], e->gx_local.p + gx_field_off(f, my_rows), GX_ELT[f] * my_rows, cudaMemcpyDeviceToDevice, e->stream));
+                else NCCL_TRY(api, api->Recv(dst + GX_ELT[f] * first_row[r], GX_ELT[f] * counts[r], ncclUint8, r, c->comm, e->stream));
+            }
+        } else if (my_rows) {
+            NCCL_TRY(api, api->Send(e->gx_local.p + gx_field_off(f, my_rows), GX_ELT[f] * my_rows, ncclUint8, root, c->comm, e->stream));
+        }
+    }
+    NCCL_TRY(api, api->GroupEnd());
+    if (c->rank == root) {
+        if (total > out->capacity) {
+            CUDA_TRY(cudaStreamSynchronize(e->stream));
+            return fail(SYN_ERR_CAPACITY, "experience needs %llu rows, caller provided %zu", (unsigned long long)total, out->capacity);
+        }
+        // ---- rebuild height / player / features from the bitboards and deliver (device destinations in place, host ones staged)
+        const uint8_t* a = e->gx_all.p;
+        const uint64_t* all_my = (const uint64_t*)(a + gx_field_off(1, total));
+        const uint64_t* all_op = (const uint64_t*)(a + gx_field_off(2, total));
+        struct Field { void* dst; size_t elt; size_t off; };
+        Field f3[3] = {{out->height, 9, 0}, {out->player, 1, 0}, {out->states, 63 * 4, 0}};
+        size_t need = 0;
+        for (auto& x : f3)
+            if (x.dst && !is_device_ptr(x.dst)) { x.off = need; need += ((x.elt * total + 255) / 256) * 256; }
+        CUDA_TRY(e->staging.reserve(need ? need : 256));
+        auto tgt = [&](int i) -> void* { return !f3[i].dst ? nullptr : (is_device_ptr(f3[i].dst) ? f3[i].dst : (void*)(e->staging.p + f3[i].off)); };
+        if (total && (f3[0].dst || f3[1].dst || f3[2].dst)) {
+            expand_rows_kernel<<<(uint32_t)((total * 32 + 255) / 256), 256, 0, e->stream>>>(total, all_my, all_op, (uint8_t*)tgt(0), (uint8_t*)tgt(1), (float*)tgt(2));
+            CUDA_TRY(cudaGetLastError());
+            e->launches += 1;
+        }
+        void* dst5[5] = {out->game_ids, out->my_bb, out->op_bb, out->pis, out->vs};
+        for (int f = 0; f < 5; ++f)
+            if ((rc = deliver(e, dst5[f], a + gx_field_off(f, total), GX_ELT[f] * total))) return rc;
+        for (int i = 0; i < 3; ++i)
+            if (f3[i].dst && !is_device_ptr(f3[i].dst) && (rc = deliver(e, f3[i].dst, e->staging.p + f3[i].off, f3[i].elt * total))) return rc;
+        // games = this call's games over all ranks as far as the root can tell: distinct ids are contiguous per rank
+        out->games = 0;
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return read_stats(e, stats, ms);
 }
 
 int syn_engine_search(syn_engine* e, const syn_rollout_cfg* cfg, uint32_t tree_kind, const uint64_t* my_bb, const uint64_t* op_bb,

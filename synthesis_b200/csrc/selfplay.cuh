@@ -595,10 +595,12 @@ struct CompactParams {
 
 // One warp per (game, ply) row; lanes spread over the 63 features.
 __global__ void compact_kernel(const __grid_constant__ CompactParams c) {
-    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // 64-bit: 2^32 threads are 2.1 M games
     int lane = threadIdx.x & 31;
-    uint32_t gi = w / 63u, k = w - gi * 63u;
-    if (gi >= c.num_games || k >= c.game_len[gi]) return;
+    const uint64_t gi64 = w / 63u;
+    if (gi64 >= c.num_games) return;
+    const uint32_t gi = (uint32_t)gi64, k = (uint32_t)(w - gi64 * 63u);
+    if (k >= c.game_len[gi]) return;
     size_t src = (size_t)gi * 63 + k, dst = c.row_off[gi] + k;
     uint64_t my = c.row_my[src], op = c.row_op[src];
     uint64_t occ = my | op;
@@ -618,6 +620,21 @@ __global__ void compact_kernel(const __grid_constant__ CompactParams c) {
     if (lane < 3 && c.vs) c.vs[dst * 3 + lane] = c.row_v[src * 3 + lane];
     if (c.states)
         for (int i = lane; i < 63; i += 32) c.states[dst * 63 + i] = c4::feature(my, op, i);
+}
+
+// What a ReplayBuffer row holds beyond (game id, bitboards, pi, v) is a function of the bitboards: Connect4::height and
+// ::player (connect4.rs:108-114) and Game::features (connect4.rs:237-258).  Rows travel between GPUs as those 72 bytes;
+// the receiving rank rebuilds the rest here (a warp per row).
+__global__ void expand_rows_kernel(uint64_t n_rows, const uint64_t* __restrict__ my_bb, const uint64_t* __restrict__ op_bb, uint8_t* height, uint8_t* player,
+                                   float* states) {
+    const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const uint64_t my = my_bb[row], op = op_bb[row], occ = my | op;
+    if (lane == 0 && player) player[row] = (uint8_t)(__popcll(occ) & 1);
+    if (lane < 9 && height) height[row * 9 + lane] = (uint8_t)c4::height(occ, lane);
+    if (states)
+        for (int i = lane; i < 63; i += 32) states[row * 63 + i] = c4::feature(my, op, i);
 }
 
 } // namespace eng

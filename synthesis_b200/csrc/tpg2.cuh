@@ -21,6 +21,9 @@
 // Node record (32 bytes = one sector), words: 0 num_visits | 1..3 outcome sums L,D,W |
 // 4 action_prob | 5 parent | 6 first_child | 7 num_children | solution<<8 | action<<16.
 #pragma once
+#ifndef SYN_TPG2_CBIAS
+#define SYN_TPG2_CBIAS 0
+#endif
 #include "mlp_team.cuh"
 #include "selfplay.cuh"
 
@@ -611,7 +614,11 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
         long long t2 = PROF ? clock64() : 0;
         if (need) mlpteam::write_features(ms.a[slot], ms.col_lut, r, my, op);
         float y[12];
+#if SYN_TPG2_CBIAS
+        mlpteam::forward_cb<TEAMS, SLOTS>(ms, p.mlp_bias, team, slot, r, mma_phase, y); // biases as constant-bank operands
+#else
         mlpteam::forward<TEAMS, SLOTS>(ms, team, slot, r, mma_phase, y);
+#endif
         mlpteam::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
         long long t3 = PROF ? clock64() : 0;
         // ---- finish: child records for leaves, then ONE backprop site for every kind of explore

@@ -11,6 +11,27 @@ _FIELDS = (("game_ids", np.uint64, ()), ("my_bb", np.uint64, ()), ("op_bb", np.u
            ("player", np.uint8, ()), ("states", np.float32, (63,)), ("pis", np.float32, (9,)), ("vs", np.float32, (3,)))
 
 
+def rows_from_bitboards(my_bb, op_bb):
+    """What a ReplayBuffer row holds beyond (game id, bitboards, pi, v) is a function of the bitboards: Connect4::height,
+    Connect4::player (connect4.rs:108-114, 191) and Game::features (connect4.rs:237-258).  Rows reach the host as 72 bytes
+    (syn_engine_gather_experience, bench.py's e2e leg); this rebuilds the other three columns, vectorised.
+    Returns (height uint8[n][9], player uint8[n], states float32[n][63])."""
+    my = np.ascontiguousarray(my_bb, np.uint64).reshape(-1)
+    op = np.ascontiguousarray(op_bb, np.uint64).reshape(-1)
+    n = my.size
+    cell = (np.arange(7, dtype=np.uint64)[:, None] + np.uint64(7) * np.arange(9, dtype=np.uint64)[None, :]).reshape(-1)  # row*9+col -> bit row + 7*col
+    mine = ((my[:, None] >> cell[None, :]) & np.uint64(1)).astype(bool)
+    theirs = ((op[:, None] >> cell[None, :]) & np.uint64(1)).astype(bool)
+    occ = (mine | theirs).reshape(n, 7, 9)
+    height = occ.sum(axis=1).astype(np.uint8)                      # stones stack from the bottom
+    player = (occ.reshape(n, -1).sum(axis=1) & 1).astype(np.uint8)  # Red (0) moves first
+    states = np.where(mine, np.float32(1.0), np.where(theirs, np.float32(-1.0), np.float32(-0.1))).astype(np.float32).reshape(n, 7, 9)
+    rows = np.arange(7, dtype=np.uint8)[None, :, None]
+    nxt = (rows == height[:, None, :]) & ~occ                      # the next playable cell of every column with room
+    states[nxt] = np.float32(0.1)
+    return height, player, states.reshape(n, 63)
+
+
 class BatchRandSampler:
     """data.rs:6-64: batches of a random permutation of 0..n, the last partial batch dropped when `drop_last`.  Yields
     index arrays (the reference index_selects its three tensors with them).  The permutation comes from `rng`
@@ -135,6 +156,10 @@ class ReplayBuffer:
         n = len(arrays["vs"])
         b.game_id = int(games_played)
         b.steps = n
+        if any(k not in arrays for k in ("height", "player", "states")):  # compact rows: rebuild what the bitboards imply
+            arrays = dict(arrays)
+            h, p, st = rows_from_bitboards(arrays["my_bb"], arrays["op_bb"])
+            arrays.setdefault("height", h); arrays.setdefault("player", p); arrays.setdefault("states", st)
         for name, dt, shape in _FIELDS:
             setattr(b, name, np.ascontiguousarray(arrays[name], dtype=dt).reshape((n,) + shape))
         return b

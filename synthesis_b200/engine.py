@@ -14,6 +14,52 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class Comm:
+    """One rank of a multi-GPU job (`syn_comm`, include/synthesis_b200.h): NCCL inside the library.  The host's only task is
+    to hand rank 0's 128-byte id to the other ranks; `Comm.from_torch` does that over an initialised torch.distributed
+    group (any backend — torch is plumbing here), `Comm(id, n, rank, device)` takes the bytes from anywhere else."""
+
+    def __init__(self, comm_id: bytes, n_ranks: int, rank: int, device: int):
+        self._lib = L.load()
+        if len(comm_id) != L.COMM_ID_BYTES:
+            raise ValueError(f"communicator id must be {L.COMM_ID_BYTES} bytes")
+        buf = (C.c_uint8 * L.COMM_ID_BYTES).from_buffer_copy(comm_id)
+        h = C.c_void_p()
+        L.check(self._lib.syn_comm_create(buf, int(n_ranks), int(rank), int(device), C.byref(h)))
+        self._h = h
+        self.rank, self.size, self.device = int(rank), int(n_ranks), int(device)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * L.COMM_ID_BYTES)()
+        L.check(L.load().syn_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch(cls, device: int, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", device) if backend == "nccl" else torch.device("cpu")
+        t = torch.zeros(L.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0, group=group)
+        return cls(bytes(t.cpu().numpy().tobytes()), world, rank, device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.syn_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, device: int = 0, max_games_in_flight: int = 4736, max_explores: int = 1600):
         self._lib = L.load()
@@ -108,6 +154,45 @@ class Engine:
         if trace:
             t = {k: v[:n] for k, v in t.items()}
         return a, stats.as_dict(), t
+
+    # ---- multi-GPU (replaces the thread fan-out / join of gather_experience and the model_{i}.ot hand-off, alpha_zero.rs:132-168, 192-194)
+    def broadcast_weights(self, comm: "Comm", blob=None, root: int = 0):
+        """ONE NCCL broadcast of the weight blob from rank `root` into every rank's engine.  blob (root only): numpy
+        float32[30492], an int device pointer, or None for the root engine's current weights."""
+        if blob is None or comm.rank != root:
+            p = None
+        elif isinstance(blob, int):
+            p = C.c_void_p(blob)
+        else:
+            b = np.ascontiguousarray(blob, dtype=np.float32).reshape(-1)
+            p = _ptr(b)
+        L.check(self._lib.syn_engine_broadcast_weights(self._h, comm._h, p, L.N_WEIGHTS, int(root)))
+
+    def gather_experience(self, comm: "Comm", cfg: RolloutConfig, leaf_eval_kind: int, first_game_index: int, num_games: int, seed: int,
+                          root: int = 0, capacity_rows: int = None, exp: "L.SynExperience" = None):
+        """Every rank plays its shard [first_game_index, +num_games); rank `root` receives all ranks' rows in rank order.
+        Returns (arrays or None, stats): arrays on the root only.  `exp` (root): caller-provided destinations (pinned host or
+        device pointers) instead of fresh numpy arrays; then arrays is None and exp.len holds the row count."""
+        ccfg = cfg.to_c(leaf_eval_kind)
+        stats = L.SynStats()
+        if comm.rank != root:
+            L.check(self._lib.syn_engine_gather_experience(self._h, comm._h, int(root), C.byref(ccfg), int(first_game_index), int(num_games), int(seed),
+                                                           None, C.byref(stats)))
+            return None, stats.as_dict()
+        if exp is not None:
+            L.check(self._lib.syn_engine_gather_experience(self._h, comm._h, int(root), C.byref(ccfg), int(first_game_index), int(num_games), int(seed),
+                                                           C.byref(exp), C.byref(stats)))
+            return None, stats.as_dict()
+        rows = int(capacity_rows) if capacity_rows is not None else L.MAX_TURNS * int(num_games) * comm.size
+        a, _ = self._alloc(rows, False)
+        exp = L.SynExperience()
+        exp.capacity = rows
+        for k in ("game_ids", "my_bb", "op_bb", "height", "player", "states", "pis", "vs"):
+            setattr(exp, k, a[k].ctypes.data)
+        L.check(self._lib.syn_engine_gather_experience(self._h, comm._h, int(root), C.byref(ccfg), int(first_game_index), int(num_games), int(seed),
+                                                       C.byref(exp), C.byref(stats)))
+        n = int(exp.len)
+        return {k: v[:n] for k, v in a.items()}, stats.as_dict()
 
     def gather_launch(self, cfg: RolloutConfig, leaf_eval_kind: int, first_game_index: int, num_games: int, seed: int):
         ccfg = cfg.to_c(leaf_eval_kind)

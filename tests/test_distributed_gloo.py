@@ -45,14 +45,15 @@ def _worker(rank, world, port, q):
         import synthesis_b200 as s
         from synthesis_b200 import distributed as D
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        # one broadcast of the weights from the trainer rank
-        blob = s.Connect4Net.new(5).blob() if rank == 0 else None
-        w = D.broadcast_weights(blob, src=0).numpy()
-        wsum = float(np.abs(w).sum())
+        # the weights reach rank 1 (on GPUs this is syn_engine_broadcast_weights inside the library; here a plain broadcast)
+        import torch
+        w = torch.from_numpy(s.Connect4Net.new(5).blob().copy()) if rank == 0 else torch.zeros(30492)
+        dist.broadcast(w, src=0)
+        wsum = float(np.abs(w.numpy()).sum())
         buf = s.ReplayBuffer()
         old = s.ReplayBuffer.from_arrays(4, {k: v for k, v in _play_with_oracle(100, 4).items()} | {"game_ids": _play_with_oracle(100, 4)["game_ids"] - np.uint64(100)})
         buf.extend(old)  # 4 older games already in the buffer
-        merged = D.gather_experience_distributed(_play_with_oracle, GAMES, buf if rank == 0 else None, games_to_keep=GAMES + 2,
+        merged = D.gather_rows_over_group(_play_with_oracle, GAMES, buf if rank == 0 else None, games_to_keep=GAMES + 2,
                                                  dst=0, first_game_index=FIRST)
         out = None
         if rank == 0:

@@ -873,25 +873,89 @@ def test_alpha_zero_loop_end_to_end(engine, tmp_path):
 
 
 def test_alpha_zero_distributed_world_of_one_equals_local(engine):
-    """The process-group form of the loop (broadcast weights -> sharded gather -> gather rows -> dedup + train on the
-    trainer rank) with a world of one rank (gloo) reproduces the local loop bit for bit: same games, same rows, same
-    batches, same kernels."""
-    import socket
-    import torch.distributed as dist
+    """The multi-GPU form of the loop (syn_engine_broadcast_weights -> sharded gather -> syn_engine_gather_experience ->
+    dedup + train on the trainer rank) with a communicator of ONE rank reproduces the local loop bit for bit: same games,
+    same rows, same batches, same kernels — NCCL collectives of one rank included."""
     from synthesis_b200 import distributed as D
     cfg = s.LearningConfig(seed=5, logs="", lr_schedule=[(1, 1e-3)], weight_decay=0.0, num_iterations=2, num_epochs=2, batch_size=32,
                            policy_weight=1.0, value_weight=1.0, games_to_keep=200, games_per_train=48,
                            rollout_cfg=s.study_connect4_rollout_cfg(num_explores=24))
     local = s.alpha_zero(cfg, s.Connect4Net.new(cfg.seed), engine=engine)
-    with socket.socket() as so:
-        so.bind(("127.0.0.1", 0))
-        port = so.getsockname()[1]
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    comm = s.Comm(s.Comm.unique_id(), 1, 0, 0)
     try:
-        net = D.alpha_zero_distributed(cfg, engine, policy=s.Connect4Net.new(cfg.seed))
+        net = D.alpha_zero_distributed(cfg, engine, comm, policy=s.Connect4Net.new(cfg.seed))
     finally:
-        dist.destroy_process_group()
+        comm.close()
     assert net.blob().tobytes() == local.blob().tobytes()
+
+
+def test_gather_experience_through_a_communicator_of_one(engine, oracle):
+    """syn_engine_gather_experience on a single rank: rows cross the wire format (72 bytes: ids, bitboards, pi, v) and the
+    height / player / features columns are rebuilt from the bitboards — every column must equal syn_engine_gather's."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=60, sample_actions_until=12)
+    a, st, _ = engine.gather(cfg, L.LEAF_ROLLOUT, 7, 40, 3)
+    comm = s.Comm(s.Comm.unique_id(), 1, 0, 0)
+    try:
+        b, st2 = engine.gather_experience(comm, cfg, L.LEAF_ROLLOUT, 7, 40, 3)
+        c, _ = engine.gather_experience(comm, cfg, L.LEAF_ROLLOUT, 7, 0, 3)  # an empty shard is allowed
+    finally:
+        comm.close()
+    assert_rows_equal(a, b, "communicator of one vs plain gather")
+    assert st["explores"] == st2["explores"] and len(c["vs"]) == 0
+
+
+def _two_rank_worker(rank, world, id_bytes, q):
+    try:
+        import numpy as np
+        import synthesis_b200 as s
+        from synthesis_b200 import _lib as L
+        from synthesis_b200 import distributed as D
+        cfg = s.study_connect4_rollout_cfg(num_explores=80, sample_actions_until=12)
+        comm = s.Comm(id_bytes, world, rank, rank)
+        with s.Engine(rank, 2048, 80) as e:
+            blob = s.Connect4Net.new(9).blob() if rank == 0 else None
+            e.broadcast_weights(comm, blob, root=0)
+            w = e.get_weights()
+            merged, st = D.gather_experience_distributed(e, comm, cfg, L.LEAF_NN, 301, 5, None, 0, root=0, first_game_index=11)
+            out = dict(wsum=float(np.abs(w).sum()), explores=st["explores"])
+            if rank == 0:
+                out["merged"] = {k: v.copy() for k, v in merged.items()}
+        comm.close()
+        q.put((rank, out))
+    except Exception as ex:  # pragma: no cover - surfaced in the parent
+        import traceback
+        q.put((rank, "ERROR " + repr(ex) + "\n" + traceback.format_exc()))
+
+
+def test_two_gpus_concatenated_shards_equal_one_gpu(engine):
+    """301 NN-leaf games sharded over TWO GPUs (150 + 151, alpha_zero.rs:138) through the library's own
+    collectives (one NCCL broadcast of the weights, one gather of 72-byte rows to rank 0) == the same games on one GPU,
+    every column of every row bit for bit.  Needs two visible GPUs (gpurun --gpus 2); fails loudly otherwise."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box (run with gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    id_bytes = s.Comm.unique_id()
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, id_bytes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in procs:
+        r, out = q.get(timeout=600)
+        assert not isinstance(out, str), out
+        res[r] = out
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    blob = s.Connect4Net.new(9).blob()
+    assert res[0]["wsum"] == res[1]["wsum"] == float(np.abs(blob).sum())  # the broadcast reached rank 1
+    cfg = s.study_connect4_rollout_cfg(num_explores=80, sample_actions_until=12)
+    engine.set_weights(blob)
+    whole, st, _ = engine.gather(cfg, L.LEAF_NN, 11, 301, 5)
+    assert_rows_equal(res[0]["merged"], whole, "two GPUs vs one")
+    assert res[0]["explores"] + res[1]["explores"] == st["explores"]
 
 
 # ---------------------------------------------------------------- tpg2 (32-byte records, the product kernels) vs tpg4 (family blocks), and seating

@@ -351,3 +351,28 @@ def test_batch_rand_sampler_and_lr_schedule():
                            batch_size=32, policy_weight=1.0, value_weight=1.0, games_to_keep=1, games_per_train=1,
                            rollout_cfg=s.study_connect4_rollout_cfg())
     assert [s.lr_for_iteration(cfg, i) for i in (0, 18, 19, 38, 39, 100)] == [1e-3, 1e-3, 5e-4, 5e-4, 1e-4, 1e-4]
+
+
+def test_rows_from_bitboards_matches_the_game_mirror():
+    """Compact 72-byte rows (ids, bitboards, pi, v) are what crosses NVLink and PCIe; height / player / features are rebuilt
+    from the bitboards.  The vectorised rebuild must equal Connect4's own accessors (connect4.rs:108-114, 237-258) on
+    random playouts, and ReplayBuffer.from_arrays must accept rows without those columns."""
+    from synthesis_b200.data import rows_from_bitboards
+    rng = np.random.default_rng(3)
+    my, op, hs, ps, fs = [], [], [], [], []
+    for _ in range(300):
+        g = s.Connect4.new()
+        for _ in range(int(rng.integers(0, 60))):
+            acts = list(g.iter_actions())
+            if not acts or g.is_over():
+                break
+            g.step(int(rng.choice(acts)))
+        my.append(g.my_bb); op.append(g.op_bb); hs.append(list(g.height)); ps.append(g.player()); fs.append(np.asarray(g.features(), np.float32).reshape(-1))
+    h, p, st = rows_from_bitboards(np.array(my, np.uint64), np.array(op, np.uint64))
+    assert np.array_equal(h, np.array(hs, np.uint8)) and np.array_equal(p, np.array(ps, np.uint8))
+    assert st.tobytes() == np.array(fs, np.float32).tobytes()
+    n = len(my)
+    compact = dict(game_ids=np.arange(1, n + 1, dtype=np.uint64), my_bb=np.array(my, np.uint64), op_bb=np.array(op, np.uint64),
+                   pis=np.zeros((n, 9), np.float32), vs=np.zeros((n, 3), np.float32))
+    buf = s.ReplayBuffer.from_arrays(n, compact)
+    assert buf.states.tobytes() == st.tobytes() and np.array_equal(buf.height, h) and np.array_equal(buf.player, p)
