@@ -14,7 +14,7 @@
  * translation unit is compiled without FP contraction and without fast-math
  * (nvcc: -fmad=false, default -prec-div/-prec-sqrt; gcc: -ffp-contract=off).
  *
- * Accuracy (checked in tests/test_detmath.py against glibc in double): <= 1 ulp for
+ * Accuracy (checked in tests/test_shared_math_gap.py against glibc in double): <= 1 ulp for
  * expf on [-104, 88.7], <= 1 ulp for logf on positive normals.
  *
  * The polynomial coefficients are the classic Cephes single-precision ones.

@@ -12,6 +12,10 @@
  *   k = 3  Normal FPU           (study-connect4/src/main.rs:43-47 uses thread_rng)
  * With seed = 0 the first two are 2g and 2g+1, the convention of SURVEY.md §8(c)'s vectors.
  * Results therefore do not depend on how games are sharded over GPUs or threads.
+ *
+ * Domain: seed < 2^30 and game_index < 2^32 (SYN_MAX_SEED, SYN_MAX_GAME_INDEX) — inside it distinct (seed, game, k) give
+ * distinct stream seeds; beyond it bits would fall off the top or run into the k selector, so the ABI refuses such
+ * arguments (the reference's own seed is the iteration index, alpha_zero.rs:49, 140).
  */
 #ifndef SYN_STREAMS_H
 #define SYN_STREAMS_H
@@ -21,6 +25,8 @@
 #define SYN_STREAM_ACTION 1u
 #define SYN_STREAM_NOISE 2u
 #define SYN_STREAM_FPU 3u
+#define SYN_MAX_SEED ((1ull << 30) - 1ull)
+#define SYN_MAX_GAME_INDEX ((1ull << 32) - 1ull)
 
 #if defined(__CUDACC__)
 __host__ __device__

@@ -165,7 +165,7 @@ int syn_engine_set_weights(syn_engine* e, const float* blob, size_t n_floats);
 /* Replaces gather_experience / run_n_games / run_game (alpha_zero.rs:120-268) for games
  * [first_game_index, first_game_index + num_games).  Game g draws its random choices from
  * private ChaCha12 streams derived from (seed, g) — see DESIGN.md "random streams" — so the
- * result does not depend on how games are sharded over GPUs.  Blocks until done.
+ * result does not depend on how games are sharded over GPUs.  seed < 2^30, game indices < 2^32 (syn_streams.h).  Blocks until done.
  * `out` rows: see syn_experience.  stats may be NULL. */
 int syn_engine_gather(syn_engine* e, const syn_rollout_cfg* cfg, uint64_t first_game_index, uint32_t num_games,
                       uint64_t seed, syn_experience* out, syn_stats* stats);
@@ -333,6 +333,12 @@ int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, f
  * rollout itself; SYN_ROLLOUT_THREADS = 512 / 640 / 768 / 896 / 1024 games per CTA, default 1024).
  * Results do not depend on any of these. */
 int syn_engine_set_group_lanes(syn_engine* e, int lanes);
+
+/* How the thread-per-game kernels would seat a gather of num_games games on this engine: persistent CTAs launched and the
+ * most games any of them holds.  Games are dealt evenly over ALL SMs (and, inside a CTA, over its warps): 1,000 games —
+ * the reference's games_per_train, study-connect4/src/main.rs:26 — are 148 CTAs of at most 7, not two CTAs of 640.
+ * Diagnostic; results never depend on the seating. */
+int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_eval_kind, uint32_t* ctas, uint32_t* games_per_cta);
 
 /* Which kernel evaluates Connect4Net: 1 (default) = fp16-operand / fp32-accumulate GEMM chain on the
  * tcgen05 tensor cores; 0 = fp32 CUDA-core kernel (kept as the device-side numerical reference).

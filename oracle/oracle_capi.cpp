@@ -156,6 +156,13 @@ int orc_ttt_kat(int which, uint32_t flags, uint32_t* nodes_len, int* best_action
 }
 
 // ---- Connect4Net forward (study-connect4/src/policies.rs:47-59)
+// syn_logf (kind 0) / syn_expf (kind 1) over an array: lets tests/test_shared_math_gap.py compare the shared functions with
+// the correctly rounded results pointwise.
+int orc_detmath(int kind, const float* x, float* y, size_t n) {
+    for (size_t i = 0; i < n; ++i) y[i] = kind == 0 ? syn_logf(x[i]) : syn_expf(x[i]);
+    return 0;
+}
+
 int orc_mlp_eval(const float* weights, const uint64_t* my_bb, const uint64_t* op_bb, uint32_t n, uint32_t flags, float* logits,
                  float* probs) {
     Connect4Net net(weights, (flags & ORC_FLAG_LIBM) != 0);

@@ -4,7 +4,7 @@ libsynthesis_b200.so (hand-written sm_100a kernels behind a C ABI, include/synth
 this package is the host-side mirror of the reference's Rust surface for that path.
 """
 from . import _lib
-from .alpha_zero import MCTS, alpha_zero, engine_for, gather_experience, lr_for_iteration, train_on
+from .alpha_zero import MCTS, alpha_zero, engine_for, games_in_flight_for, gather_experience, lr_for_iteration, train_on
 from .config import (ActionSelection, EvaluationConfig, Exploration, Fpu, LearningConfig, MCTSConfig, PolicyNoise,
                      RolloutConfig, ValueTarget, study_connect4_mcts_cfg, study_connect4_rollout_cfg,
                      study_connect4_rollout_mcts_cfg)

@@ -23,6 +23,13 @@ from .policies import Connect4Net, RolloutPolicy
 _engines = {}
 
 
+def games_in_flight_for(num_games: int) -> int:
+    """How many games an engine made for `num_games` games per iteration should hold in flight: all of them, up to what one
+    B200 seats (148 SMs x 640 threads).  The kernels seat a launch's games evenly over ALL SMs (tp2::seat_of), so the
+    reference's 1,000 games per iteration (study-connect4/src/main.rs:26) run 6-7 per SM, not 640 on two SMs."""
+    return int(min(max(int(num_games), 1), 148 * 640))
+
+
 def engine_for(device: int, max_games_in_flight: int, max_explores: int) -> Engine:
     """One cached engine per (device, capacity): arenas are allocated once, not per iteration."""
     key = (device, max_games_in_flight, max_explores)
@@ -44,7 +51,7 @@ def gather_experience(cfg: LearningConfig, policy, buffer: ReplayBuffer, seed: i
                       device: int = 0, first_game_index: int = 0, return_stats: bool = False):
     kind = _leaf_kind(policy)
     n = int(cfg.games_per_train)
-    eng = engine or engine_for(device, min(max(n, 32), 18944), int(cfg.rollout_cfg.num_explores))
+    eng = engine or engine_for(device, games_in_flight_for(n), int(cfg.rollout_cfg.num_explores))
     if kind == L.LEAF_NN:
         eng.set_weights(policy.blob())
     arrays, stats, _ = eng.gather(cfg.rollout_cfg, kind, first_game_index, n, seed)
@@ -86,7 +93,7 @@ def alpha_zero(cfg: LearningConfig, policy: Connect4Net = None, *, engine: Engin
     git metadata) are the caller's business: `on_iteration(i_iter, engine, buffer, dedup, epoch_losses)` is called where
     the reference saves them.  Returns the trained Connect4Net."""
     n = int(cfg.games_per_train)
-    eng = engine or engine_for(device, min(max(n, 32), 18944), int(cfg.rollout_cfg.num_explores))
+    eng = engine or engine_for(device, games_in_flight_for(n), int(cfg.rollout_cfg.num_explores))
     policy = policy or Connect4Net.new(cfg.seed)
     eng.set_weights(policy.blob())
     eng.reset_optimizer()

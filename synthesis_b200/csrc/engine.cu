@@ -613,6 +613,18 @@ int syn_engine_debug_counters(syn_engine* e, uint64_t* out, uint32_t n) {
     return SYN_OK;
 }
 
+int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_eval_kind, uint32_t* ctas, uint32_t* games_per_cta) {
+    if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    KParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.num_games = num_games;
+    const bool nn = leaf_eval_kind == SYN_LEAF_NN;
+    const uint32_t blocks = nn ? seat_games(e, kp, 128u, (uint32_t)e->tpg_teams) : seat_games(e, kp, (uint32_t)e->rollout_threads, 1u);
+    if (ctas) *ctas = blocks;
+    if (games_per_cta) *games_per_cta = kp.seats_q + (kp.seats_rem ? 1u : 0u);
+    return SYN_OK;
+}
+
 int syn_engine_set_mlp_mode(syn_engine* e, int tensor_cores) {
     if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
     e->use_tc = tensor_cores != 0;
@@ -657,6 +669,10 @@ int syn_engine_gather_launch(syn_engine* e, const syn_rollout_cfg* cfg, uint64_t
     int rc = validate_cfg(cfg, e);
     if (rc) return rc;
     if (num_games == 0) return fail(SYN_ERR_INVALID_ARGUMENT, "num_games must be > 0");
+    // the domain on which (seed, game, stream) -> ChaCha12 seed is injective (include/syn_streams.h)
+    if (seed > SYN_MAX_SEED) return fail(SYN_ERR_INVALID_ARGUMENT, "seed %llu exceeds 2^30 - 1 (syn_streams.h)", (unsigned long long)seed);
+    if (first_game_index + num_games - 1ull > SYN_MAX_GAME_INDEX)
+        return fail(SYN_ERR_INVALID_ARGUMENT, "game indices must stay below 2^32 (first %llu + %u games)", (unsigned long long)first_game_index, num_games);
     CUDA_TRY(cudaSetDevice(e->device));
     size_t rows = (size_t)num_games * 63;
     CUDA_TRY(e->row_my.reserve(rows)); CUDA_TRY(e->row_op.reserve(rows)); CUDA_TRY(e->row_pi.reserve(rows * 9));

@@ -50,7 +50,14 @@ class _Module:
 
 def _rebuild_tensor_v2(storage, storage_offset, size, stride, requires_grad=False, backward_hooks=None, metadata=None):
     size, stride = tuple(int(x) for x in size), tuple(int(x) for x in stride)
+    storage_offset = int(storage_offset)
     item = storage.dtype.itemsize
+    # the view must lie inside the storage record: a truncated or crafted archive must not read out of bounds
+    if len(size) != len(stride) or storage_offset < 0 or any(n < 0 for n in size) or any(st < 0 for st in stride):
+        raise pickle.UnpicklingError("tensor with negative or mismatched size / stride / offset")
+    last = storage_offset + sum((n - 1) * st for n, st in zip(size, stride)) if all(n > 0 for n in size) else storage_offset - 1
+    if last >= len(storage) or (not size and storage_offset >= len(storage)):
+        raise pickle.UnpicklingError(f"tensor view (offset {storage_offset}, size {size}, stride {stride}) exceeds its storage of {len(storage)} elements")
     if not size:
         return np.array(storage[storage_offset], dtype=storage.dtype)
     view = np.lib.stride_tricks.as_strided(storage[storage_offset:], shape=size, strides=tuple(s * item for s in stride))

@@ -1016,3 +1016,16 @@ def test_games_in_flight_do_not_change_results(leaf, in_flight):
     assert_rows_equal(a[2], b[2], "trace")
     for k in _COUNTERS:
         assert a[1][k] == b[1][k], k
+
+
+def test_a_thousand_games_occupy_every_sm():
+    """the public gather_experience sized its engine so that the reference's own configuration
+    (games_per_train = 1000) ran on ONE CTA.  Now the engine holds all of an iteration's games in flight and the kernels
+    seat them over all SMs: 1,000 games = 148 CTAs of at most 7 games, 4,096 = 148 x 28, the bench's 94,720 = 148 x 640."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for n, leaf in ((1000, L.LEAF_NN), (1000, L.LEAF_ROLLOUT), (4096, L.LEAF_NN), (256, L.LEAF_ROLLOUT), (148 * 640, L.LEAF_NN), (5, L.LEAF_NN)):
+        with s.Engine(0, s.games_in_flight_for(n), 50) as e:
+            ctas, per = e.launch_geometry(n, leaf)
+        assert ctas == min(sms, n), (n, ctas)
+        assert per == -(-n // ctas), (n, per)

@@ -126,3 +126,16 @@ def test_export_file_and_slimnn_loading():
     assert W.load_nd(s32, (96, 128)).tobytes() == net.params["l_2.weight"].tobytes()
     with pytest.raises(ValueError):
         W.load_nd(s32, (96, 127))
+
+
+def test_ot_reader_rejects_views_outside_their_storage(tmp_path):
+    """A truncated or crafted archive must not make the reader look outside a tensor's storage record (as_strided on sizes,
+    strides and offsets taken from the pickle)."""
+    import pickle
+    from synthesis_b200.weights import _rebuild_tensor_v2
+    storage = np.arange(12, dtype=np.float32)
+    assert _rebuild_tensor_v2(storage, 0, (3, 4), (4, 1)).shape == (3, 4)
+    assert float(_rebuild_tensor_v2(storage, 11, (), ())) == 11.0
+    for off, size, stride in ((0, (4, 4), (4, 1)), (1, (3, 4), (4, 1)), (0, (3, 4), (5, 1)), (-1, (3,), (1,)), (0, (3,), (-1,)), (12, (), ()), (0, (3, 4), (4,))):
+        with pytest.raises(pickle.UnpicklingError):
+            _rebuild_tensor_v2(storage, off, size, stride)
