@@ -340,10 +340,22 @@ int syn_engine_set_group_lanes(syn_engine* e, int lanes);
  * Diagnostic; results never depend on the seating. */
 int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_eval_kind, uint32_t* ctas, uint32_t* games_per_cta);
 
-/* Which kernel evaluates Connect4Net: 1 (default) = fp16-operand / fp32-accumulate GEMM chain on the
- * tcgen05 tensor cores; 0 = fp32 CUDA-core kernel (kept as the device-side numerical reference).
- * The SYN_MLP=fp32 environment variable selects 0 at syn_engine_create. */
-int syn_engine_set_mlp_mode(syn_engine* e, int tensor_cores);
+/* How Connect4Net (study-connect4/src/policies.rs:28-59, fp32 through libtorch in the reference) is evaluated:
+ *   3 (default) = auto: every time the weights change the engine MEASURES the single-fp16 chain against the split chain on
+ *       1,024 reachable positions and uses the fast one only while its largest error stays below a quarter of the
+ *       tolerance BASELINE.json states (1e-3 abs + 1e-3 rel, logits and outcome probabilities).  Random-init weights
+ *       pass with a margin of 25; trained-size weights do not and get the split chain;
+ *   2 = tcgen05 tensor cores, split-fp16 operands (x = hi + lo, three MMAs per K-step), fp32 accumulate, activations in
+ *       tensor memory: agrees with an fp32 forward to ~1e-7 at any weight scale;
+ *   1 = tcgen05 tensor cores, single fp16 operands (11-bit significands), fp32 accumulate: ~4e-5 at initialisation scale,
+ *       several 1e-3 at trained scale.  Matches between two DIFFERENT networks (syn_engine_set_opponent_weights) and the
+ *       lane-group kernels always run this chain (two split weight images do not fit one SM);
+ *   0 = fp32 CUDA-core kernel (kept as the device-side numerical reference).
+ * SYN_MLP=fp32|fp16|split overrides the default at syn_engine_create.  syn_engine_mlp_in_use reports the chain the next
+ * launch will use (0, 1 or 2) and, in auto mode, the measured error of the fast chain in units of the tolerance (-1 if
+ * not measured). */
+int syn_engine_set_mlp_mode(syn_engine* e, int mode);
+int syn_engine_mlp_in_use(syn_engine* e, int* chain, float* calibration_ratio);
 
 /* Profiling aid, not part of the reference's surface: per-warp clock totals of the last thread-per-game
  * launch, out[0..7) = cycles in {tree advance, waiting for the team, Connect4Net forward, explore

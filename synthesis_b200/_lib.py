@@ -98,7 +98,7 @@ EXPORTED_SYMBOLS = (
     "syn_engine_search", "syn_engine_match", "syn_engine_eval", "syn_engine_play", "syn_engine_set_trace", "syn_engine_set_group_lanes", "syn_engine_set_mlp_mode", "syn_engine_debug_counters",
     "syn_engine_deduplicate", "syn_engine_train", "syn_engine_reset_optimizer", "syn_engine_get_weights",
     "syn_comm_unique_id", "syn_comm_create", "syn_comm_destroy", "syn_comm_rank", "syn_comm_size",
-    "syn_engine_broadcast_weights", "syn_engine_gather_experience", "syn_engine_launch_geometry",
+    "syn_engine_broadcast_weights", "syn_engine_gather_experience", "syn_engine_launch_geometry", "syn_engine_mlp_in_use",
 )
 COMM_ID_BYTES = 128
 
@@ -146,6 +146,7 @@ def load():
     lib.syn_engine_get_weights.argtypes = [vp, vp, C.c_size_t]
     lib.syn_engine_deduplicate.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(SynFlatBatch), C.POINTER(SynStats)]
     lib.syn_engine_launch_geometry.argtypes = [vp, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    lib.syn_engine_mlp_in_use.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_float)]
     lib.syn_comm_unique_id.argtypes = [vp]
     lib.syn_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
     lib.syn_comm_destroy.argtypes = [vp]

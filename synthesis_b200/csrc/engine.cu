@@ -23,6 +23,7 @@
 #include "match.cuh"
 #include "tpg2.cuh"
 #include "tpg2_rollout.cuh"
+#include "tpg2_split.cuh"
 #include "tpg4.cuh"
 #include "tpg4_rollout.cuh"
 #include "dedup.cuh"
@@ -91,6 +92,12 @@ struct syn_engine {
     bool has_weights = false;
     float bias_host[mlptc::BIAS_FLOATS] = {}; // the weight image's biases, for KParams::mlp_bias
     bool use_tc = true;           // Connect4Net on tcgen05 tensor cores (false: fp32 CUDA-core kernel)
+    int mlp_mode = 3;             // requested: 3 = auto (default: see calibrate_mlp), 2 = split-fp16 operands, fp32-grade (mlp_split.cuh), 1 = single fp16 operands (mlp_team.cuh), 0 = fp32 CUDA cores
+    int mlp_eff = 2;              // the chain in use: 0, 1 or 2
+    float calib_ratio = -1.0f;    // auto mode: the single-fp16 chain's largest error on the calibration positions, in units of the tolerance 1e-3 + 1e-3 |y|
+    DevBuf<uint64_t> calib_pos;   // 2 x CALIB_N bitboards of reachable positions
+    DevBuf<float> calib_out;      // 2 x CALIB_N x 12 outputs
+    DevBuf<uint8_t> weight_image_lo; // mlp_split.cuh: fp16(W - fp16(W)) in the layout of weight_image
     DevBuf<unsigned int> next_game;
     DevBuf<unsigned long long> counters;
     DevBuf<int> error;
@@ -126,11 +133,42 @@ struct syn_engine {
     float* trace_visits = nullptr;
 };
 
+constexpr uint32_t CALIB_N = 1024;
+constexpr float CALIB_MAX_RATIO = 0.25f; // the fast chain is used while its observed error stays below a quarter of the tolerance
+
 // Connect4::won on the host (connect4.rs:77-83), for argument validation only
 static bool host_won(uint64_t bb) {
     const uint64_t d1 = bb & (bb >> 6) & (bb >> 12) & (bb >> 18) & c4::D1_MASK, d2 = bb & (bb >> 8) & (bb >> 16) & (bb >> 24) & c4::D2_MASK;
     const uint64_t h = bb & (bb >> 7) & (bb >> 14) & (bb >> 21) & c4::H_MASK, v = bb & (bb >> 1) & (bb >> 2) & (bb >> 3) & c4::V_MASK;
     return (d1 | d2 | h | v) != 0;
+}
+
+// CALIB_N positions reached by random legal play from the empty board (0 .. 40 plies, never past the end of a game): what the
+// network is asked about during self-play.  Deterministic (a fixed xorshift stream), so every engine and every rank calibrates alike.
+static void calibration_positions(std::vector<uint64_t>& my, std::vector<uint64_t>& op) {
+    my.assign(CALIB_N, 0); op.assign(CALIB_N, 0);
+    uint64_t s = 0x9e3779b97f4a7c15ull;
+    auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    for (uint32_t i = 0; i < CALIB_N; ++i) {
+        for (;;) {
+            uint64_t a = 0, b = 0; // a = player to move
+            const uint32_t plies = (uint32_t)(next() % 41);
+            bool ok = true;
+            for (uint32_t k = 0; k < plies && ok; ++k) {
+                const uint64_t occ = a | b;
+                int cols[9], n = 0;
+                for (int c = 0; c < 9; ++c)
+                    if (!((occ >> (7 * c + 6)) & 1ull)) cols[n++] = c;
+                if (n == 0) { ok = false; break; }
+                const int c = cols[next() % (uint64_t)n];
+                const uint64_t bit = (occ + (1ull << (7 * c))) & (0x7full << (7 * c));
+                const uint64_t mover = a | bit;
+                a = b; b = mover;
+                if (host_won(mover) || (occ | bit) == c4::ALL) ok = false;
+            }
+            if (ok) { my[i] = a; op[i] = b; break; }
+        }
+    }
 }
 
 static bool is_device_ptr(const void* p) {
@@ -175,6 +213,19 @@ static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     return SYN_OK;
 }
 
+template <int TEAMS>
+static int launch_tpg_split(syn_engine* e, KParams& kp, uint32_t blocks) { // network leaves at fp32-grade accuracy (tpg2_split.cuh)
+    const size_t smem = tp2s::smem_bytes<TEAMS>();
+    if (e->tpg_prof) {
+        CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2s_kernel<TEAMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        selfplay_nn_tpg2s_kernel<TEAMS, true><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+        return SYN_OK;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2s_kernel<TEAMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_nn_tpg2s_kernel<TEAMS, false><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+    return SYN_OK;
+}
+
 template <int NT, int CW>
 static int launch_rollout_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     const size_t smem = tp2r::smem_bytes(NT);
@@ -183,20 +234,20 @@ static int launch_rollout_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     return SYN_OK;
 }
 
-template <int TEAMS, int SLOTS, bool PROF, int FPU>
+template <int TEAMS, bool PROF, int FPU>
 static int launch_tpg4_k(syn_engine* e, KParams& kp, uint32_t blocks) {
-    size_t smem = sizeof(mlpteam::Smem<TEAMS, SLOTS>) + (size_t)tp2::path_cap(TEAMS) * 128 * TEAMS * sizeof(uint32_t);
-    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg4_kernel<TEAMS, SLOTS, PROF, FPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    selfplay_nn_tpg4_kernel<TEAMS, SLOTS, PROF, FPU><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+    const size_t smem = tp2s::smem_bytes<TEAMS>();
+    CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg4_kernel<TEAMS, PROF, FPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selfplay_nn_tpg4_kernel<TEAMS, PROF, FPU><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
     return SYN_OK;
 }
-template <int TEAMS, int SLOTS>
+template <int TEAMS>
 static int launch_tpg4(syn_engine* e, KParams& kp, uint32_t blocks) {
     const uint32_t fpu = kp.cfg.mcts.fpu_kind;
-    if (fpu == SYN_FPU_PARENT_Q) return launch_tpg4_k<TEAMS, SLOTS, false, SYN_FPU_PARENT_Q>(e, kp, blocks);
-    if (fpu == SYN_FPU_NORMAL) return launch_tpg4_k<TEAMS, SLOTS, false, SYN_FPU_NORMAL>(e, kp, blocks);
-    if (e->tpg_prof) return launch_tpg4_k<TEAMS, SLOTS, true, SYN_FPU_CONST>(e, kp, blocks); // per-warp phase clocks (syn_engine_debug_counters)
-    return launch_tpg4_k<TEAMS, SLOTS, false, SYN_FPU_CONST>(e, kp, blocks);
+    if (fpu == SYN_FPU_PARENT_Q) return launch_tpg4_k<TEAMS, false, SYN_FPU_PARENT_Q>(e, kp, blocks);
+    if (fpu == SYN_FPU_NORMAL) return launch_tpg4_k<TEAMS, false, SYN_FPU_NORMAL>(e, kp, blocks);
+    if (e->tpg_prof) return launch_tpg4_k<TEAMS, true, SYN_FPU_CONST>(e, kp, blocks); // per-warp phase clocks (syn_engine_debug_counters)
+    return launch_tpg4_k<TEAMS, false, SYN_FPU_CONST>(e, kp, blocks);
 }
 
 template <int NT, int FPU>
@@ -248,11 +299,10 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
     const bool tpg4_teams = e->tpg_teams == 4 || e->tpg_teams == 5 || e->tpg_teams == 6;
     const bool tpg4_nt = e->rollout_threads == 512 || e->rollout_threads == 768 || e->rollout_threads == 1024;
     const bool tpg4_ok = e->tpg_ver == 4 && e->max_explores <= tp4::MAX_EXPLORES && (e->arena_nodes >> 2) <= tp4::MAX_LINES;
-    if (nn && e->group_lanes == 1 && e->use_tc && tpg4_ok && tpg4_teams) { // thread per game on family blocks (tpg4.cuh), SYN_TPG_VER=4
+    if (nn && e->group_lanes == 1 && e->mlp_eff == 2 && tpg4_ok && tpg4_teams) { // thread per game on family blocks (tpg4.cuh), SYN_TPG_VER=4
         const uint32_t blocks = seat_games(e, kp, 128u, (uint32_t)e->tpg_teams);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-        int rc = e->tpg_teams == 6 ? launch_tpg4<6, 4>(e, kp, blocks)
-                 : e->tpg_teams == 5 ? launch_tpg4<5, 4>(e, kp, blocks) : launch_tpg4<4, 4>(e, kp, blocks);
+        int rc = e->tpg_teams == 6 ? launch_tpg4<6>(e, kp, blocks) : e->tpg_teams == 5 ? launch_tpg4<5>(e, kp, blocks) : launch_tpg4<4>(e, kp, blocks);
         if (rc) return rc;
         CUDA_TRY(cudaGetLastError());
         e->launches += 1;
@@ -268,7 +318,16 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         e->launches += 1;
         return SYN_OK;
     }
-    if (nn && e->group_lanes == 1 && e->use_tc) { // thread per game (tpg2.cuh): one persistent CTA per SM, games seated over all SMs
+    if (nn && e->group_lanes == 1 && e->mlp_eff == 2 && (e->tpg_teams == 4 || e->tpg_teams == 5 || e->tpg_teams == 6)) { // the product path for network leaves
+        const uint32_t blocks = seat_games(e, kp, 128u, (uint32_t)e->tpg_teams);
+        CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
+        int rc = e->tpg_teams == 6 ? launch_tpg_split<6>(e, kp, blocks) : e->tpg_teams == 5 ? launch_tpg_split<5>(e, kp, blocks) : launch_tpg_split<4>(e, kp, blocks);
+        if (rc) return rc;
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        return SYN_OK;
+    }
+    if (nn && e->group_lanes == 1 && e->mlp_eff != 0) { // thread per game (tpg2.cuh), single-fp16 forward: one persistent CTA per SM, games seated over all SMs
         const uint32_t blocks = seat_games(e, kp, 128u, (uint32_t)e->tpg_teams);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         int rc = e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
@@ -307,7 +366,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
     }
     if (blocks == 0) blocks = 1;
     CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-    if (nn && e->use_tc) {
+    if (nn && e->mlp_eff != 0) {
         size_t smem = nn_tc_smem_bytes(gpb);
         if (gl == 32) {
             CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tc_kernel<32, NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -345,6 +404,7 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.error = e->error.p;
     kp.weights = e->weights.p;
     kp.weight_image = e->weight_image.p;
+    kp.weight_image_lo = e->weight_image_lo.p;
     std::memcpy(kp.mlp_bias, e->bias_host, sizeof(kp.mlp_bias));
     const char* nored = std::getenv("SYN_TPG_NO_RED"); // read per launch so that one test process can run both forms
     kp.no_reductions = (nored && std::atoi(nored) == 1) ? 1u : 0u;
@@ -435,6 +495,14 @@ static int launch_match(syn_engine* e, KParams& kp, mtc::MParams& mp) {
         return SYN_OK;
     }
     mp.active_per_block = active;
+    if (e->mlp_eff == 2 && (mp.players[0].leaf_eval_kind == SYN_LEAF_NN || mp.players[1].leaf_eval_kind == SYN_LEAF_NN)) { // one network, fp32-grade forward
+        const size_t smem_s = sizeof(mlps::Smem<MATCH_TEAMS, 2>);
+        CUDA_TRY(cudaFuncSetAttribute(match_tpg_split_kernel<MATCH_TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        match_tpg_split_kernel<MATCH_TEAMS><<<blocks, per_cta, smem_s, e->stream>>>(kp, mp);
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        return SYN_OK;
+    }
     // no Connect4Net player: the kernel never touches the MLP state, and the shared memory it would take comes out of the L1
     const bool any_nn = mp.players[0].leaf_eval_kind == SYN_LEAF_NN || mp.players[1].leaf_eval_kind == SYN_LEAF_NN;
     size_t smem = any_nn ? sizeof(mlpteam::Smem<MATCH_TEAMS, MATCH_TEAMS>) : 0;
@@ -507,6 +575,69 @@ static size_t gx_field_off(int f, size_t rows) { // 256-byte aligned arrays of `
     return off;
 }
 
+static int launch_eval(syn_engine* e, int chain, const uint64_t* my, const uint64_t* op, uint32_t n, float* logits, float* probs) {
+    if (chain == 2) {
+        const size_t smem = sizeof(mlps::Smem<1, 1>);
+        CUDA_TRY(cudaFuncSetAttribute(eval_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uint32_t blocks = (n + 127) / 128;
+        if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
+        mlps::Bias bias;
+        std::memcpy(bias.b, e->bias_host, sizeof(bias.b));
+        eval_split_kernel<<<blocks, 128, smem, e->stream>>>(e->weight_image.p, e->weight_image_lo.p, bias, my, op, n, logits, probs);
+    } else if (chain == 1) {
+        size_t smem = sizeof(mlptc::Smem);
+        CUDA_TRY(cudaFuncSetAttribute(eval_tc_kernel<NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uint32_t blocks = (n + 127) / 128;
+        if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
+        eval_tc_kernel<NN_THREADS><<<blocks, NN_THREADS, smem, e->stream>>>(e->weight_image.p, my, op, n, logits, probs);
+    } else {
+        size_t smem = (size_t)(mlp::WEIGHT_FLOATS + 2 * 32 * mlp::XS) * sizeof(float);
+        CUDA_TRY(cudaFuncSetAttribute(eval_kernel<NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uint32_t blocks = (n + 31) / 32;
+        if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
+        eval_kernel<NN_THREADS><<<blocks, NN_THREADS, smem, e->stream>>>(e->weights.p, my, op, n, logits, probs);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SYN_OK;
+}
+
+// Which Connect4Net chain the kernels use.  Requested modes 0 / 1 / 2 are taken as they are.  In auto mode (the default) the
+// engine MEASURES, every time the weights change, the single-fp16 chain against the fp32-grade split chain on CALIB_N reachable
+// positions: the fast chain is used only while its largest error stays below a quarter of BASELINE.json's tolerance
+// (1e-3 abs + 1e-3 rel, logits and outcome probabilities).  Random-init weights pass with a margin of 25 (4e-5); trained-size
+// weights do not (7x the tolerance) and get the split chain.  Needs the weights and both images on the device and bias_host filled.
+static int calibrate_mlp(syn_engine* e) {
+    e->calib_ratio = -1.0f;
+    if (e->mlp_mode != 3 || !e->has_weights) { e->mlp_eff = e->mlp_mode == 3 ? 2 : e->mlp_mode; return SYN_OK; }
+    if (!e->calib_pos.p) {
+        std::vector<uint64_t> my, op;
+        calibration_positions(my, op);
+        CUDA_TRY(e->calib_pos.reserve(2 * (size_t)CALIB_N));
+        CUDA_TRY(e->calib_out.reserve(2 * (size_t)CALIB_N * 12));
+        CUDA_TRY(cudaMemcpyAsync(e->calib_pos.p, my.data(), CALIB_N * 8, cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(cudaMemcpyAsync(e->calib_pos.p + CALIB_N, op.data(), CALIB_N * 8, cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    float* o1 = e->calib_out.p;
+    float* o2 = e->calib_out.p + (size_t)CALIB_N * 12;
+    int rc;
+    if ((rc = launch_eval(e, 1, e->calib_pos.p, e->calib_pos.p + CALIB_N, CALIB_N, o1, o1 + (size_t)CALIB_N * 9))) return rc;
+    if ((rc = launch_eval(e, 2, e->calib_pos.p, e->calib_pos.p + CALIB_N, CALIB_N, o2, o2 + (size_t)CALIB_N * 9))) return rc;
+    std::vector<float> h(2 * (size_t)CALIB_N * 12);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), e->calib_out.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float worst = 0.0f;
+    const size_t n = (size_t)CALIB_N * 12;
+    for (size_t i = 0; i < n; ++i) {
+        const float a = h[i], b = h[n + i];
+        const float r = std::fabs(a - b) / (1e-3f + 1e-3f * std::fabs(b));
+        if (!(r <= worst)) worst = r; // a NaN ratio (a chain that overflowed fp16) also lands here
+    }
+    e->calib_ratio = worst;
+    e->mlp_eff = (worst <= CALIB_MAX_RATIO) ? 1 : 2;
+    return SYN_OK;
+}
+
 extern "C" {
 
 int syn_abi_version(void) { return SYN_ABI_VERSION; }
@@ -540,6 +671,8 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     e->sm_count = prop.multiProcessorCount;
     const char* mlpenv = std::getenv("SYN_MLP");
     e->use_tc = !(mlpenv && std::strcmp(mlpenv, "fp32") == 0);
+    e->mlp_mode = !e->use_tc ? 0 : ((mlpenv && std::strcmp(mlpenv, "fp16") == 0) ? 1 : ((mlpenv && std::strcmp(mlpenv, "split") == 0) ? 2 : 3));
+    e->mlp_eff = e->mlp_mode == 3 ? 2 : e->mlp_mode;
     const char* glenv = std::getenv("SYN_GROUP_LANES");
     e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : ((glenv && std::atoi(glenv) == 32) ? 32 : 1);
     const char* tenv = std::getenv("SYN_TPG_TEAMS");
@@ -569,7 +702,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
         (ce = e->nodes.reserve(2 * total)) != cudaSuccess || (ce = e->slot_state.reserve((size_t)e->max_games * tp2::SS_WORDS)) != cudaSuccess ||
-        (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->weight_image.reserve(mlptc::IMG_BYTES)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
+        (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->weight_image.reserve(mlptc::IMG_BYTES)) != cudaSuccess || (ce = e->weight_image_lo.reserve(mlptc::W_TOTAL)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
         (ce = e->counters.reserve(CNT_ALL)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
         int rc = fail(SYN_ERR_CUDA, "engine allocation failed (%zu arena nodes = %.1f MiB): %s", total,
                       (double)total * 32.0 / 1048576.0, cudaGetErrorString(ce));
@@ -584,7 +717,7 @@ void syn_engine_destroy(syn_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->nodes.release(); e->slot_state.release(); e->weights.release(); e->weight_image.release(); e->weights2.release(); e->weight_image2.release(); e->next_game.release(); e->counters.release(); e->error.release();
+    e->nodes.release(); e->slot_state.release(); e->weights.release(); e->weight_image.release(); e->weight_image_lo.release(); e->calib_pos.release(); e->calib_out.release(); e->weights2.release(); e->weight_image2.release(); e->next_game.release(); e->counters.release(); e->error.release();
     e->row_my.release(); e->row_op.release(); e->row_off.release(); e->row_pi.release(); e->row_v.release(); e->row_visits.release();
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();
@@ -613,6 +746,13 @@ int syn_engine_debug_counters(syn_engine* e, uint64_t* out, uint32_t n) {
     return SYN_OK;
 }
 
+int syn_engine_mlp_in_use(syn_engine* e, int* chain, float* calibration_ratio) {
+    if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    if (chain) *chain = e->mlp_eff;
+    if (calibration_ratio) *calibration_ratio = e->calib_ratio;
+    return SYN_OK;
+}
+
 int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_eval_kind, uint32_t* ctas, uint32_t* games_per_cta) {
     if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
     KParams kp;
@@ -627,8 +767,12 @@ int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_
 
 int syn_engine_set_mlp_mode(syn_engine* e, int tensor_cores) {
     if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
+    if (tensor_cores < 0 || tensor_cores > 3) return fail(SYN_ERR_INVALID_ARGUMENT, "mlp mode must be 0 (fp32 CUDA cores), 1 (fp16 operands), 2 (split-fp16 operands) or 3 (auto)");
+    if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is in flight");
     e->use_tc = tensor_cores != 0;
-    return SYN_OK;
+    e->mlp_mode = tensor_cores;
+    CUDA_TRY(cudaSetDevice(e->device));
+    return calibrate_mlp(e);
 }
 
 int syn_engine_set_weights(syn_engine* e, const float* blob, size_t n_floats) {
@@ -638,12 +782,13 @@ int syn_engine_set_weights(syn_engine* e, const float* blob, size_t n_floats) {
     bool dev = is_device_ptr(blob);
     CUDA_TRY(cudaMemcpyAsync(e->weights.p, blob, n_floats * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
     mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p);
+    mlps::build_weight_image_lo<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image_lo.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(e->bias_host, e->weight_image.p + mlptc::BIAS_OFF, sizeof(e->bias_host), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (!dev) e->h2d += n_floats * sizeof(float);
     e->has_weights = true;
-    return SYN_OK;
+    return calibrate_mlp(e);
 }
 
 int syn_engine_set_opponent_weights(syn_engine* e, const float* blob, size_t n_floats) {
@@ -852,6 +997,7 @@ int syn_engine_broadcast_weights(syn_engine* e, syn_comm* c, const float* blob, 
     }
     NCCL_TRY(api, api->Broadcast(e->weights.p, e->weights.p, n_floats, ncclFloat32, root, c->comm, e->stream));
     mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p);
+    mlps::build_weight_image_lo<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image_lo.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(e->bias_host, e->weight_image.p + mlptc::BIAS_OFF, sizeof(e->bias_host), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -1097,18 +1243,9 @@ int syn_engine_eval(syn_engine* e, const uint64_t* my_bb, const uint64_t* op_bb,
     CUDA_TRY(e->s_visits.reserve((size_t)n * 9)); CUDA_TRY(e->s_q.reserve((size_t)n * 3));
     CUDA_TRY(cudaMemcpyAsync(e->pos_my.p, my_bb, n * 8, cudaMemcpyDefault, e->stream));
     CUDA_TRY(cudaMemcpyAsync(e->pos_op.p, op_bb, n * 8, cudaMemcpyDefault, e->stream));
-    if (e->use_tc) {
-        size_t smem = sizeof(mlptc::Smem);
-        CUDA_TRY(cudaFuncSetAttribute(eval_tc_kernel<NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uint32_t blocks = (n + 127) / 128;
-        if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
-        eval_tc_kernel<NN_THREADS><<<blocks, NN_THREADS, smem, e->stream>>>(e->weight_image.p, e->pos_my.p, e->pos_op.p, n, e->s_visits.p, e->s_q.p);
-    } else {
-        size_t smem = (size_t)(mlp::WEIGHT_FLOATS + 2 * 32 * mlp::XS) * sizeof(float);
-        CUDA_TRY(cudaFuncSetAttribute(eval_kernel<NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uint32_t blocks = (n + 31) / 32;
-        if (blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
-        eval_kernel<NN_THREADS><<<blocks, NN_THREADS, smem, e->stream>>>(e->weights.p, e->pos_my.p, e->pos_op.p, n, e->s_visits.p, e->s_q.p);
+    {
+        int rc0 = launch_eval(e, e->mlp_eff, e->pos_my.p, e->pos_op.p, n, e->s_visits.p, e->s_q.p);
+        if (rc0) return rc0;
     }
     CUDA_TRY(cudaGetLastError());
     int rc;
@@ -1388,6 +1525,7 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
     else trn::train_kernel<<<1, trn::NT, sizeof(trn::Smem), e->stream>>>(tp);
     CUDA_TRY(cudaGetLastError());
     mlptc::build_weight_image<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image.p); // the search kernels see the new weights
+    mlps::build_weight_image_lo<<<32, 256, 0, e->stream>>>(e->weights.p, e->weight_image_lo.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(e->bias_host, e->weight_image.p + mlptc::BIAS_OFF, sizeof(e->bias_host), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
@@ -1418,7 +1556,7 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
         stats->h2d_bytes = e->h2d;
         stats->d2h_bytes = e->d2h + 4;
     }
-    return SYN_OK;
+    return calibrate_mlp(e); // the weights moved: which forward chain is accurate enough is measured again
 }
 
 } // extern "C"

@@ -10,6 +10,7 @@
 //
 // FrozenMCTS reuses the 32-byte node record of tpg.cuh with word 1 = cum_value (words 2, 3 unused).
 #pragma once
+#include "mlp_split.cuh"
 #include "mlp_team.cuh"
 #include "tpg.cuh"
 
@@ -420,6 +421,47 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) match_tpg_kernel(const __grid_
     }
     tpg::flush_counters(p, g);
     if (any_nn) mlpteam::teardown<TEAMS, SLOTS>(ms);
+}
+
+// The same with the fp32-grade forward of mlp_split.cuh (one network: two split images do not fit one SM's shared memory, so
+// matches between two DIFFERENT networks run match_tpg_kernel<.., TWO> with the single-fp16 chain).
+template <int TEAMS>
+__global__ void __launch_bounds__(128 * TEAMS, 1) match_tpg_split_kernel(const __grid_constant__ KParams p, const __grid_constant__ mtc::MParams m) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int SLOTS = TEAMS < 2 ? TEAMS : 2;
+    constexpr bool TWO = false;
+    mlps::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlps::Smem<TEAMS, SLOTS>*>(smem_raw);
+    const bool any_nn = m.players[0].leaf_eval_kind == SYN_LEAF_NN || m.players[1].leaf_eval_kind == SYN_LEAF_NN;
+    if (any_nn) mlps::setup<TEAMS, SLOTS>(ms, p.weight_image, p.weight_image_lo);
+    const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
+    tpg::Game g;
+    tpg::init_game(p, g, (size_t)blockIdx.x * m.active_per_block + (threadIdx.x < m.active_per_block ? threadIdx.x : 0u));
+    if (threadIdx.x >= m.active_per_block) g.phase = PH_DONE;
+    uint32_t next_gi = threadIdx.x * gridDim.x + blockIdx.x;
+    rng::Stream rs;
+    rs.init(0, 0);
+    tpg::Leaf lf;
+    uint64_t my = 0, op = 0;
+    for (;;) {
+        int st = mtc::advance(p, m, g, next_gi, rs, lf, my, op);
+        __syncwarp();
+        if (!mlps::team_any(team, st != 0)) break; // no thread of this team has a match left
+        if (!any_nn) continue;
+        const bool second = TWO && st == 1 && (g.ply & 1u) != 0u; // this leaf belongs to players[1]'s tree
+        const bool any1 = mlps::team_any(team, st == 1 && !second);
+        const bool any2 = TWO && mlps::team_any(team, second);
+        if (!any1 && !any2) continue; // nobody needs a network this round
+        uint32_t mma_phase;
+        const int slot = mlps::acquire_slot<TEAMS, SLOTS>(ms, team, r, mma_phase);
+        float y[12];
+        mlps::write_features<TEAMS, SLOTS>(ms, slot, r, my, op, st == 1);
+        mlps::forward<TEAMS, SLOTS>(ms, p.mlp_bias, team, slot, r, mma_phase, y);
+        mlps::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
+        if (st == 1) mtc::finish_nn(p, m, g, lf, y);
+        __syncwarp();
+    }
+    tpg::flush_counters(p, g);
+    if (any_nn) mlps::teardown<TEAMS, SLOTS>(ms);
 }
 
 } // namespace eng

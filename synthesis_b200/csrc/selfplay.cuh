@@ -58,6 +58,7 @@ struct KParams {
     int* error;
     const float* weights; // device blob, NN mode
     const uint8_t* weight_image; // mlptc image (fp16 UMMA layout), NN mode on tensor cores
+    const uint8_t* weight_image_lo; // mlp_split.cuh: the fp16 remainders W - fp16(W) in the same layout
     float mlp_bias[mlptc::BIAS_FLOATS]; // the image's padded fp32 biases again, in the parameter space: constant-bank operands (mlp_team.cuh forward_cb)
 };
 

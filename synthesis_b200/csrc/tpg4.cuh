@@ -4,7 +4,7 @@
 //
 // Replaces synthesis/src/mcts.rs:29-489 and synthesis/src/alpha_zero.rs:229-338 of the reference.
 #pragma once
-#include "tpg2.cuh"
+#include "tpg2_split.cuh"
 #include "tpg4_tree.cuh"
 
 namespace tp4 {
@@ -57,18 +57,19 @@ namespace eng {
 // tcgen05 -> finish (children block, the walk up).
 // FPU = the configured syn_fpu_kind: a kernel per kind, so that the common Fpu::Const build carries neither ParentQ's
 // state nor Normal's call in the child loop.
-template <int TEAMS, int SLOTS, bool PROF, int FPU>
+template <int TEAMS, bool PROF, int FPU>
 __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg4_kernel(const __grid_constant__ KParams p) {
+    constexpr int SLOTS = TEAMS < 2 ? TEAMS : 2; // mlp_split.cuh: the fp32-grade forward, activations in tensor memory
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ unsigned long long s_cnt[CNT_ALL];
     __shared__ unsigned long long s_wcnt[4 * TEAMS][tp2::WC_N]; // per-warp statistics rows (plain adds by lane 0)
-    mlpteam::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlpteam::Smem<TEAMS, SLOTS>*>(smem_raw);
-    constexpr int NT = 128 * TEAMS, PATH_CAP = tp2::path_cap(TEAMS);
-    uint32_t* const path = reinterpret_cast<uint32_t*>(smem_raw + sizeof(mlpteam::Smem<TEAMS, SLOTS>)) + threadIdx.x; // [PATH_CAP][NT] after the MLP state
+    mlps::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlps::Smem<TEAMS, SLOTS>*>(smem_raw);
+    constexpr int NT = 128 * TEAMS, PATH_CAP = tp2s::PATH_CAP;
+    uint32_t* const path = reinterpret_cast<uint32_t*>(smem_raw + sizeof(mlps::Smem<TEAMS, SLOTS>)) + threadIdx.x; // [PATH_CAP][NT] after the MLP state
     if (threadIdx.x < CNT_ALL) s_cnt[threadIdx.x] = 0ull;
     for (int i = threadIdx.x; i < 4 * TEAMS * tp2::WC_N; i += 128 * TEAMS) (&s_wcnt[0][0])[i] = 0ull;
     unsigned long long* const wc = s_wcnt[threadIdx.x >> 5];
-    mlpteam::setup<TEAMS, SLOTS>(ms, p.weight_image);
+    mlps::setup<TEAMS, SLOTS>(ms, p.weight_image, p.weight_image_lo);
     const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
     const tp2::Seat seat = tp2::seat_of(p, team, r, 4);
     uint32_t* const ss = p.slot_state + tp2::SS_WORDS * seat.slot;
@@ -130,14 +131,14 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg4_kernel(const 
         long long t1 = PROF ? clock64() : 0;
         const bool need = (pd.kind & tp2::K_LEAF) != 0u;
         if (PROF) leaves += (uint32_t)__popc(__ballot_sync(0xffffffffu, need));
-        if (!mlpteam::team_any(team, phase != PH_DONE)) break; // no thread of this team has a game left
+        if (!mlps::team_any(team, phase != PH_DONE)) break; // no thread of this team has a game left
         uint32_t mma_phase;
-        const int slot = mlpteam::acquire_slot<TEAMS, SLOTS>(ms, team, r, mma_phase);
+        const int slot = mlps::acquire_slot<TEAMS, SLOTS>(ms, team, r, mma_phase);
         long long t2 = PROF ? clock64() : 0;
-        if (need) mlpteam::write_features(ms.a[slot], ms.col_lut, r, my, op);
+        mlps::write_features<TEAMS, SLOTS>(ms, slot, r, my, op, need);
         float y[12];
-        mlpteam::forward_cb<TEAMS, SLOTS>(ms, p.mlp_bias, team, slot, r, mma_phase, y);
-        mlpteam::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
+        mlps::forward<TEAMS, SLOTS>(ms, p.mlp_bias, team, slot, r, mma_phase, y);
+        mlps::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
         long long t3 = PROF ? clock64() : 0;
         // ---- finish: child records for leaves, then ONE backprop site for every kind of explore
         uint32_t bp_levels = 0u;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg4_kernel(const 
         atomicAdd(&s_cnt[DBG_LEAVES], (unsigned long long)leaves);
         atomicAdd(&s_cnt[DBG_T_TOTAL], (unsigned long long)(clock64() - t_start));
     }
-    mlpteam::teardown<TEAMS, SLOTS>(ms); // ends with a CTA barrier: every warp's counters are in s_cnt / s_wcnt
+    mlps::teardown<TEAMS, SLOTS>(ms); // ends with a CTA barrier: every warp's counters are in s_cnt / s_wcnt
     __syncthreads();
     if (threadIdx.x < CNT_ALL && s_cnt[threadIdx.x]) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
     if (threadIdx.x < tp2::WC_N) {

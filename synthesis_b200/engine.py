@@ -105,9 +105,17 @@ class Engine:
         b = np.ascontiguousarray(blob, dtype=np.float32).reshape(-1)
         L.check(self._lib.syn_engine_set_opponent_weights(self._h, _ptr(b), b.size))
 
-    def set_mlp_mode(self, tensor_cores: bool):
-        """True (default): Connect4Net on the tcgen05 tensor cores; False: the fp32 CUDA-core kernel."""
-        L.check(self._lib.syn_engine_set_mlp_mode(self._h, int(bool(tensor_cores))))
+    def set_mlp_mode(self, mode):
+        """How Connect4Net is evaluated (include/synthesis_b200.h): 3 / True = auto (default: the fast single-fp16 chain while
+        its measured error stays below a quarter of the 1e-3 tolerance, else the split chain), 2 = split-fp16 operands
+        (fp32-grade), 1 = single fp16 operands, 0 / False = fp32 CUDA-core kernel."""
+        L.check(self._lib.syn_engine_set_mlp_mode(self._h, 3 if mode is True else int(mode)))
+
+    def mlp_in_use(self):
+        """(chain the next launch uses: 0 / 1 / 2, the fast chain's measured error in units of the tolerance or -1)."""
+        chain, ratio = C.c_int(), C.c_float()
+        L.check(self._lib.syn_engine_mlp_in_use(self._h, C.byref(chain), C.byref(ratio)))
+        return chain.value, float(ratio.value)
 
     def debug_counters(self):
         """Per-warp phase clocks of the last thread-per-game launch (profiling aid)."""

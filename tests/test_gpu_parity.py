@@ -213,6 +213,7 @@ def test_group_lanes_do_not_change_results(engine, leaf):
     kind = L.LEAF_ROLLOUT if leaf == "rollout" else L.LEAF_NN
     if leaf == "nn":
         engine.set_weights(s.Connect4Net.new(3).blob())
+        engine.set_mlp_mode(1)  # the lane-group kernels carry the single-fp16 chain only: compare the three mappings on that one
     res = {}
     try:
         for gl in (32, 16, 1):
@@ -220,6 +221,7 @@ def test_group_lanes_do_not_change_results(engine, leaf):
             res[gl] = engine.gather(cfg, kind, 0, 200, 1, trace=True)
     finally:
         engine.set_group_lanes(1)
+        engine.set_mlp_mode(3)
     for gl in (16, 1):
         assert_rows_equal(res[gl][0], res[32][0], f"GL{gl} vs GL32 experience")
         assert_rows_equal(res[gl][2], res[32][2], f"GL{gl} vs GL32 trace")
@@ -275,11 +277,14 @@ def test_sharding_is_invisible(engine):
 
 
 # ---------------------------------------------------------------- A9: the network
-@pytest.fixture(params=["tensor_cores", "fp32_cuda_cores"])
+_MLP_MODES = {"split_fp16_tensor_cores": 2, "fp16_tensor_cores": 1, "fp32_cuda_cores": 0}
+
+
+@pytest.fixture(params=list(_MLP_MODES))
 def mlp_mode(request, engine):
-    engine.set_mlp_mode(request.param == "tensor_cores")
+    engine.set_mlp_mode(_MLP_MODES[request.param])
     yield request.param
-    engine.set_mlp_mode(True)
+    engine.set_mlp_mode(3)
 
 
 def test_nn_eval_within_tolerance(engine, oracle, mlp_mode):
@@ -296,11 +301,41 @@ def test_nn_eval_within_tolerance(engine, oracle, mlp_mode):
     np.testing.assert_allclose(pr, rp, rtol=1e-3, atol=1e-3)
     assert np.allclose(pr.sum(1), 1.0, atol=1e-5)
     print(f"{mlp_mode}: max |logit err| = {np.abs(lg - rl).max():.3e}, max |prob err| = {np.abs(pr - rp).max():.3e}")
+    if mlp_mode != "fp16_tensor_cores":  # the product forward (split-fp16 operands) is fp32-grade: two orders below the contract
+        np.testing.assert_allclose(lg, rl, rtol=1e-5, atol=1e-5)
+
+
+def test_forward_chain_is_chosen_by_measurement(engine, oracle):
+    """Auto mode (the default): random-init weights keep the single-fp16 chain (its measured error on 1,024 reachable
+    positions is a few percent of the tolerance); the same network with every weight tripled (logits of tens, the scale
+    training reaches) fails the quarter-tolerance test and gets the split chain; either way the outputs meet the
+    UNRELAXED 1e-3 abs / rel against the fp32 oracle forward."""
+    rng = np.random.default_rng(8)
+    games = random_positions(rng, 500, max_plies=60)
+    my = np.array([g.my_bb for g in games], np.uint64)
+    op = np.array([g.op_bb for g in games], np.uint64)
+    seen = {}
+    for name, blob in (("init", s.Connect4Net.new(5).blob()), ("tripled", (s.Connect4Net.new(5).blob() * np.float32(3.0)).astype(np.float32))):
+        engine.set_weights(blob)
+        chain, ratio = engine.mlp_in_use()
+        lg, pr = engine.eval(my, op)
+        rl, rp = oracle.mlp_eval(blob, my, op)
+        print(f"{name}: chain {chain}, fast chain's measured error {ratio:.3f} of the tolerance, max |logit| {np.abs(rl).max():.1f}, max |logit err| {np.abs(lg - rl).max():.2e}")
+        np.testing.assert_allclose(lg, rl, rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(pr, rp, rtol=1e-3, atol=1e-3)
+        seen[name] = (chain, ratio)
+    assert seen["init"][0] == 1 and 0.0 <= seen["init"][1] <= 0.25
+    assert seen["tripled"][0] == 2 and seen["tripled"][1] > 0.25
+    engine.set_mlp_mode(2)
+    assert engine.mlp_in_use() == (2, -1.0)
+    engine.set_mlp_mode(3)
 
 
 def test_nn_eval_large_weights_and_batch_independence(engine, oracle):
-    """Trained-scale weights (10x the init range) and: a position's output must not depend on which
-    tile row / batch it is evaluated in (that is what lets the oracle replay the GPU's leaf outputs)."""
+    """Trained-scale weights (up to 4x the init range per weight, logits of tens) at BASELINE.json's UNRELAXED tolerance
+    (1e-3 abs / rel against the fp32 forward; round 1 had to loosen it to 2e-3 x max|logit| for the single-fp16 chain), and: a
+    position's output must not depend on which tile row / batch it is evaluated in (that is what lets the oracle replay the
+    GPU's leaf outputs)."""
     rng = np.random.default_rng(21)
     blob = (s.Connect4Net.new(5).blob() * rng.uniform(0.5, 4.0, size=L.N_WEIGHTS)).astype(np.float32)
     engine.set_weights(blob)
@@ -309,7 +344,15 @@ def test_nn_eval_large_weights_and_batch_independence(engine, oracle):
     op = np.array([g.op_bb for g in games], np.uint64)
     lg, pr = engine.eval(my, op)
     rl, rp = oracle.mlp_eval(blob, my, op)
-    np.testing.assert_allclose(lg, rl, rtol=2e-3, atol=2e-3 * max(1.0, float(np.abs(rl).max())))
+    print(f"large weights: max |logit| = {np.abs(rl).max():.1f}, max |logit err| = {np.abs(lg - rl).max():.3e}")
+    np.testing.assert_allclose(lg, rl, rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(pr, rp, rtol=1e-3, atol=1e-3)
+    blob10 = (s.Connect4Net.new(5).blob() * np.float32(3.0)).astype(np.float32)  # every layer 3x: logits ~ 3^5 times the init scale
+    engine.set_weights(blob10)
+    lg10, _ = engine.eval(my, op)
+    rl10, _ = oracle.mlp_eval(blob10, my, op)
+    np.testing.assert_allclose(lg10, rl10, rtol=1e-3, atol=1e-3)
+    engine.set_weights(blob)
     perm = rng.permutation(len(games))
     lg2, pr2 = engine.eval(my[perm], op[perm])
     assert np.array_equal(lg2.view(np.uint32), lg[perm].view(np.uint32))
@@ -368,10 +411,12 @@ def test_gather_nn_close_to_fp32_oracle(engine, oracle, mlp_mode):
     first_gpu = a["vs"][np.r_[True, a["game_ids"][1:] != a["game_ids"][:-1]]]
     first_ref = ra["vs"][np.r_[True, ra["game_ids"][1:] != ra["game_ids"][:-1]]]
     np.testing.assert_allclose(first_gpu, first_ref, rtol=1e-3, atol=1e-3)
-    # fraction of rows that are bit-identical is reported, not asserted (near-ties may flip)
     n = min(len(a["vs"]), len(ra["vs"]))
     same = np.mean(np.all(a["pis"][:n] == ra["pis"][:n], axis=1))
-    print(f"rows identical to the fp32-oracle run: {same:.3f}")
+    print(f"{mlp_mode}: rows identical to the fp32-oracle run: {same:.3f}")
+    if mlp_mode != "fp16_tensor_cores":
+        # fp32-grade leaves: the search almost never meets a near-tie that 1e-6 of a logit could flip (round 1 only printed this)
+        assert same >= 0.99, same
     assert np.allclose(a["pis"].sum(1), 1.0, atol=1e-5)
 
 
@@ -513,13 +558,24 @@ def test_match_two_networks_bit_exact(engine, oracle):
     """eval_against_old(p1, p2) with p1 != p2 (evaluator.rs:131-161, called at :87-94): both weight images resident, a
     forward per image in rounds where a team holds leaves of both players.  The oracle is fed each side's GPU leaf
     outputs (a second small engine holds p2), so moves, per-move visit counts and tree sizes must be identical; and the
-    result must change sides correctly when the two networks swap colours."""
+    result must change sides correctly when the two networks swap colours.
+    Two split-fp16 weight images (2 x 130 KB) do not fit one SM's shared memory, so matches between two DIFFERENT networks
+    run the single-fp16 chain (mlp mode 1); the leaf outputs fed to the oracle are taken in the same mode."""
     import ctypes
     import synthesis_b200.evaluator as ev
+    engine.set_mlp_mode(1)
+    try:
+        _match_two_networks(engine, oracle, ev, ctypes)
+    finally:
+        engine.set_mlp_mode(3)
+
+
+def _match_two_networks(engine, oracle, ev, ctypes):
     p1, p2 = s.Connect4Net.new(21), s.Connect4Net.new(22)
     nn = ev.Player(L.TREE_MCTS, L.LEAF_NN, 150, s.study_connect4_mcts_cfg(), s.ActionSelection.NumVisits)
     mover = ctypes.c_uint32(0)
     with s.Engine(0, 1024, 8) as e2:
+        e2.set_mlp_mode(1)
         for first, second, what in ((p1, p2, "p1 first"), (p2, p1, "p2 first")):
             engine.set_weights(first.blob())
             engine.set_opponent_weights(second.blob())
@@ -818,7 +874,12 @@ def _train_matches_torch_fp32(engine, weight_decay, pw, vw):
     import torch
     with torch.no_grad():
         pl, vl = ref.forward(torch.from_numpy(d["states"][:64]))
+    # after 40 Adam steps, at the unrelaxed tolerance: the forward sees the GPU-trained weights, torch its own (<= 1e-3 apart)
     assert np.allclose(lg, pl.numpy(), rtol=1e-3, atol=2e-3) and np.allclose(pr, torch.softmax(vl, -1).numpy(), rtol=1e-3, atol=2e-3)
+    from oracle_binding import Oracle
+    ol, op_ = Oracle().mlp_eval(engine.get_weights(), d["my_bb"][:64], d["op_bb"][:64])  # same weights on both sides
+    np.testing.assert_allclose(lg, ol, rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(pr, op_, rtol=1e-3, atol=1e-3)
 
 
 def test_train_loss_decreases_and_edge_cases(engine):
