@@ -50,8 +50,9 @@ def parse_args():
                    help="games per step as a multiple of the games one GPU holds in flight (amortises the end-of-step tail)")
     p.add_argument("--explores", type=int, default=0)
     p.add_argument("--leaf", default="", choices=["", "nn", "rollout"])
-    p.add_argument("--group-lanes", type=int, default=int(os.environ.get("SYN_GROUP_LANES", "1")),
-                   help="lanes per game: 1 = thread per game (default), 16 / 32 = lane group per game")
+    p.add_argument("--group-lanes", type=int, default=int(os.environ.get("SYN_GROUP_LANES", "0")),
+                   help="lanes per game: 0 = the engine chooses per launch (default: a thread per game for the large batches, a lane group per game "
+                        "for configs[0] / configs[2]), 1 = thread per game, 16 / 32 = lane group per game")
     p.add_argument("--cpu-games", type=int, default=0, help="games in the CPU sample (default sized for ~10-20 s)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     a = p.parse_args()
@@ -76,11 +77,11 @@ def size_workload(args):
     if args.config == 2:
         args.in_flight, args.games = 4096, args.games or 4096
         return args.in_flight, args.games
-    if args.leaf == "nn" and args.group_lanes == 1:
+    if args.leaf == "nn" and args.group_lanes in (0, 1):
         in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "5"))  # one CTA per SM, teams of 128 games
     elif args.leaf == "nn":
         in_flight = 148 * (512 // args.group_lanes)
-    elif args.group_lanes == 1:
+    elif args.group_lanes in (0, 1):
         in_flight = 148 * int(os.environ.get("SYN_ROLLOUT_THREADS", "1024"))  # one CTA per SM, a thread per game
     else:
         in_flight = 148 * 8 * (256 // args.group_lanes)
@@ -468,10 +469,12 @@ def run_ours(args):
         kernel_s = dev_ns * 1e-9 / max(1, args.steps)  # rank 0's kernel, average launch duration
         per_launch = acc["explores"] / max(1, args.steps)
         achieved = bpe * per_launch / kernel_s / 1e9
-        kernel = (("selfplay_nn_tpg2_kernel" if args.group_lanes == 1 else "selfplay_nn_tc_kernel") if args.leaf == "nn"
-                  else ("selfplay_rollout_tpg2_kernel" if args.group_lanes == 1 else "selfplay_rollout_kernel"))
-        if os.environ.get("SYN_TPG_VER") == "4" and args.group_lanes == 1:
-            kernel = kernel.replace("tpg2", "tpg4")
+        lanes = eng.launch_geometry(games, leaf)[2]
+        chain, calib = eng.mlp_in_use()
+        kernel = ((("selfplay_nn_tpg2s_kernel" if chain == 2 else "selfplay_nn_tpg2_kernel") if lanes == 1 else "selfplay_nn_tc_kernel<%d>" % lanes) if args.leaf == "nn"
+                  else ("selfplay_rollout_tpg2_kernel" if lanes == 1 else "selfplay_rollout_kernel<%d>" % lanes))
+        if os.environ.get("SYN_TPG_VER") == "4" and lanes == 1:
+            kernel = kernel.replace("tpg2s", "tpg4").replace("tpg2", "tpg4")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic(args, kernel, 1e3 * kernel_s), "kernel": kernel,
                     "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": per_launch,
@@ -492,14 +495,17 @@ def run_ours(args):
         line = {
             "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 tree arithmetic; Connect4Net forward: f16 operands, f32 accumulate (tcgen05)" if args.leaf == "nn" else "f32 tree arithmetic, u64 bitboards",
+            "dtype": ("f32 tree arithmetic; Connect4Net forward on tcgen05: %s, f32 accumulate%s" % (
+                          "split-f16 operands (hi + lo, three MMAs per K-step)" if chain == 2 else "f16 operands" if chain == 1 else "f32 CUDA cores",
+                          "; chosen by measurement: the f16 chain's error on 1,024 reachable positions is %.3f of the 1e-3 tolerance" % calib if calib >= 0 else ""))
+                     if args.leaf == "nn" else "f32 tree arithmetic, u64 bitboards",
             "data": "synthetic (random-init weights, seeded games)", "config": config_dict(args, world),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": int(e_h2d) // max(1, args.steps), "d2h_bytes_per_step": int(e_d2h) // max(1, args.steps)},
             "clocks": clocks, "gpu_launches": int(launches_all),
             "positions_per_s": rows / t_dev, "leaf_evals_per_s": leafs / t_dev, "wall_ms_per_step": 1e3 * t_wall / max(1, args.steps),
             "value_excludes": "the row compaction kernel (compact_kernel, ~0.1 % of a step): `value` times the search kernel with the rows left in HBM at rows[game*63+ply]",
-            "group_lanes": args.group_lanes,
+            "group_lanes": lanes,
         }
         emit(line)
     eng.close()

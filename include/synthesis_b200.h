@@ -327,18 +327,20 @@ int syn_engine_gather_experience(syn_engine* e, syn_comm* c, int root, const syn
  * it is what the parity tests compare ("bit-exact visit counts"). */
 int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, float* child_visits /*[cap][9]*/);
 
-/* Lanes per game: 1 (default; a thread per game, 128 games = one tensor-core tile of leaves), 32 (a
- * warp per game) or 16 (two games per warp).  The SYN_GROUP_LANES environment variable overrides the
- * default at syn_engine_create.  With rollout leaves 1 is a thread per game too (the thread plays the
- * rollout itself; SYN_ROLLOUT_THREADS = 512 / 640 / 768 / 896 / 1024 games per CTA, default 1024).
- * Results do not depend on any of these. */
+/* Lanes per game: 0 (default) = chosen per launch from the games in flight — a lane group per game (32 lanes up to 2,368 games,
+ * 16 up to 4,736 with network leaves; 32 up to 4,736 with rollout leaves: children scored in parallel, the shortest time per
+ * explore) and a thread per game beyond (128 games = one tensor-core tile of leaves: the highest throughput); 1, 16, 32 force a
+ * mapping.  The SYN_GROUP_LANES environment variable sets the default at syn_engine_create.  With rollout leaves 1 is a thread
+ * per game too (the thread plays the rollout itself; SYN_ROLLOUT_THREADS = 512 / 640 / 768 / 896 / 1024 games per CTA, default
+ * 1024).  Results do not depend on any of these. */
 int syn_engine_set_group_lanes(syn_engine* e, int lanes);
 
 /* How the thread-per-game kernels would seat a gather of num_games games on this engine: persistent CTAs launched and the
  * most games any of them holds.  Games are dealt evenly over ALL SMs (and, inside a CTA, over its warps): 1,000 games —
  * the reference's games_per_train, study-connect4/src/main.rs:26 — are 148 CTAs of at most 7, not two CTAs of 640.
  * Diagnostic; results never depend on the seating. */
-int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_eval_kind, uint32_t* ctas, uint32_t* games_per_cta);
+int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_eval_kind, uint32_t* ctas, uint32_t* games_per_cta,
+                               uint32_t* lanes_per_game);
 
 /* How Connect4Net (study-connect4/src/policies.rs:28-59, fp32 through libtorch in the reference) is evaluated:
  *   3 (default) = auto: every time the weights change the engine MEASURES the single-fp16 chain against the split chain on

@@ -5,7 +5,7 @@ import synthesis_b200 as s
 from synthesis_b200 import _lib as L
 games = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 explores = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-gl = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+gl = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 modes = sys.argv[4].split(",") if len(sys.argv) > 4 else ["rollout", "nn"]
 in_flight = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # games in flight (default: as many as the GPU seats)
 cfg = s.study_connect4_rollout_cfg(num_explores=explores)

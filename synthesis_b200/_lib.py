@@ -145,7 +145,7 @@ def load():
     lib.syn_engine_reset_optimizer.argtypes = [vp]
     lib.syn_engine_get_weights.argtypes = [vp, vp, C.c_size_t]
     lib.syn_engine_deduplicate.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(SynFlatBatch), C.POINTER(SynStats)]
-    lib.syn_engine_launch_geometry.argtypes = [vp, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    lib.syn_engine_launch_geometry.argtypes = [vp, u32, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     lib.syn_engine_mlp_in_use.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_float)]
     lib.syn_comm_unique_id.argtypes = [vp]
     lib.syn_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]

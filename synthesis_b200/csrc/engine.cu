@@ -76,7 +76,7 @@ struct syn_engine {
     uint32_t max_games = 0, max_explores = 0, arena_nodes = 0; // max_games = arena slots allocated (>= req_games)
     uint32_t req_games = 0; // max_games_in_flight as the caller asked for it
     int tpg_ver = 2;        // thread-per-game tree layout: 2 = tpg2.cuh (32-byte records, the product path), 4 = tpg4.cuh (family blocks; SYN_TPG_VER=4)
-    int group_lanes = 32;  // lanes per game: 32, 16, or 1 (thread per game)
+    int group_lanes = 0;   // lanes per game: 0 = chosen per launch from the games in flight (pick_group_lanes), 32, 16, or 1 (thread per game)
     int tpg_teams = 5;     // teams of 128 threads per CTA in thread-per-game mode (640 threads, 96 registers each; SYN_TPG_TEAMS)
     int rollout_threads = 1024; // threads (= games) per CTA of the thread-per-game rollout kernel: 512, 640, 768, 896 or 1024
     int rollout_cw = 3;         // child records per memory round trip at 896 / 1024 threads (SYN_ROLLOUT_CW = 3 or 5)
@@ -293,13 +293,33 @@ static size_t nn_smem_bytes(int gpb) { return (size_t)(mlp::WEIGHT_FLOATS + 2 * 
 constexpr int ROLLOUT_THREADS = 256;
 constexpr int NN_THREADS = 512;
 
+// Which mapping a launch uses when the caller has not forced one.  A tree is a strictly serial object, so with FEW games in
+// flight the time of an explore is what matters: a lane group per game scores a node's children in parallel and reads a family
+// with one instruction (tree.cuh), and wins below ~5 k games (profiles/r2_small_batches.txt: 4,096 network games 134 M explores/s
+// against 95 M thread-per-game; 256 rollout games 17 M against 9 M).  With many games the thread-per-game kernels win by
+// keeping every lane busy (1.37 G against 0.1-0.3 G).  The lane-group network kernels carry the single-fp16 chain only.
+static int pick_group_lanes(const syn_engine* e, const KParams& kp) {
+    if (e->group_lanes != 0) return e->group_lanes;
+    const bool nn = kp.cfg.leaf_eval_kind == SYN_LEAF_NN;
+    const uint32_t want = kp.num_games < e->req_games ? kp.num_games : e->req_games;
+    if (nn) {
+        if (e->mlp_eff != 1) return 1;                        // fp32-grade (or fp32 CUDA-core) leaves: thread per game
+        if (want <= (uint32_t)e->sm_count * 16u) return 32;    // one wave of warps: 2,368 games
+        if (want <= (uint32_t)e->sm_count * 32u) return 16;    // one wave of half warps: 4,736 games
+        return 1;
+    }
+    if (want <= (uint32_t)e->sm_count * 32u) return 32;
+    return 1;
+}
+
 // Launches the self-play kernel for `n` games/positions.  Rows/search buffers must be set in kp.
 static int launch_selfplay(syn_engine* e, KParams& kp) {
     const bool nn = kp.cfg.leaf_eval_kind == SYN_LEAF_NN;
+    const int lanes = pick_group_lanes(e, kp);
     const bool tpg4_teams = e->tpg_teams == 4 || e->tpg_teams == 5 || e->tpg_teams == 6;
     const bool tpg4_nt = e->rollout_threads == 512 || e->rollout_threads == 768 || e->rollout_threads == 1024;
     const bool tpg4_ok = e->tpg_ver == 4 && e->max_explores <= tp4::MAX_EXPLORES && (e->arena_nodes >> 2) <= tp4::MAX_LINES;
-    if (nn && e->group_lanes == 1 && e->mlp_eff == 2 && tpg4_ok && tpg4_teams) { // thread per game on family blocks (tpg4.cuh), SYN_TPG_VER=4
+    if (nn && lanes == 1 && e->mlp_eff == 2 && tpg4_ok && tpg4_teams) { // thread per game on family blocks (tpg4.cuh), SYN_TPG_VER=4
         const uint32_t blocks = seat_games(e, kp, 128u, (uint32_t)e->tpg_teams);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         int rc = e->tpg_teams == 6 ? launch_tpg4<6>(e, kp, blocks) : e->tpg_teams == 5 ? launch_tpg4<5>(e, kp, blocks) : launch_tpg4<4>(e, kp, blocks);
@@ -308,7 +328,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         e->launches += 1;
         return SYN_OK;
     }
-    if (!nn && e->group_lanes == 1 && tpg4_ok && tpg4_nt) { // rollout leaves on family blocks (tpg4_rollout.cuh), SYN_TPG_VER=4
+    if (!nn && lanes == 1 && tpg4_ok && tpg4_nt) { // rollout leaves on family blocks (tpg4_rollout.cuh), SYN_TPG_VER=4
         const uint32_t blocks = seat_games(e, kp, (uint32_t)e->rollout_threads, 1u);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         int rc = e->rollout_threads == 1024 ? launch_rollout_tpg4<1024>(e, kp, blocks)
@@ -318,7 +338,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         e->launches += 1;
         return SYN_OK;
     }
-    if (nn && e->group_lanes == 1 && e->mlp_eff == 2 && (e->tpg_teams == 4 || e->tpg_teams == 5 || e->tpg_teams == 6)) { // the product path for network leaves
+    if (nn && lanes == 1 && e->mlp_eff == 2 && (e->tpg_teams == 4 || e->tpg_teams == 5 || e->tpg_teams == 6)) { // the product path for network leaves
         const uint32_t blocks = seat_games(e, kp, 128u, (uint32_t)e->tpg_teams);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         int rc = e->tpg_teams == 6 ? launch_tpg_split<6>(e, kp, blocks) : e->tpg_teams == 5 ? launch_tpg_split<5>(e, kp, blocks) : launch_tpg_split<4>(e, kp, blocks);
@@ -327,7 +347,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         e->launches += 1;
         return SYN_OK;
     }
-    if (nn && e->group_lanes == 1 && e->mlp_eff != 0) { // thread per game (tpg2.cuh), single-fp16 forward: one persistent CTA per SM, games seated over all SMs
+    if (nn && lanes == 1 && e->mlp_eff != 0) { // thread per game (tpg2.cuh), single-fp16 forward: one persistent CTA per SM, games seated over all SMs
         const uint32_t blocks = seat_games(e, kp, 128u, (uint32_t)e->tpg_teams);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         int rc = e->tpg_teams == 8 ? launch_tpg<8, 4>(e, kp, blocks)
@@ -340,7 +360,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         e->launches += 1;
         return SYN_OK;
     }
-    if (!nn && e->group_lanes == 1) { // rollout leaves, thread per game (tpg2_rollout.cuh): one persistent CTA per SM
+    if (!nn && lanes == 1) { // rollout leaves, thread per game (tpg2_rollout.cuh): one persistent CTA per SM
         const uint32_t blocks = seat_games(e, kp, (uint32_t)e->rollout_threads, 1u);
         CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
         const bool cw5 = e->rollout_cw == 5;
@@ -353,7 +373,7 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         e->launches += 1;
         return SYN_OK;
     }
-    const int gl = e->group_lanes == 1 ? 16 : e->group_lanes; // lane groups (NN leaves without tensor cores land here too)
+    const int gl = lanes == 1 ? 16 : lanes; // lane groups (NN leaves without tensor cores land here too)
     const int threads = nn ? NN_THREADS : ROLLOUT_THREADS;
     const int gpb = threads / gl;
     uint32_t max_blocks = e->max_games / gpb;
@@ -674,7 +694,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     e->mlp_mode = !e->use_tc ? 0 : ((mlpenv && std::strcmp(mlpenv, "fp16") == 0) ? 1 : ((mlpenv && std::strcmp(mlpenv, "split") == 0) ? 2 : 3));
     e->mlp_eff = e->mlp_mode == 3 ? 2 : e->mlp_mode;
     const char* glenv = std::getenv("SYN_GROUP_LANES");
-    e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : ((glenv && std::atoi(glenv) == 32) ? 32 : 1);
+    e->group_lanes = (glenv && std::atoi(glenv) == 16) ? 16 : ((glenv && std::atoi(glenv) == 32) ? 32 : ((glenv && std::atoi(glenv) == 1) ? 1 : 0));
     const char* tenv = std::getenv("SYN_TPG_TEAMS");
     const char* penv = std::getenv("SYN_TPG_PROF");
     e->tpg_prof = penv && std::atoi(penv) == 1;
@@ -731,7 +751,7 @@ void syn_engine_destroy(syn_engine* e) {
 }
 
 int syn_engine_set_group_lanes(syn_engine* e, int lanes) {
-    if (!e || (lanes != 1 && lanes != 16 && lanes != 32)) return fail(SYN_ERR_INVALID_ARGUMENT, "group lanes must be 1, 16 or 32");
+    if (!e || (lanes != 0 && lanes != 1 && lanes != 16 && lanes != 32)) return fail(SYN_ERR_INVALID_ARGUMENT, "group lanes must be 0 (chosen per launch), 1, 16 or 32");
     e->group_lanes = lanes;
     return SYN_OK;
 }
@@ -753,15 +773,27 @@ int syn_engine_mlp_in_use(syn_engine* e, int* chain, float* calibration_ratio) {
     return SYN_OK;
 }
 
-int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_eval_kind, uint32_t* ctas, uint32_t* games_per_cta) {
+int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_eval_kind, uint32_t* ctas, uint32_t* games_per_cta, uint32_t* lanes_per_game) {
     if (!e) return fail(SYN_ERR_INVALID_ARGUMENT, "engine is NULL");
     KParams kp;
     std::memset(&kp, 0, sizeof(kp));
     kp.num_games = num_games;
+    kp.cfg.leaf_eval_kind = leaf_eval_kind;
     const bool nn = leaf_eval_kind == SYN_LEAF_NN;
-    const uint32_t blocks = nn ? seat_games(e, kp, 128u, (uint32_t)e->tpg_teams) : seat_games(e, kp, (uint32_t)e->rollout_threads, 1u);
-    if (ctas) *ctas = blocks;
-    if (games_per_cta) *games_per_cta = kp.seats_q + (kp.seats_rem ? 1u : 0u);
+    const int lanes = pick_group_lanes(e, kp);
+    if (lanes_per_game) *lanes_per_game = (uint32_t)lanes;
+    if (lanes == 1) {
+        const uint32_t blocks = nn ? seat_games(e, kp, 128u, (uint32_t)e->tpg_teams) : seat_games(e, kp, (uint32_t)e->rollout_threads, 1u);
+        if (ctas) *ctas = blocks;
+        if (games_per_cta) *games_per_cta = kp.seats_q + (kp.seats_rem ? 1u : 0u);
+        return SYN_OK;
+    }
+    const uint32_t gpb = (uint32_t)((nn ? NN_THREADS : ROLLOUT_THREADS) / lanes);
+    uint32_t want = num_games < e->req_games ? num_games : e->req_games;
+    uint32_t blocks = (want + gpb - 1) / gpb;
+    if (nn && blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
+    if (ctas) *ctas = blocks ? blocks : 1u;
+    if (games_per_cta) *games_per_cta = gpb;
     return SYN_OK;
 }
 

@@ -125,10 +125,10 @@ class Engine:
         return {k: int(v) for k, v in zip(names, out)}
 
     def launch_geometry(self, num_games: int, leaf_eval_kind: int):
-        """(persistent CTAs, most games per CTA) a gather of num_games games would be seated as (diagnostic)."""
-        ctas, per = C.c_uint32(), C.c_uint32()
-        L.check(self._lib.syn_engine_launch_geometry(self._h, int(num_games), int(leaf_eval_kind), C.byref(ctas), C.byref(per)))
-        return ctas.value, per.value
+        """(CTAs, most games per CTA, lanes per game) a gather of num_games games would be launched as (diagnostic)."""
+        ctas, per, lanes = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        L.check(self._lib.syn_engine_launch_geometry(self._h, int(num_games), int(leaf_eval_kind), C.byref(ctas), C.byref(per), C.byref(lanes)))
+        return ctas.value, per.value, lanes.value
 
     def set_group_lanes(self, lanes: int):
         L.check(self._lib.syn_engine_set_group_lanes(self._h, int(lanes)))

@@ -45,5 +45,9 @@ def engine(engine_lib):
     """One engine for the GPU tests.  Fails (does not skip) when the CUDA library cannot run: a GPU
     test that silently passes without the native code would void the parity claim."""
     eng = engine_lib.Engine(device=0, max_games_in_flight=4736, max_explores=1600)
+    # the parity suite plays tens to hundreds of games per call: left to itself the engine would run all of them on the lane-group
+    # kernels it prefers for small batches.  The suite pins the thread-per-game kernels (the large-batch product path);
+    # tests/test_gpu_parity.py::test_mapping_chosen_per_launch_does_not_change_results covers the automatic choice.
+    eng.set_group_lanes(1)
     yield eng
     eng.close()

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def big_engine():
     eng = s.Engine(device=0, max_games_in_flight=256, max_explores=10000)
+    eng.set_group_lanes(1)  # the thread-per-game kernels (see tests/conftest.py); the last test below runs the default mapping too
     yield eng
     eng.close()
 
@@ -111,3 +112,11 @@ def test_config0_literally_256_rollout_games_at_800_explores(big_engine, oracle)
     assert_rows_equal(a, ra, "experience")
     for k in ("explores", "leaf_evals", "rows", "trees", "nodes", "select_levels", "children_scanned", "expansions", "children_created", "backprop_levels", "rollout_plies"):
         assert st[k] == rst[k], (k, st[k], rst[k])
+    big_engine.set_group_lanes(0)  # the mapping the engine itself picks for 256 games: a warp per game
+    try:
+        assert big_engine.launch_geometry(256, L.LEAF_ROLLOUT)[2] == 32
+        b, st2, tr2 = big_engine.gather(cfg, L.LEAF_ROLLOUT, 0, 256, 0, trace=True)
+    finally:
+        big_engine.set_group_lanes(1)
+    assert_rows_equal(tr2, rtr, "trace (warp per game)")
+    assert_rows_equal(b, ra, "experience (warp per game)")

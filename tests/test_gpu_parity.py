@@ -1087,6 +1087,37 @@ def test_a_thousand_games_occupy_every_sm():
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     for n, leaf in ((1000, L.LEAF_NN), (1000, L.LEAF_ROLLOUT), (4096, L.LEAF_NN), (256, L.LEAF_ROLLOUT), (148 * 640, L.LEAF_NN), (5, L.LEAF_NN)):
         with s.Engine(0, s.games_in_flight_for(n), 50) as e:
-            ctas, per = e.launch_geometry(n, leaf)
-        assert ctas == min(sms, n), (n, ctas)
+            e.set_group_lanes(1)
+            ctas, per, lanes = e.launch_geometry(n, leaf)
+        assert lanes == 1 and ctas == min(sms, n), (n, ctas)
         assert per == -(-n // ctas), (n, per)
+    # left to itself the engine gives few games a lane group each (the shortest time per explore) and many games a thread each
+    with s.Engine(0, 148 * 640, 50) as e:
+        e.set_weights(s.Connect4Net.new(0).blob())
+        assert e.launch_geometry(1000, L.LEAF_NN)[2] == 32 and e.launch_geometry(4096, L.LEAF_NN)[2] == 16
+        assert e.launch_geometry(256, L.LEAF_ROLLOUT)[2] == 32 and e.launch_geometry(4096, L.LEAF_ROLLOUT)[2] == 32
+        assert e.launch_geometry(148 * 640, L.LEAF_NN)[2] == 1 and e.launch_geometry(20000, L.LEAF_ROLLOUT)[2] == 1
+        e.set_mlp_mode(2)  # fp32-grade leaves exist in the thread-per-game kernels only
+        assert e.launch_geometry(1000, L.LEAF_NN)[2] == 1
+
+
+@pytest.mark.parametrize("leaf", ["nn", "rollout"])
+@pytest.mark.parametrize("games", [100, 3000, 12000])
+def test_mapping_chosen_per_launch_does_not_change_results(leaf, games):
+    """The default engine picks the mapping per launch (32 lanes, 16 lanes or a thread per game by the games in flight); whatever
+    it picks, rows, per-move visit counts and counters equal the thread-per-game kernels'."""
+    cfg = s.study_connect4_rollout_cfg(num_explores=40, sample_actions_until=12)
+    kind = L.LEAF_NN if leaf == "nn" else L.LEAF_ROLLOUT
+    blob = s.Connect4Net.new(5).blob()
+
+    def run(lanes):
+        with s.Engine(0, 148 * 640, 40) as e:
+            e.set_weights(blob)
+            e.set_mlp_mode(1)  # the chain every mapping carries
+            e.set_group_lanes(lanes)
+            return e.gather(cfg, kind, 2, games, 6, trace=True)
+    a, b = run(0), run(1)
+    assert_rows_equal(a[0], b[0], "experience")
+    assert_rows_equal(a[2], b[2], "trace")
+    for k in _COUNTERS:
+        assert a[1][k] == b[1][k], k
