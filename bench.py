@@ -214,7 +214,7 @@ def ncu_traffic(args, kernel, launch_ms):
             for rec in json.load(f):
                 if (rec["leaf"], rec["explores"], rec["games"], rec["group_lanes"]) != (args.leaf, args.explores, args.games, args.group_lanes):
                     continue
-                if rec.get("config", 1 if rec["leaf"] == "nn" else 0) != args.config or kernel not in rec["kernel"]:
+                if rec.get("config", 1 if rec["leaf"] == "nn" else 0) != args.config or kernel.split("<")[0] not in rec["kernel"]:
                     continue
                 if abs(rec["gpu_time_ns"] * 1e-6 - launch_ms) > 0.03 * launch_ms:
                     continue

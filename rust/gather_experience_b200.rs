@@ -97,3 +97,80 @@ pub fn gather_experience_b200<G: 'static + B200Game<N>, const N: usize>(
     buffer.keep_last_n_games(cfg.games_to_keep - cfg.games_per_train); // alpha_zero.rs:164
     buffer.extend(&mut worker);                                        // alpha_zero.rs:165-168
 }
+
+/// `l_1.weight, l_1.bias, ..., l_5.weight, l_5.bias` of the trainer's VarStore as one blob of `SYN_N_WEIGHTS` floats — the
+/// layout `syn_engine_set_weights` takes.  `VarStore::variables()` (tch) is a name -> Tensor map; Connect4Net names its
+/// layers "l_1".."l_5" (study-connect4/src/policies.rs:28-45) and nn::linear stores [out, in] weights row-major.
+pub fn flatten_weights(vs: &tch::nn::VarStore) -> Vec<f32> {
+    let vars = vs.variables();
+    let mut blob = Vec::with_capacity(sys::SYN_N_WEIGHTS);
+    for layer in ["l_1", "l_2", "l_3", "l_4", "l_5"] {
+        for part in ["weight", "bias"] {
+            let t = vars.get(&format!("{}.{}", layer, part)).expect("Connect4Net variable");
+            blob.extend(Vec::<f32>::from(t.to_kind(tch::Kind::Float).flatten(0, -1)));
+        }
+    }
+    assert_eq!(blob.len(), sys::SYN_N_WEIGHTS);
+    blob
+}
+
+/// The reference's `remaining / workers_left` split (alpha_zero.rs:134-141) with ranks in the place of worker threads:
+/// rank r plays `count` games starting at global game index `first`.
+pub fn shard_of(games_per_train: usize, n_ranks: usize, rank: usize) -> (u64, u32) {
+    let (mut first, mut left) = (0usize, games_per_train);
+    for r in 0..n_ranks {
+        let n = left / (n_ranks - r);
+        if r == rank {
+            return (first as u64, n as u32);
+        }
+        first += n;
+        left -= n;
+    }
+    unreachable!()
+}
+
+/// `gather_experience` across GPUs: one process (or thread) per GPU, each with its own engine and a `syn_comm` built from
+/// the 128-byte id of `syn_comm_unique_id` (rank 0 creates it; any transport carries it to the others).  Every rank calls
+/// this; only `root` touches `buffer`.  Two collectives per iteration, both inside the library: the weight blob out, the
+/// 72-byte experience rows in, in rank order == the order `extend` would have produced in worker order.
+pub fn gather_experience_b200_ranks<G: 'static + B200Game<N>, const N: usize>(
+    engine: *mut sys::syn_engine,
+    comm: *mut sys::syn_comm,
+    root: i32,
+    cfg: &LearningConfig,
+    weights: Option<&[f32]>, // Some(..) on root after a tch optimiser step; None = the root engine's own (syn_engine_train)
+    buffer: Option<&mut ReplayBuffer<G, N>>,
+    seed: usize,
+) {
+    let (rank, n_ranks) = unsafe { (sys::syn_comm_rank(comm), sys::syn_comm_size(comm)) };
+    let (first, count) = shard_of(cfg.games_per_train, n_ranks as usize, rank as usize);
+    let ccfg = to_c(&cfg.rollout_cfg);
+    let (ptr, len) = weights.map_or((std::ptr::null(), sys::SYN_N_WEIGHTS), |w| (w.as_ptr(), w.len()));
+    unsafe { check(sys::syn_engine_broadcast_weights(engine, comm, ptr, len, root)) };
+    if rank != root {
+        unsafe { check(sys::syn_engine_gather_experience(engine, comm, root, &ccfg, first, count, seed as u64, std::ptr::null_mut(), std::ptr::null_mut())) };
+        return;
+    }
+    let cap = G::MAX_TURNS * cfg.games_per_train;
+    let (mut ids, mut my, mut op) = (vec![0u64; cap], vec![0u64; cap], vec![0u64; cap]);
+    let (mut height, mut player) = (vec![0u8; cap * 9], vec![0u8; cap]);
+    let (mut states, mut pis, mut vs) = (vec![0f32; cap * 63], vec![0f32; cap * N], vec![0f32; cap * 3]);
+    let mut exp = sys::syn_experience {
+        capacity: cap, len: 0, games: 0,
+        game_ids: ids.as_mut_ptr(), my_bb: my.as_mut_ptr(), op_bb: op.as_mut_ptr(), height: height.as_mut_ptr(),
+        player: player.as_mut_ptr(), states: states.as_mut_ptr(), pis: pis.as_mut_ptr(), vs: vs.as_mut_ptr(),
+    };
+    unsafe { check(sys::syn_engine_gather_experience(engine, comm, root, &ccfg, first, count, seed as u64, &mut exp, std::ptr::null_mut())) };
+    let buffer = buffer.expect("the root rank owns the replay buffer");
+    let mut joined = ReplayBuffer::<G, N>::new(exp.len);
+    let mut last = u64::MAX;
+    for i in 0..exp.len {
+        if ids[i] != last { joined.new_game(); last = ids[i]; }
+        let game = G::from_b200_row(my[i], op[i], &height[9 * i..9 * i + 9], player[i]);
+        let mut pi = [0f32; N];
+        pi.copy_from_slice(&pis[N * i..N * i + N]);
+        joined.add(&game, &pi, [vs[3 * i], vs[3 * i + 1], vs[3 * i + 2]]);
+    }
+    buffer.keep_last_n_games(cfg.games_to_keep - cfg.games_per_train);
+    buffer.extend(&mut joined);
+}

@@ -10,6 +10,11 @@ pub const SYN_N_WEIGHTS: usize = 30492;
 
 pub const SYN_OK: c_int = 0;
 pub const SYN_ERR_UNSUPPORTED: c_int = -4;
+pub const SYN_ERR_COMM: c_int = -8;
+pub const SYN_COMM_ID_BYTES: usize = 128;
+/// include/syn_streams.h: seeds and global game indices are limited so that (seed, game) pairs never alias
+pub const SYN_MAX_SEED: u64 = (1 << 30) - 1;
+pub const SYN_MAX_GAME_INDEX: u64 = (1 << 32) - 1;
 
 pub const SYN_EXPLORATION_UCT: u32 = 0;
 pub const SYN_EXPLORATION_POLYNOMIAL_UCT: u32 = 1;
@@ -143,6 +148,12 @@ pub struct syn_engine {
     _private: [u8; 0],
 }
 
+/// One NCCL communicator, created inside the library (the reference's worker threads become ranks)
+#[repr(C)]
+pub struct syn_comm {
+    _private: [u8; 0],
+}
+
 extern "C" {
     pub fn syn_abi_version() -> c_int;
     pub fn syn_build_info() -> *const c_char;
@@ -170,4 +181,27 @@ extern "C" {
                             losses: *mut f32 /* [n_batches][2] or null */, stats: *mut syn_stats) -> c_int;
     pub fn syn_engine_reset_optimizer(e: *mut syn_engine) -> c_int;
     pub fn syn_engine_get_weights(e: *mut syn_engine, blob: *mut f32, n_floats: usize) -> c_int;
+    pub fn syn_engine_play(e: *mut syn_engine, moves: *const u8, n_moves: *const u32, stride: u32, n_games: u32, my_bb: *mut u64,
+                           op_bb: *mut u64, height: *mut u8 /* [n][9] */, legal_mask_lo: *mut u8, legal_mask_hi: *mut u8,
+                           status: *mut u8, features: *mut f32 /* [n][63] or null */) -> c_int;
+
+    // multi-GPU: alpha_zero.rs:132-168 (fan-out / join) and :192-194 (every worker's vs.load) across ranks
+    pub fn syn_comm_unique_id(id: *mut u8 /* [SYN_COMM_ID_BYTES] */) -> c_int;
+    pub fn syn_comm_create(id: *const u8, n_ranks: c_int, rank: c_int, cuda_device: c_int, out: *mut *mut syn_comm) -> c_int;
+    pub fn syn_comm_destroy(c: *mut syn_comm);
+    pub fn syn_comm_rank(c: *const syn_comm) -> c_int;
+    pub fn syn_comm_size(c: *const syn_comm) -> c_int;
+    pub fn syn_engine_broadcast_weights(e: *mut syn_engine, c: *mut syn_comm, blob: *const f32, n_floats: usize, root: c_int) -> c_int;
+    pub fn syn_engine_gather_experience(e: *mut syn_engine, c: *mut syn_comm, root: c_int, cfg: *const syn_rollout_cfg,
+                                        first_game_index: u64, num_games: u32, seed: u64, out: *mut syn_experience,
+                                        stats: *mut syn_stats) -> c_int;
+
+    // knobs and diagnostics; results never depend on them
+    pub fn syn_engine_set_trace(e: *mut syn_engine, action: *mut u8, tree_nodes: *mut u32, child_visits: *mut f32) -> c_int;
+    pub fn syn_engine_set_group_lanes(e: *mut syn_engine, lanes: c_int) -> c_int;
+    pub fn syn_engine_launch_geometry(e: *mut syn_engine, num_games: u32, leaf_eval_kind: u32, ctas: *mut u32, games_per_cta: *mut u32,
+                                      lanes_per_game: *mut u32) -> c_int;
+    pub fn syn_engine_set_mlp_mode(e: *mut syn_engine, mode: c_int) -> c_int;
+    pub fn syn_engine_mlp_in_use(e: *mut syn_engine, chain: *mut c_int, calibration_ratio: *mut f32) -> c_int;
+    pub fn syn_engine_debug_counters(e: *mut syn_engine, out: *mut u64, n: u32) -> c_int;
 }
