@@ -74,8 +74,8 @@ def size_workload(args):
     if args.config == 0 and not args.scaled_up:
         args.in_flight, args.games = 256, args.games or 256
         return args.in_flight, args.games
-    if args.config == 2:
-        args.in_flight, args.games = 4096, args.games or 4096
+    if args.config == 2:  # 4,096 CONCURRENT games: seats are refilled as games end, 4 x 4,096 games per step
+        args.in_flight, args.games = 4096, args.games or 4 * 4096
         return args.in_flight, args.games
     if args.leaf == "nn" and args.group_lanes in (0, 1):
         in_flight = 148 * 128 * int(os.environ.get("SYN_TPG_TEAMS", "5"))  # one CTA per SM, teams of 128 games
@@ -471,7 +471,7 @@ def run_ours(args):
         achieved = bpe * per_launch / kernel_s / 1e9
         lanes = eng.launch_geometry(games, leaf)[2]
         chain, calib = eng.mlp_in_use()
-        kernel = ((("selfplay_nn_tpg2s_kernel" if chain == 2 else "selfplay_nn_tpg2_kernel") if lanes == 1 else "selfplay_nn_tc_kernel<%d>" % lanes) if args.leaf == "nn"
+        kernel = ((("selfplay_nn_tpg2s_kernel" if chain == 2 else "selfplay_nn_tpg2_kernel") if lanes == 1 else "selfplay_nn_team_kernel<%d>" % lanes) if args.leaf == "nn"
                   else ("selfplay_rollout_tpg2_kernel" if lanes == 1 else "selfplay_rollout_kernel<%d>" % lanes))
         if os.environ.get("SYN_TPG_VER") == "4" and lanes == 1:
             kernel = kernel.replace("tpg2s", "tpg4").replace("tpg2", "tpg4")

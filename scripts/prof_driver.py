@@ -17,8 +17,13 @@ for m in modes:
     eng.gather_launch(cfg, leaf, 0, games, 0)
     st = eng.gather_wait(None)
     print(m, "in flight", in_flight or "max", st["explores"], st["device_ns"] / 1e6, "ms", st["explores"] / st["device_ns"] * 1e3, "M explores/s")
-    if gl == 1 and m == "nn":
-        d = eng.debug_counters()
+    d = eng.debug_counters()
+    if d["x_select"]:  # a -DSYN_LG_PROF build of the lane-group kernels: cycles per round and group
+        r = max(1, d["rounds"])
+        print("   lane-group clocks per round: advance %.0f (select %.0f expand %.0f end-of-move %.0f) wait %.0f leaf %.0f finish %.0f (backprop %.0f) | total %.0f | groups %d rounds/group %.0f"
+              % (d["t_advance"] / r, d["x_select"] / r, d["x_expand"] / r, d["x_eom"] / r, d["t_teamwait"] / r, d["t_mlp"] / r, d["t_finish"] / r, d["x_backprop"] / r,
+                 d["t_total"] / r, d["leaves"], r / max(1, d["leaves"])))
+    elif gl == 1 and m == "nn":
         tot = max(1, d["t_total"])
         print("   phase share of warp time: advance %.1f%% teamwait %.1f%% mlp %.1f%% finish %.1f%% | rounds/warp %.0f leaves/round/warp %.1f | cycles/round %.0f"
               % (100 * d["t_advance"] / tot, 100 * d["t_teamwait"] / tot, 100 * d["t_mlp"] / tot, 100 * d["t_finish"] / tot,

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "selfplay.cuh"
+#include "selfplay_team.cuh"
 #include "match.cuh"
 #include "tpg2.cuh"
 #include "tpg2_rollout.cuh"
@@ -80,6 +81,7 @@ struct syn_engine {
     int tpg_teams = 5;     // teams of 128 threads per CTA in thread-per-game mode (640 threads, 96 registers each; SYN_TPG_TEAMS)
     int rollout_threads = 1024; // threads (= games) per CTA of the thread-per-game rollout kernel: 512, 640, 768, 896 or 1024
     int rollout_cw = 3;         // child records per memory round trip at 896 / 1024 threads (SYN_ROLLOUT_CW = 3 or 5)
+    int lg_teams = 4;      // SYN_LG_TEAMS: teams per CTA of the lane-group network kernel (4 or 5; 0 = the CTA-wide tile of selfplay_nn_tc_kernel)
     bool tpg_prof = false; // SYN_TPG_PROF=1: the instantiation with per-warp phase clocks
    // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
     DevBuf<uint32_t> slot_state;
@@ -292,6 +294,10 @@ static size_t nn_smem_bytes(int gpb) { return (size_t)(mlp::WEIGHT_FLOATS + 2 * 
 
 constexpr int ROLLOUT_THREADS = 256;
 constexpr int NN_THREADS = 512;
+#ifndef SYN_NN_TC_THREADS
+#define SYN_NN_TC_THREADS 512
+#endif
+constexpr int NN_TC_THREADS = SYN_NN_TC_THREADS; // CTA-wide lane-group kernel (SYN_LG_TEAMS=0): 512 = one CTA per SM (faster: profiles/r2_lane_group_clocks.txt), 256 = two
 
 // Which mapping a launch uses when the caller has not forced one.  A tree is a strictly serial object, so with FEW games in
 // flight the time of an explore is what matters: a lane group per game scores a node's children in parallel and reads a family
@@ -310,6 +316,31 @@ static int pick_group_lanes(const syn_engine* e, const KParams& kp) {
     }
     if (want <= (uint32_t)e->sm_count * 32u) return 32;
     return 1;
+}
+
+// Geometry of a lane-group launch: persistent CTAs, all resident, groups dealt evenly over them (lg_seated).
+struct LgGeometry { int gl, threads, gpb; uint32_t blocks, seats_q, seats_rem; bool tc; };
+static bool lg_geometry(const syn_engine* e, const KParams& kp, int lanes, LgGeometry& G) {
+    const bool nn = kp.cfg.leaf_eval_kind == SYN_LEAF_NN;
+    G.gl = lanes == 1 ? 16 : lanes; // NN leaves without tensor cores land here at "1" too
+    G.tc = nn && e->mlp_eff != 0;
+    // tensor-core network leaves: 256-thread CTAs, two per SM (107 KB of shared memory each) — their rounds interleave and
+    // half as many groups share a CTA barrier; fp32 network leaves: one 512-thread CTA per SM (120 KB of fp32 weights)
+    G.threads = G.tc ? (e->lg_teams ? 128 * e->lg_teams : NN_TC_THREADS) : nn ? NN_THREADS : ROLLOUT_THREADS;
+    G.gpb = G.threads / G.gl;
+    const uint32_t max_blocks = e->max_games / (uint32_t)G.gpb;
+    if (max_blocks == 0) return false;
+    const uint32_t resident = (uint32_t)e->sm_count * (G.tc ? ((e->lg_teams == 0 && NN_TC_THREADS <= 256) ? 2u : 1u) : nn ? 1u : (uint32_t)(2048 / ROLLOUT_THREADS));
+    G.blocks = max_blocks < resident ? max_blocks : resident;
+    if (G.blocks > kp.num_games) G.blocks = kp.num_games ? kp.num_games : 1u;
+    const uint64_t seats = (uint64_t)G.blocks * (uint32_t)G.gpb;
+    uint32_t want = kp.num_games < seats ? kp.num_games : (uint32_t)seats;
+    if (want > e->req_games) want = e->req_games; // never more games in flight than the caller allowed
+    if (want == 0) want = 1;
+    if (G.blocks > want) G.blocks = want;
+    G.seats_q = want / G.blocks;
+    G.seats_rem = want % G.blocks;
+    return true;
 }
 
 // Launches the self-play kernel for `n` games/positions.  Rows/search buffers must be set in kp.
@@ -373,27 +404,33 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
         e->launches += 1;
         return SYN_OK;
     }
-    const int gl = lanes == 1 ? 16 : lanes; // lane groups (NN leaves without tensor cores land here too)
-    const int threads = nn ? NN_THREADS : ROLLOUT_THREADS;
-    const int gpb = threads / gl;
-    uint32_t max_blocks = e->max_games / gpb;
-    if (max_blocks == 0) return fail(SYN_ERR_CAPACITY, "max_games_in_flight %u is smaller than one CTA's %d games", e->max_games, gpb);
-    uint32_t want_blocks = (kp.num_games + gpb - 1) / gpb;
-    uint32_t blocks = want_blocks < max_blocks ? want_blocks : max_blocks;
-    if (nn) {
-        uint32_t cap = (uint32_t)e->sm_count; // one CTA per SM: the weights fill most of its shared memory
-        if (blocks > cap) blocks = cap;
-    }
-    if (blocks == 0) blocks = 1;
+    LgGeometry G;
+    if (!lg_geometry(e, kp, lanes, G)) return fail(SYN_ERR_CAPACITY, "max_games_in_flight %u is smaller than one CTA of lane groups", e->max_games);
+    const int gl = G.gl, threads = G.threads, gpb = G.gpb;
+    const uint32_t blocks = G.blocks;
+    const bool tc = G.tc;
+    kp.seats_q = G.seats_q;
+    kp.seats_rem = G.seats_rem;
     CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-    if (nn && e->mlp_eff != 0) {
+    if (tc && e->lg_teams) { // teams of four warps with their own tile and barrier (selfplay_team.cuh)
+#define SYN_LAUNCH_TEAM(GLv, Tv)                                                                                                        \
+    do {                                                                                                                                \
+        const size_t smem = nn_team_smem_bytes<Tv, 4, GLv>();                                                                           \
+        CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_team_kernel<GLv, Tv, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        selfplay_nn_team_kernel<GLv, Tv, 4><<<blocks, threads, smem, e->stream>>>(kp);                                                  \
+    } while (0)
+        if (e->lg_teams == 6) { if (gl == 32) SYN_LAUNCH_TEAM(32, 6); else SYN_LAUNCH_TEAM(16, 6); }
+        else if (e->lg_teams == 5) { if (gl == 32) SYN_LAUNCH_TEAM(32, 5); else SYN_LAUNCH_TEAM(16, 5); }
+        else { if (gl == 32) SYN_LAUNCH_TEAM(32, 4); else SYN_LAUNCH_TEAM(16, 4); }
+#undef SYN_LAUNCH_TEAM
+    } else if (tc) {
         size_t smem = nn_tc_smem_bytes(gpb);
         if (gl == 32) {
-            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tc_kernel<32, NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            selfplay_nn_tc_kernel<32, NN_THREADS><<<blocks, threads, smem, e->stream>>>(kp);
+            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tc_kernel<32, NN_TC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            selfplay_nn_tc_kernel<32, NN_TC_THREADS><<<blocks, threads, smem, e->stream>>>(kp);
         } else {
-            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tc_kernel<16, NN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            selfplay_nn_tc_kernel<16, NN_THREADS><<<blocks, threads, smem, e->stream>>>(kp);
+            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tc_kernel<16, NN_TC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            selfplay_nn_tc_kernel<16, NN_TC_THREADS><<<blocks, threads, smem, e->stream>>>(kp);
         }
     } else if (nn) {
         size_t smem = nn_smem_bytes(gpb);
@@ -698,6 +735,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     const char* tenv = std::getenv("SYN_TPG_TEAMS");
     const char* penv = std::getenv("SYN_TPG_PROF");
     e->tpg_prof = penv && std::atoi(penv) == 1;
+    if (const char* lt = std::getenv("SYN_LG_TEAMS")) { const int v = std::atoi(lt); if (v == 0 || v == 4 || v == 5 || v == 6) e->lg_teams = v; }
     if (tenv && (std::atoi(tenv) == 1 || std::atoi(tenv) == 2 || std::atoi(tenv) == 4 || std::atoi(tenv) == 5 || std::atoi(tenv) == 6 || std::atoi(tenv) == 8)) e->tpg_teams = std::atoi(tenv);
     const char* venv = std::getenv("SYN_TPG_VER");
     if (venv && std::atoi(venv) == 4) e->tpg_ver = 4;
@@ -788,12 +826,10 @@ int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_
         if (games_per_cta) *games_per_cta = kp.seats_q + (kp.seats_rem ? 1u : 0u);
         return SYN_OK;
     }
-    const uint32_t gpb = (uint32_t)((nn ? NN_THREADS : ROLLOUT_THREADS) / lanes);
-    uint32_t want = num_games < e->req_games ? num_games : e->req_games;
-    uint32_t blocks = (want + gpb - 1) / gpb;
-    if (nn && blocks > (uint32_t)e->sm_count) blocks = (uint32_t)e->sm_count;
-    if (ctas) *ctas = blocks ? blocks : 1u;
-    if (games_per_cta) *games_per_cta = gpb;
+    LgGeometry G;
+    if (!lg_geometry(e, kp, lanes, G)) return fail(SYN_ERR_CAPACITY, "max_games_in_flight %u is smaller than one CTA of lane groups", e->max_games);
+    if (ctas) *ctas = G.blocks;
+    if (games_per_cta) *games_per_cta = G.seats_q + (G.seats_rem ? 1u : 0u);
     return SYN_OK;
 }
 

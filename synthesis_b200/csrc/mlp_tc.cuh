@@ -59,9 +59,10 @@ static_assert(w_off(4) == 63488 && b_off(4) == 336, "layer table");
 constexpr int BIAS_FLOATS = b_off(4) + layer_n(4);       // 352
 constexpr int IMG_BYTES = W_TOTAL + BIAS_FLOATS * 4;     // 66432 B, multiple of 16
 static_assert(IMG_BYTES % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
-// activation tiles: even layers read A0, odd layers read A1
-constexpr int A0_BYTES = (96 / 8) * M_TILE * 16;         // K up to 96  -> 24576 B
-constexpr int A1_BYTES = (128 / 8) * M_TILE * 16;        // K up to 128 -> 32768 B
+// ONE activation tile, rewritten in place: a layer's epilogue starts after all of the layer's MMAs have completed
+// (mbarrier), so the rows of the next layer's A operand can overwrite the rows just consumed.  32 KB instead of two
+// tiles (56 KB) is what lets two CTAs share an SM (107 KB each with the weight image).
+constexpr int A_BYTES = (128 / 8) * M_TILE * 16;         // K up to 128 -> 32768 B
 constexpr int TMEM_COLS = 128;
 
 // blob offsets (floats) of l_k.weight / l_k.bias in the caller's weight blob
@@ -156,8 +157,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | ((
 // Shared-memory block of the tensor-core MLP.
 struct __align__(128) Smem {
     uint8_t img[IMG_BYTES];   // fp16 weights of the five layers + fp32 biases (the bulk-copied image)
-    uint8_t a0[A0_BYTES];     // A tile read by layers 0, 2, 4
-    uint8_t a1[A1_BYTES];     // A tile read by layers 1, 3
+    uint8_t a[A_BYTES];       // the A tile: features first, then every layer's activations in place
     float y[M_TILE][16];      // final layer output per row: 9 policy logits, 3 value logits, 4 pad
     uint64_t bar_w;           // weights landed
     uint64_t bar_mma;         // a layer's MMAs completed
@@ -183,7 +183,7 @@ __device__ __forceinline__ void setup(Smem& s, const uint8_t* __restrict__ weigh
     if (warp == 1) tmem_alloc(&s.tmem_base, TMEM_COLS);
     // zero the activation tiles once: rows that never carry a leaf must not hold NaN patterns that
     // could leak (they cannot: rows are independent) — zeroing just keeps the tile deterministic
-    for (int i = threadIdx.x; i < (A0_BYTES + A1_BYTES) / 16; i += blockDim.x) reinterpret_cast<uint4*>(s.a0)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(s.a)[i] = make_uint4(0u, 0u, 0u, 0u);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -202,8 +202,8 @@ __device__ __forceinline__ void teardown(Smem& s) {
     if ((threadIdx.x >> 5) == 1) tmem_dealloc(s.tmem_base, TMEM_COLS);
 }
 
-// Forward pass over the rows currently in s.a0 (fp16 features, K = 80, permuted: kperm()).  All NW warps call; every
-// thread must have finished writing its part of a0 (generic-proxy stores) before the call — the
+// Forward pass over the rows currently in s.a (fp16 features, K = 80, permuted: kperm()).  All NW warps call; every
+// thread must have finished writing its part of the tile (generic-proxy stores) before the call — the
 // function issues the proxy fence and the CTA barrier itself.  `phase` is the running parity of
 // bar_mma and must be kept by the caller across calls (start at 0).  nrows_per_quarter = number
 // of valid rows in each 32-row quarter (valid slots / 4, rounded up).
@@ -218,8 +218,8 @@ __device__ __forceinline__ void forward(Smem& s, uint32_t& phase, int nrows_per_
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
         const int K = layer_k(l), N = layer_n(l);
-        uint8_t* a_in = (l & 1) ? s.a1 : s.a0;
-        uint8_t* a_out = (l & 1) ? s.a0 : s.a1;
+        uint8_t* a_in = s.a;
+        uint8_t* a_out = s.a;
         if (threadIdx.x == 0) {
             tc_fence_after();
             const uint32_t a_base = smem_u32(a_in), b_base = smem_u32(s.img + w_off(l));

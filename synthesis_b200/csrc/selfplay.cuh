@@ -227,6 +227,41 @@ __device__ __forceinline__ void flush_counters(const Grp<GL>& g, const KParams& 
     for (int i = 0; i < CNT_N; ++i) t.cnt[i] = 0u;
 }
 
+// Seating of the lane-group kernels: CTA b runs seats_q + (b < seats_rem) groups, so that few games are dealt over all SMs
+// (and both CTAs of an SM) instead of filling the first CTAs — with network leaves a round ends at a CTA barrier, and the
+// fewer groups share it the less each waits for the slowest descent.  Idle groups still join the barriers.
+__device__ __forceinline__ bool lg_seated(const KParams& p, int grp) { return (uint32_t)grp < p.seats_q + (blockIdx.x < p.seats_rem ? 1u : 0u); }
+
+#ifdef SYN_LG_PROF
+// Phase clocks of the lane-group kernels (a -DSYN_LG_PROF build only; syn_engine_debug_counters): one set per group.
+struct LgProf {
+    long long adv = 0, wait = 0, leaf = 0, fin = 0, rounds = 0, t_start;
+    __device__ __forceinline__ LgProf() { t_start = clock64(); }
+    template <int GL>
+    __device__ __forceinline__ void flush(const Grp<GL>& g, const KParams& p, Tree<GL>& t) {
+        if (g.gl != 0) return;
+        atomicAdd(p.counters + DBG_T_ADVANCE, (unsigned long long)adv);
+        atomicAdd(p.counters + DBG_T_TEAMWAIT, (unsigned long long)wait);
+        atomicAdd(p.counters + DBG_T_MLP, (unsigned long long)leaf);
+        atomicAdd(p.counters + DBG_T_FINISH, (unsigned long long)fin);
+        atomicAdd(p.counters + DBG_ROUNDS, (unsigned long long)rounds);
+        atomicAdd(p.counters + DBG_LEAVES, 1ull); // groups
+        atomicAdd(p.counters + DBG_T_TOTAL, (unsigned long long)(clock64() - t_start));
+        atomicAdd(p.counters + DBG_X_SELECT, (unsigned long long)t.pt[0]);
+        atomicAdd(p.counters + DBG_X_EXPAND, (unsigned long long)t.pt[1]);
+        atomicAdd(p.counters + DBG_X_EOM, (unsigned long long)t.pt[2]);
+        atomicAdd(p.counters + DBG_X_BACKPROP, (unsigned long long)t.pt[3]);
+    }
+};
+#define LGP_INIT(t) LgProf lgp; (t).pt[0] = (t).pt[1] = (t).pt[2] = (t).pt[3] = 0
+#define LGP_MARK(field, since) do { long long _n = clock64(); lgp.field += _n - (since); (since) = _n; } while (0)
+#define LGP_FLUSH(g, p, t) lgp.flush(g, p, t)
+#else
+#define LGP_INIT(t) ((void)0)
+#define LGP_MARK(field, since) ((void)(since))
+#define LGP_FLUSH(g, p, t) ((void)0)
+#endif
+
 // Runs the group's state machine until a leaf needs Policy::eval (returns true, `pend` filled) or
 // no games are left (returns false, phase == PH_DONE).
 template <int GL, bool NN>
@@ -279,7 +314,9 @@ __device__ __forceinline__ bool advance(const Grp<GL>& g, const KParams& p, Tree
         } else { // explore_n (mcts.rs:139-147): stop at num_explores or as soon as the root is solved
             uint32_t rpk = t.meta[0].w;
             if (st.e_done >= p.cfg.num_explores || ((rpk >> 8) & 0xffu) != 0u) {
+                const long long lgp_eom = LGP_NOW();
                 end_of_move(g, p, t, st);
+                LGP_ADD(t, 2, lgp_eom);
                 if (t.err) {
                     if (g.gl == 0) atomicCAS(p.error, 0, t.err);
                     st.phase = PH_DONE;
@@ -326,19 +363,28 @@ __global__ void __launch_bounds__(THREADS) selfplay_rollout_kernel(const __grid_
 #pragma unroll
     for (int i = 0; i < CNT_N; ++i) t.cnt[i] = 0u;
     GroupState<GL, false> st;
-    st.phase = PH_NEED_GAME;
+    st.phase = lg_seated(p, grp) ? PH_NEED_GAME : PH_DONE;
     st.is_init = false;
     RolloutRng<GL> rr;
     rr.buf = s_rng[grp]; rr.kA = rr.kB = 0; rr.pos = 0;
     Pending pend;
+    LGP_INIT(t);
+    long long lgp_t = LGP_NOW();
     while (advance<GL, false>(g, p, t, st, rr, s_rng[grp], pend)) {
+        LGP_MARK(adv, lgp_t);
         uint32_t plies = 0;
         int idx = rollout(g, pend.my, pend.op, rr, plies);
         t.cnt[CNT_ROLLOUT_PLIES] += plies;
+        LGP_MARK(leaf, lgp_t);
         explore_finish(g, t, pend, true, 0.0f, idx == 0 ? 1.0f : 0.0f, idx == 1 ? 1.0f : 0.0f, idx == 2 ? 1.0f : 0.0f);
         after_eval(g, t, st);
+        LGP_MARK(fin, lgp_t);
+#ifdef SYN_LG_PROF
+        ++lgp.rounds;
+#endif
     }
     flush_counters(g, p, t);
+    LGP_FLUSH(g, p, t);
 }
 
 // ------------------------------------------------------------------ NN-mode kernel (fp32 CUDA-core MLP)
@@ -366,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_kernel(const __grid_co
 #pragma unroll
     for (int i = 0; i < CNT_N; ++i) t.cnt[i] = 0u;
     GroupState<GL, true> st;
-    st.phase = PH_NEED_GAME;
+    st.phase = lg_seated(p, grp) ? PH_NEED_GAME : PH_DONE;
     st.is_init = false;
     RolloutRng<GL> rr;
     rr.buf = nullptr; rr.kA = rr.kB = 0; rr.pos = 0;
@@ -399,7 +445,7 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_kernel(const __grid_co
 // Group i of the CTA owns tile row mlptc::row_of_slot(i); the whole CTA runs one five-GEMM chain per
 // round for all of its groups' leaves.
 template <int GL, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) selfplay_nn_tc_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) selfplay_nn_tc_kernel(const __grid_constant__ KParams p) {
     constexpr int GPB = THREADS / GL;
     static_assert(GPB <= 128 && GPB % 4 == 0, "one tile row per group");
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -422,23 +468,31 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_tc_kernel(const __grid
 #pragma unroll
     for (int i = 0; i < CNT_N; ++i) t.cnt[i] = 0u;
     GroupState<GL, true> st;
-    st.phase = PH_NEED_GAME;
+    st.phase = lg_seated(p, grp) ? PH_NEED_GAME : PH_DONE;
     st.is_init = false;
     RolloutRng<GL> rr;
     rr.buf = nullptr; rr.kA = rr.kB = 0; rr.pos = 0;
     Pending pend;
     uint32_t mma_phase = 0;
+    LGP_INIT(t);
+    long long lgp_t = LGP_NOW();
     for (;;) {
         bool need = advance<GL, true>(g, p, t, st, rr, nullptr, pend);
         if (need) { // Game::features of the leaf, fp16, straight into the A tile (K-major UMMA layout, permuted K)
             for (int k = g.gl; k < 80; k += GL) {
                 int col = k >> 3, row = k & 7;
                 float f = (row < 7 && col < 9) ? c4::feature(pend.my, pend.op, row * 9 + col) : 0.0f;
-                *reinterpret_cast<__half*>(ms.a0 + mlptc::a_off(row_of_grp, k)) = __float2half_rn(f);
+                *reinterpret_cast<__half*>(ms.a + mlptc::a_off(row_of_grp, k)) = __float2half_rn(f);
             }
         }
+        LGP_MARK(adv, lgp_t);
         if (!__syncthreads_or(need ? 1 : 0)) break;
+        LGP_MARK(wait, lgp_t);
         mlptc::forward<THREADS / 32>(ms, mma_phase, GPB / 4);
+        LGP_MARK(leaf, lgp_t);
+#ifdef SYN_LG_PROF
+        ++lgp.rounds;
+#endif
         if (need) {
             const float* y = ms.y[row];
             float logit = g.gl < 9 ? y[g.gl] : 0.0f;
@@ -449,10 +503,12 @@ __global__ void __launch_bounds__(THREADS, 1) selfplay_nn_tc_kernel(const __grid
             explore_finish(g, t, pend, false, logit, __fdiv_rn(e0, tot), __fdiv_rn(e1, tot), __fdiv_rn(e2, tot));
             after_eval(g, t, st);
         }
+        LGP_MARK(fin, lgp_t);
         // no trailing barrier needed: the next forward() starts with a CTA barrier before any MMA, and
-        // y / a0 are only rewritten after that barrier (a0 by this thread's own group, y by the epilogue)
+        // y / the A tile are only rewritten after that barrier (the tile row by this thread's own group, y by the epilogue)
     }
     flush_counters(g, p, t);
+    LGP_FLUSH(g, p, t);
     mlptc::teardown(ms);
 }
 
@@ -472,7 +528,7 @@ __global__ void __launch_bounds__(THREADS, 1) eval_tc_kernel(const uint8_t* __re
             uint32_t idx = base + r;
             float f = 0.0f;
             if (idx < n && row < 7 && col < 9) f = c4::feature(my_bb[idx], op_bb[idx], row * 9 + col);
-            *reinterpret_cast<__half*>(ms.a0 + mlptc::a_off(r, k)) = __float2half_rn(f);
+            *reinterpret_cast<__half*>(ms.a + mlptc::a_off(r, k)) = __float2half_rn(f);
         }
         mlptc::forward<THREADS / 32>(ms, mma_phase, 32);
         if (threadIdx.x < 128) {

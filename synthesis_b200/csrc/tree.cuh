@@ -35,7 +35,9 @@ enum Counter {
     CNT_EXPLORES = 0, CNT_LEAF_EVALS, CNT_ROWS, CNT_GAMES, CNT_TREES, CNT_NODES, CNT_SELECT_LEVELS,
     CNT_CHILDREN_SCANNED, CNT_EXPANSIONS, CNT_CHILDREN_CREATED, CNT_BACKPROP_LEVELS, CNT_ROLLOUT_PLIES, CNT_N,
     // per-warp phase clocks of the thread-per-game kernels (lane 0 of every warp; syn_engine_debug_counters)
-    DBG_T_ADVANCE = CNT_N, DBG_T_TEAMWAIT, DBG_T_MLP, DBG_T_FINISH, DBG_ROUNDS, DBG_LEAVES, DBG_T_TOTAL, CNT_ALL
+    DBG_T_ADVANCE = CNT_N, DBG_T_TEAMWAIT, DBG_T_MLP, DBG_T_FINISH, DBG_ROUNDS, DBG_LEAVES, DBG_T_TOTAL,
+    // finer clocks of the lane-group kernels in a -DSYN_LG_PROF build: select loop, expansion, end of move, backprop
+    DBG_X_SELECT, DBG_X_EXPAND, DBG_X_EOM, DBG_X_BACKPROP, CNT_ALL
 };
 
 
@@ -127,32 +129,90 @@ struct RolloutRng {
     }
 };
 
-// policies/rollout.rs:8-31 from a non-terminal leaf.  Uniform across the group.  Returns the
-// one-hot index (0 Lose, 1 Draw, 2 Win) for the leaf's player to move.
+// policies/rollout.rs:8-31 from a non-terminal leaf.  Returns the one-hot index (0 Lose, 1 Draw, 2 Win) for the leaf's
+// player to move; uniform across the group.
+//
+// A playout is a chain of dependent plies (~150 dependent instructions each for a lone warp), but the chain is only as long
+// as the SET of legal columns changes: while no column fills up, ply i's column is a function of stream word i alone
+// (gen_range(0..n) with the same n and the same legal set).  So the group plays a WINDOW of plies at once, lane i taking
+// word i of the stream: columns in parallel, the row of every stone from a ballot per column (stones before it in the
+// same column), each mover's board by a prefix-OR over the lanes of the same parity, won() for every ply in parallel.
+// The window ends after the first ply that fills a column (the legal set changes), before a rejected word (2^32 mod n
+// zone, rand 0.8 UniformInt), at the end of the buffered words, or at the first terminal ply — whichever comes first;
+// the plies before that point are exactly the sequential playout's, and so is the number of words consumed.
 template <int GL>
 __device__ __forceinline__ int rollout(const Grp<GL>& g, uint64_t my, uint64_t op, RolloutRng<GL>& rr, uint32_t& plies) {
-    uint32_t k = 0;
+    uint32_t k = 0; // plies played so far
     for (;;) {
-        uint64_t occ = my | op;
-        uint64_t legal = (~(occ >> 6)) & c4::ROW0; // bit 7c set <=> column c has room
-        uint32_t n = (uint32_t)__popcll(legal);
-        uint32_t zone = GEN_RANGE_ZONE[n];
-        uint32_t hi;
-        for (;;) {
-            uint32_t v = rr.next(g);
-            uint64_t m = (uint64_t)v * (uint64_t)n;
-            hi = (uint32_t)(m >> 32);
-            if ((uint32_t)m <= zone) break;
+        if ((rr.pos & (RolloutRng<GL>::WORDS - 1)) == 0u) rr.refill(g);
+        const uint64_t occ = my | op;
+        const uint64_t legal = (~(occ >> 6)) & c4::ROW0; // bit 7c set <=> column c has room
+        const uint32_t n = (uint32_t)__popcll(legal);
+        const uint32_t zone = GEN_RANGE_ZONE[n];
+        const uint32_t in_buf = RolloutRng<GL>::WORDS - (rr.pos & (RolloutRng<GL>::WORDS - 1));
+        const uint32_t w = in_buf < (uint32_t)GL ? in_buf : (uint32_t)GL; // lanes that hold a word
+        const bool has = (uint32_t)g.gl < w;
+        const uint32_t v = has ? rr.buf[(rr.pos + (uint32_t)g.gl) & (RolloutRng<GL>::WORDS - 1)] : 0u;
+        const uint64_t m = (uint64_t)v * (uint64_t)n;
+        const uint32_t hi = (uint32_t)(m >> 32);
+        const bool rejected = has && (uint32_t)m > zone;
+        const uint32_t rejm = g.ballot(rejected);
+        // the hi-th legal column, ascending
+        int col = 0;
+        {
+            uint32_t seen = 0;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const uint32_t bit = (uint32_t)(legal >> (7 * c)) & 1u;
+                if (bit && seen == hi) col = c;
+                seen += bit;
+            }
         }
-        for (uint32_t t = 0; t < hi; ++t) legal &= legal - 1; // hi-th legal column, ascending
-        int p7 = __ffsll((long long)legal) - 1;
-        uint64_t bit = (occ + (1ull << p7)) & (0x7full << p7);
-        uint64_t mover = my | bit;
-        my = op;
-        op = mover;
-        ++k;
-        if (c4::won(mover)) { plies += k; return (k & 1u) ? 2 : 0; }
-        if ((occ | bit) == c4::ALL) { plies += k; return 1; }
+        // stones of this window that land in my column before mine
+        uint32_t below = 0;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const uint32_t b = g.ballot(has && col == c);
+            if (col == c) below = b;
+        }
+        below = (uint32_t)__popc(below & ((1u << g.gl) - 1u));
+        const uint32_t row = (uint32_t)__popc((uint32_t)(occ >> (7 * col)) & 0x7fu) + below;
+        const bool overflow = has && row >= 7u;           // only possible after a ply of this window filled the column
+        const bool fills = has && row == 6u;              // the legal set changes after this ply
+        const uint32_t bad = g.ballot(rejected || overflow || !has);
+        const uint32_t first_bad = bad ? (uint32_t)__ffs(bad) - 1u : (uint32_t)GL;
+        const uint32_t fillm = g.ballot(fills) & ((first_bad >= 32u) ? 0xffffffffu : ((1u << first_bad) - 1u));
+        uint32_t end = first_bad;                          // plies 0..end-1 of the window are the sequential playout's
+        if (fillm) { const uint32_t f = (uint32_t)__ffs(fillm); if (f < end) end = f; }
+        // every mover's board after its ply: the mover's board at the start of the window | its stones so far
+        uint64_t x = (has && row < 7u) ? (1ull << (7 * col + (int)row)) : 0ull;
+#pragma unroll
+        for (int o = 2; o < GL; o <<= 1) {
+            const uint32_t lo = __shfl_up_sync(g.mask, (uint32_t)x, o, GL), hi32 = __shfl_up_sync(g.mask, (uint32_t)(x >> 32), o, GL);
+            if (g.gl >= o) x |= ((uint64_t)hi32 << 32) | lo;
+        }
+        x |= (g.gl & 1) ? op : my;
+        const bool in_win = (uint32_t)g.gl < end;
+        const bool win = in_win && c4::won(x);
+        const bool full = in_win && (uint32_t)__popcll(occ) + (uint32_t)g.gl + 1u == 63u;
+        const uint32_t term = g.ballot(win || full);
+        if (term) {
+            const int tl = __ffs(term) - 1;
+            const bool was_win = (g.ballot(win) >> tl) & 1u;
+            k += (uint32_t)tl + 1u;
+            rr.pos += (uint32_t)tl + 1u;
+            plies += k;
+            return was_win ? ((k & 1u) ? 2 : 0) : 1;
+        }
+        // no terminal ply in the window: take all of it (and the rejected word behind it, if that is what ended it)
+        if (end > 0u) {
+            const uint64_t last = g.shfl(x, (int)end - 1);                               // the board of the window's last mover
+            const uint64_t prev = end >= 2u ? g.shfl(x, (int)end - 2) : op;              // the other player's board
+            my = prev;
+            op = last;
+        }
+        k += end;
+        rr.pos += end + ((end == first_bad && end < w && ((rejm >> end) & 1u)) ? 1u : 0u);
     }
 }
 
@@ -179,7 +239,17 @@ struct Tree {
     int err;
     uint32_t fpu_pos, noise_pos; // words drawn from the per-game FPU / noise streams
     uint64_t fpu_seed, noise_seed;
+#ifdef SYN_LG_PROF
+    long long pt[4]; // cycles in {select loop, expansion, end of move, backprop}
+#endif
 };
+#ifdef SYN_LG_PROF
+#define LGP_NOW() clock64()
+#define LGP_ADD(t, i, since) ((t).pt[i] += clock64() - (since))
+#else
+#define LGP_NOW() 0ll
+#define LGP_ADD(t, i, since) ((void)(since))
+#endif
 
 struct Pending { // an expanded leaf waiting for Policy::eval
     uint32_t leaf, first_child, legal; // legal = 9-bit column mask of the leaf's children
@@ -192,6 +262,7 @@ struct Pending { // an expanded leaf waiting for Policy::eval
 template <int GL>
 __device__ __forceinline__ void backprop(const Grp<GL>& g, Tree<GL>& t, int d, float v0, float v1, float v2, bool solved) {
     const syn_mcts_cfg& cfg = *t.cfg;
+    const long long lgp_bp = LGP_NOW();
     g.sync();
     t.cnt[CNT_BACKPROP_LEVELS] += (uint32_t)(d + 1);
     // serial part: only while the solver may still mark nodes
@@ -229,7 +300,7 @@ __device__ __forceinline__ void backprop(const Grp<GL>& g, Tree<GL>& t, int d, f
         }
         s.y += v0; s.z += v1; s.w += v2; s.x += 1.0f;
         if (g.gl == 0) t.stat[id] = s;
-        if (d == 0) { g.sync(); return; }
+        if (d == 0) { g.sync(); LGP_ADD(t, 3, lgp_bp); return; }
         float tmp = v0; v0 = v2; v2 = tmp;
         --d;
         g.sync(); // the parent's scan must see this node's new solution
@@ -246,6 +317,7 @@ __device__ __forceinline__ void backprop(const Grp<GL>& g, Tree<GL>& t, int d, f
         t.stat[id] = s;
     }
     g.sync();
+    LGP_ADD(t, 3, lgp_bp);
 }
 
 // Normal FPU for the unvisited children of one parent, in child order (mcts.rs:351-355 with
@@ -283,10 +355,12 @@ __device__ __forceinline__ bool explore_descend(const Grp<GL>& g, Tree<GL>& t, u
     uint32_t cfc = m.y, cpk = m.w;
     float cvis = s.x, cop0 = s.y, cop2 = s.w;
     if (g.gl == 0) t.path[0] = 0u;
+    const long long lgp_sel = LGP_NOW();
     for (;;) {
         uint32_t sol = (cpk >> 8) & 0xffu, nch = cpk & 0xffu;
         if (sol) { // mcts.rs:314-316
             int idx = sol_index(sol);
+            LGP_ADD(t, 0, lgp_sel);
             backprop(g, t, d, idx == 0 ? 1.0f : 0.0f, idx == 1 ? 1.0f : 0.0f, idx == 2 ? 1.0f : 0.0f, true);
             return false;
         }
@@ -300,6 +374,8 @@ __device__ __forceinline__ bool explore_descend(const Grp<GL>& g, Tree<GL>& t, u
             cm = t.meta[cfc + g.gl];
         }
         uint32_t csol = (cm.w >> 8) & 0xffu, cn = cm.w & 0xffu;
+        // (every lane prefetching ITS child's family into L2 before the winner is known was measured: select +1-10 % slower —
+        // at these batch sizes the descent waits for its own instruction chain, not for DRAM; profiles/r2_lane_group_clocks.txt)
         bool unvisited = act && csol == 0u && cn == 0u;
         float q;
         if (csol) {
@@ -349,6 +425,8 @@ __device__ __forceinline__ bool explore_descend(const Grp<GL>& g, Tree<GL>& t, u
         if (g.gl == 0) t.path[d] = cur;
     }
     // ---- visit (mcts.rs:374-406): push the children of `cur`; auto-extend through only-children
+    LGP_ADD(t, 0, lgp_sel);
+    const long long lgp_exp = LGP_NOW();
     for (;;) {
         uint64_t occ = my | op;
         int col = g.gl;
@@ -392,12 +470,14 @@ __device__ __forceinline__ bool explore_descend(const Grp<GL>& g, Tree<GL>& t, u
             if (g.gl == 0) t.path[d] = cur;
             if (osol) { // visit() of a solved node returns its one-hot (mcts.rs:377-379)
                 int idx = sol_index(osol);
+                LGP_ADD(t, 1, lgp_exp);
                 backprop(g, t, d, idx == 0 ? 1.0f : 0.0f, idx == 1 ? 1.0f : 0.0f, idx == 2 ? 1.0f : 0.0f, true);
                 return false;
             }
             continue;
         }
         p.leaf = cur; p.first_child = fc; p.legal = lm; p.depth = d; p.any_solved = any_solved; p.my = my; p.op = op;
+        LGP_ADD(t, 1, lgp_exp);
         return true;
     }
 }

@@ -119,9 +119,9 @@ class Engine:
 
     def debug_counters(self):
         """Per-warp phase clocks of the last thread-per-game launch (profiling aid)."""
-        out = np.zeros(7, np.uint64)
-        L.check(self._lib.syn_engine_debug_counters(self._h, _ptr(out), 7))
-        names = ("t_advance", "t_teamwait", "t_mlp", "t_finish", "rounds", "leaves", "t_total")
+        out = np.zeros(11, np.uint64)
+        L.check(self._lib.syn_engine_debug_counters(self._h, _ptr(out), 11))
+        names = ("t_advance", "t_teamwait", "t_mlp", "t_finish", "rounds", "leaves", "t_total", "x_select", "x_expand", "x_eom", "x_backprop")
         return {k: int(v) for k, v in zip(names, out)}
 
     def launch_geometry(self, num_games: int, leaf_eval_kind: int):
