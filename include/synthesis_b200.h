@@ -328,9 +328,9 @@ int syn_engine_gather_experience(syn_engine* e, syn_comm* c, int root, const syn
 int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, float* child_visits /*[cap][9]*/);
 
 /* Lanes per game: 0 (default) = chosen per launch from the games in flight — a lane group per game (32 lanes up to 2,368 games,
- * 16 up to 4,736 with network leaves; 32 up to 4,736 with rollout leaves: children scored in parallel, the shortest time per
- * explore) and a thread per game beyond (128 games = one tensor-core tile of leaves: the highest throughput); 1, 16, 32 force a
- * mapping.  The SYN_GROUP_LANES environment variable sets the default at syn_engine_create.  With rollout leaves 1 is a thread
+ * 16 up to 4,736 with network leaves in either tensor-core chain; 32 up to 4,736 with rollout leaves: children scored and
+ * playouts played in parallel, the shortest time per explore) and a thread per game beyond (128 games = one tensor-core tile
+ * of leaves: the highest throughput); 1, 16, 32 force a mapping.  The SYN_GROUP_LANES environment variable sets the default at syn_engine_create.  With rollout leaves 1 is a thread
  * per game too (the thread plays the rollout itself; SYN_ROLLOUT_THREADS = 512 / 640 / 768 / 896 / 1024 games per CTA, default
  * 1024).  Results do not depend on any of these. */
 int syn_engine_set_group_lanes(syn_engine* e, int lanes);
@@ -350,8 +350,8 @@ int syn_engine_launch_geometry(syn_engine* e, uint32_t num_games, uint32_t leaf_
  *   2 = tcgen05 tensor cores, split-fp16 operands (x = hi + lo, three MMAs per K-step), fp32 accumulate, activations in
  *       tensor memory: agrees with an fp32 forward to ~1e-7 at any weight scale;
  *   1 = tcgen05 tensor cores, single fp16 operands (11-bit significands), fp32 accumulate: ~4e-5 at initialisation scale,
- *       several 1e-3 at trained scale.  Matches between two DIFFERENT networks (syn_engine_set_opponent_weights) and the
- *       lane-group kernels always run this chain (two split weight images do not fit one SM);
+ *       several 1e-3 at trained scale.  Matches between two DIFFERENT networks (syn_engine_set_opponent_weights) always
+ *       run this chain (two pairs of split weight images do not fit one SM);
  *   0 = fp32 CUDA-core kernel (kept as the device-side numerical reference).
  * SYN_MLP=fp32|fp16|split overrides the default at syn_engine_create.  syn_engine_mlp_in_use reports the chain the next
  * launch will use (0, 1 or 2) and, in auto mode, the measured error of the fast chain in units of the tolerance (-1 if

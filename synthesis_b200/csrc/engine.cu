@@ -303,13 +303,13 @@ constexpr int NN_TC_THREADS = SYN_NN_TC_THREADS; // CTA-wide lane-group kernel (
 // flight the time of an explore is what matters: a lane group per game scores a node's children in parallel and reads a family
 // with one instruction (tree.cuh), and wins below ~5 k games (profiles/r2_small_batches.txt: 4,096 network games 134 M explores/s
 // against 95 M thread-per-game; 256 rollout games 17 M against 9 M).  With many games the thread-per-game kernels win by
-// keeping every lane busy (1.37 G against 0.1-0.3 G).  The lane-group network kernels carry the single-fp16 chain only.
+// keeping every lane busy (1.37 G against 0.1-0.3 G).  The team kernels (selfplay_team.cuh) carry both tensor-core chains.
 static int pick_group_lanes(const syn_engine* e, const KParams& kp) {
     if (e->group_lanes != 0) return e->group_lanes;
     const bool nn = kp.cfg.leaf_eval_kind == SYN_LEAF_NN;
     const uint32_t want = kp.num_games < e->req_games ? kp.num_games : e->req_games;
     if (nn) {
-        if (e->mlp_eff != 1) return 1;                        // fp32-grade (or fp32 CUDA-core) leaves: thread per game
+        if (e->mlp_eff == 0 || (e->mlp_eff == 2 && e->lg_teams == 0)) return 1; // no lane-group kernel carries this chain: thread per game
         if (want <= (uint32_t)e->sm_count * 16u) return 32;    // one wave of warps: 2,368 games
         if (want <= (uint32_t)e->sm_count * 32u) return 16;    // one wave of half warps: 4,736 games
         return 1;
@@ -326,7 +326,8 @@ static bool lg_geometry(const syn_engine* e, const KParams& kp, int lanes, LgGeo
     G.tc = nn && e->mlp_eff != 0;
     // tensor-core network leaves: 256-thread CTAs, two per SM (107 KB of shared memory each) — their rounds interleave and
     // half as many groups share a CTA barrier; fp32 network leaves: one 512-thread CTA per SM (120 KB of fp32 weights)
-    G.threads = G.tc ? (e->lg_teams ? 128 * e->lg_teams : NN_TC_THREADS) : nn ? NN_THREADS : ROLLOUT_THREADS;
+    const int teams = e->mlp_eff == 2 ? 4 : e->lg_teams; // the split chain is instantiated for four teams
+    G.threads = G.tc ? (e->lg_teams ? 128 * teams : NN_TC_THREADS) : nn ? NN_THREADS : ROLLOUT_THREADS;
     G.gpb = G.threads / G.gl;
     const uint32_t max_blocks = e->max_games / (uint32_t)G.gpb;
     if (max_blocks == 0) return false;
@@ -412,7 +413,17 @@ static int launch_selfplay(syn_engine* e, KParams& kp) {
     kp.seats_q = G.seats_q;
     kp.seats_rem = G.seats_rem;
     CUDA_TRY(cudaMemsetAsync(e->next_game.p, 0, sizeof(unsigned int), e->stream));
-    if (tc && e->lg_teams) { // teams of four warps with their own tile and barrier (selfplay_team.cuh)
+    if (tc && e->lg_teams && e->mlp_eff == 2) { // teams of four warps, split-fp16 chain (fp32-grade leaves)
+        if (gl == 32) {
+            const size_t smem = nn_team_split_smem_bytes<4, 32>();
+            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_team_split_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            selfplay_nn_team_split_kernel<32, 4><<<blocks, threads, smem, e->stream>>>(kp);
+        } else {
+            const size_t smem = nn_team_split_smem_bytes<4, 16>();
+            CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_team_split_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            selfplay_nn_team_split_kernel<16, 4><<<blocks, threads, smem, e->stream>>>(kp);
+        }
+    } else if (tc && e->lg_teams) { // teams of four warps with their own barrier and MLP slot, one shared tile (selfplay_team.cuh)
 #define SYN_LAUNCH_TEAM(GLv, Tv)                                                                                                        \
     do {                                                                                                                                \
         const size_t smem = nn_team_smem_bytes<Tv, 4, GLv>();                                                                           \
@@ -1070,7 +1081,7 @@ int syn_engine_broadcast_weights(syn_engine* e, syn_comm* c, const float* blob, 
     CUDA_TRY(cudaMemcpyAsync(e->bias_host, e->weight_image.p + mlptc::BIAS_OFF, sizeof(e->bias_host), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->has_weights = true;
-    return SYN_OK;
+    return calibrate_mlp(e); // every rank measures the same weights on the same positions, so every rank picks the same chain
 }
 
 int syn_engine_gather_experience(syn_engine* e, syn_comm* c, int root, const syn_rollout_cfg* cfg, uint64_t first_game_index, uint32_t num_games,

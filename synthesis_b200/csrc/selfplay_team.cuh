@@ -11,6 +11,7 @@
 // lane), the lane whose thread index in the team equals that row runs the row's epilogue like a tpg2 thread does, and
 // hands the 12 outputs to the group by shuffles.
 #pragma once
+#include "mlp_split.cuh"
 #include "mlp_team.cuh"
 #include "selfplay.cuh"
 
@@ -230,6 +231,80 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_team_kernel(const 
     flush_counters(g, p, t);
     LGP_FLUSH(g, p, t);
     lgteam::teardown<TEAMS, SLOTS>(ms);
+}
+
+// The same schedule with the split-fp16 chain (mlp_split.cuh: x = hi + lo operands, three MMAs per K-step, activations in
+// tensor memory — fp32-grade outputs, what the engine selects for weights that the single-fp16 chain cannot carry).
+// Activations never touch shared memory here, so there is no tile to share: every lane of a group puts the group's leaf on
+// ITS OWN tile row (the rows of a group are copies), runs its row's epilogue in lockstep with the others, and ends up
+// holding all 12 outputs — no hand-over by shuffles.  Four teams take turns on two slots of 256 TMEM columns.
+template <int TEAMS, int GL>
+constexpr size_t nn_team_split_smem_bytes() { return sizeof(mlps::Smem<TEAMS, 2>) + (size_t)(128 * TEAMS / GL) * 64 * sizeof(uint32_t); }
+
+template <int GL, int TEAMS>
+__global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_team_split_kernel(const __grid_constant__ KParams p) {
+    constexpr int SLOTS = 2;
+    constexpr int GPT = 128 / GL, GPB = GPT * TEAMS;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    mlps::Smem<TEAMS, SLOTS>& ms = *reinterpret_cast<mlps::Smem<TEAMS, SLOTS>*>(smem_raw);
+    uint32_t* s_path = reinterpret_cast<uint32_t*>(smem_raw + sizeof(mlps::Smem<TEAMS, SLOTS>));
+    mlps::setup<TEAMS, SLOTS>(ms, p.weight_image, p.weight_image_lo);
+
+    Grp<GL> g;
+    const int team = threadIdx.x >> 7, r = threadIdx.x & 127;
+    const int gt = r / GL;
+    const int seat = gt * TEAMS + team;
+    const size_t slot_id = (size_t)blockIdx.x * GPB + (size_t)seat;
+    Tree<GL> t;
+    t.stat.base = t.meta.base = p.nodes + 2 * slot_id * p.arena_nodes;
+    t.path = s_path + (team * GPT + gt) * 64;
+    t.cap = p.arena_nodes;
+    t.cfg = &p.cfg.mcts;
+    t.err = 0;
+    t.nn = 1;
+#pragma unroll
+    for (int i = 0; i < CNT_N; ++i) t.cnt[i] = 0u;
+    GroupState<GL, true> st;
+    st.phase = lg_seated(p, seat) ? PH_NEED_GAME : PH_DONE;
+    st.is_init = false;
+    RolloutRng<GL> rr;
+    rr.buf = nullptr; rr.kA = rr.kB = 0; rr.pos = 0;
+    Pending pend;
+    pend.my = pend.op = 0ull;
+    LGP_INIT(t);
+    long long lgp_t = LGP_NOW();
+    for (;;) {
+        const bool need = advance<GL, true>(g, p, t, st, rr, nullptr, pend);
+        LGP_MARK(adv, lgp_t);
+        if (!mlps::team_any(team, need)) break;
+        uint32_t mma_phase;
+        const int slot = mlps::acquire_slot<TEAMS, SLOTS>(ms, team, r, mma_phase);
+        LGP_MARK(wait, lgp_t);
+        mlps::write_features<TEAMS, SLOTS>(ms, slot, r, pend.my, pend.op, need);
+        float y[12];
+        mlps::forward<TEAMS, SLOTS>(ms, p.mlp_bias, team, slot, r, mma_phase, y);
+        mlps::release_slot<TEAMS, SLOTS>(ms, team, r, slot, mma_phase);
+        LGP_MARK(leaf, lgp_t);
+#ifdef SYN_LG_PROF
+        ++lgp.rounds;
+#endif
+        if (need) {
+            float logit = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (g.gl == j) logit = y[j];
+            // value.softmax(-1) (study-connect4/src/policies.rs:54-56)
+            const float m = fmaxf(y[9], fmaxf(y[10], y[11]));
+            const float e0 = syn_expf(__fsub_rn(y[9], m)), e1 = syn_expf(__fsub_rn(y[10], m)), e2 = syn_expf(__fsub_rn(y[11], m));
+            const float tot = __fadd_rn(__fadd_rn(e0, e1), e2);
+            explore_finish(g, t, pend, false, logit, __fdiv_rn(e0, tot), __fdiv_rn(e1, tot), __fdiv_rn(e2, tot));
+            after_eval(g, t, st);
+        }
+        LGP_MARK(fin, lgp_t);
+    }
+    flush_counters(g, p, t);
+    LGP_FLUSH(g, p, t);
+    mlps::teardown<TEAMS, SLOTS>(ms);
 }
 
 } // namespace eng

@@ -205,15 +205,17 @@ def test_gather_stop_games_when_solved(engine, oracle):
     assert_rows_equal(a, ra, "experience")
 
 
-@pytest.mark.parametrize("leaf", ["rollout", "nn"])
+@pytest.mark.parametrize("leaf", ["rollout", "nn", "nn_split"])
 def test_group_lanes_do_not_change_results(engine, leaf):
     """Thread-per-game (1), half-warp-per-game (16) and warp-per-game (32) are three schedules of the
-    same serial per-tree algorithm: experience and visit counts must be identical bit for bit."""
+    same serial per-tree algorithm: experience and visit counts must be identical bit for bit — with rollout leaves and
+    with network leaves in either tensor-core chain (single fp16: tpg2 / selfplay_nn_team_kernel; split fp16: tpg2s /
+    selfplay_nn_team_split_kernel)."""
     cfg = s.study_connect4_rollout_cfg(num_explores=100)
     kind = L.LEAF_ROLLOUT if leaf == "rollout" else L.LEAF_NN
-    if leaf == "nn":
+    if leaf != "rollout":
         engine.set_weights(s.Connect4Net.new(3).blob())
-        engine.set_mlp_mode(1)  # the lane-group kernels carry the single-fp16 chain only: compare the three mappings on that one
+        engine.set_mlp_mode(1 if leaf == "nn" else 2)
     res = {}
     try:
         for gl in (32, 16, 1):
@@ -978,7 +980,7 @@ def _two_rank_worker(rank, world, id_bytes, q):
             e.broadcast_weights(comm, blob, root=0)
             w = e.get_weights()
             merged, st = D.gather_experience_distributed(e, comm, cfg, L.LEAF_NN, 301, 5, None, 0, root=0, first_game_index=11)
-            out = dict(wsum=float(np.abs(w).sum()), explores=st["explores"])
+            out = dict(wsum=float(np.abs(w).sum()), explores=st["explores"], chain=e.mlp_in_use()[0])
             if rank == 0:
                 out["merged"] = {k: v.copy() for k, v in merged.items()}
         comm.close()
@@ -1014,6 +1016,8 @@ def test_two_gpus_concatenated_shards_equal_one_gpu(engine):
     assert res[0]["wsum"] == res[1]["wsum"] == float(np.abs(blob).sum())  # the broadcast reached rank 1
     cfg = s.study_connect4_rollout_cfg(num_explores=80, sample_actions_until=12)
     engine.set_weights(blob)
+    # a broadcast measures the forward chains like set_weights does: every rank picks what one GPU picks
+    assert res[0]["chain"] == res[1]["chain"] == engine.mlp_in_use()[0] == 1
     whole, st, _ = engine.gather(cfg, L.LEAF_NN, 11, 301, 5)
     assert_rows_equal(res[0]["merged"], whole, "two GPUs vs one")
     assert res[0]["explores"] + res[1]["explores"] == st["explores"]
@@ -1097,23 +1101,29 @@ def test_a_thousand_games_occupy_every_sm():
         assert e.launch_geometry(1000, L.LEAF_NN)[2] == 32 and e.launch_geometry(4096, L.LEAF_NN)[2] == 16
         assert e.launch_geometry(256, L.LEAF_ROLLOUT)[2] == 32 and e.launch_geometry(4096, L.LEAF_ROLLOUT)[2] == 32
         assert e.launch_geometry(148 * 640, L.LEAF_NN)[2] == 1 and e.launch_geometry(20000, L.LEAF_ROLLOUT)[2] == 1
-        e.set_mlp_mode(2)  # fp32-grade leaves exist in the thread-per-game kernels only
+        e.set_mlp_mode(2)  # fp32-grade leaves: the team kernels carry the split chain too
+        assert e.launch_geometry(1000, L.LEAF_NN)[2] == 32 and e.launch_geometry(148 * 640, L.LEAF_NN)[2] == 1
+        e.set_mlp_mode(0)  # the fp32 CUDA-core forward has no small-batch mapping of its own: thread per game's seating
         assert e.launch_geometry(1000, L.LEAF_NN)[2] == 1
+        # a lane-group launch is dealt over all SMs too: 1,000 games are 148 CTAs of at most 7 groups
+        e.set_mlp_mode(1)
+        ctas, per, lanes = e.launch_geometry(1000, L.LEAF_NN)
+        assert (ctas, per, lanes) == (sms, 7, 32)
 
 
-@pytest.mark.parametrize("leaf", ["nn", "rollout"])
+@pytest.mark.parametrize("leaf", ["nn", "nn_split", "rollout"])
 @pytest.mark.parametrize("games", [100, 3000, 12000])
 def test_mapping_chosen_per_launch_does_not_change_results(leaf, games):
     """The default engine picks the mapping per launch (32 lanes, 16 lanes or a thread per game by the games in flight); whatever
     it picks, rows, per-move visit counts and counters equal the thread-per-game kernels'."""
     cfg = s.study_connect4_rollout_cfg(num_explores=40, sample_actions_until=12)
-    kind = L.LEAF_NN if leaf == "nn" else L.LEAF_ROLLOUT
+    kind = L.LEAF_ROLLOUT if leaf == "rollout" else L.LEAF_NN
     blob = s.Connect4Net.new(5).blob()
 
     def run(lanes):
         with s.Engine(0, 148 * 640, 40) as e:
             e.set_weights(blob)
-            e.set_mlp_mode(1)  # the chain every mapping carries
+            e.set_mlp_mode(2 if leaf == "nn_split" else 1)  # a pinned chain: auto could choose differently per weights, never per mapping
             e.set_group_lanes(lanes)
             return e.gather(cfg, kind, 2, games, 6, trace=True)
     a, b = run(0), run(1)
