@@ -450,13 +450,17 @@ def run_ours(args):
             _, st = eng.gather_experience(comm, cfg, leaf, first, games, seed, root=0, exp=exp)
         return st, h2d + st["h2d_bytes"], st["d2h_bytes"], int(exp.len) if exp is not None else 0
 
-    e2e_step(2000)
+    for w in range(max(1, min(args.warmup, 2))):  # untimed: the host-buffer path sizes its staging on the first calls
+        e2e_step(2000 + w)
     barrier()
     t0 = time.perf_counter()
     e_expl = e_h2d = e_d2h = 0
     for k in range(args.steps):
+        t_k = time.perf_counter()
         st, h2d, d2h, _ = e2e_step(k)
         e_expl += st["explores"]; e_h2d += h2d; e_d2h += d2h
+        if os.environ.get("SYN_BENCH_TRACE") and rank == 0:
+            print("e2e step %d: %.1f ms wall, %.1f ms device" % (k, 1e3 * (time.perf_counter() - t_k), st["device_ns"] * 1e-6), file=sys.stderr)
     barrier()
     e_wall = reduce(time.perf_counter() - t0, "MAX")
     e_value = reduce(e_expl, "SUM") / e_wall

@@ -271,7 +271,7 @@ typedef struct {
     float weight_decay;   /* LearningConfig::weight_decay */
     float policy_weight;  /* LearningConfig::policy_weight */
     float value_weight;   /* LearningConfig::value_weight */
-    uint32_t batch_size;  /* LearningConfig::batch_size; the device learner supports 32 */
+    uint32_t batch_size;  /* LearningConfig::batch_size (config.rs:76-94): a multiple of 32 up to 4096; larger than 32 = gradients summed over micro-batches of 32 */
 } syn_train_cfg;
 
 /* Replaces the batch loop of alpha_zero (alpha_zero.rs:73-92): n_batches optimizer steps on the engine's CURRENT
@@ -327,12 +327,13 @@ int syn_engine_gather_experience(syn_engine* e, syn_comm* c, int root, const syn
  * it is what the parity tests compare ("bit-exact visit counts"). */
 int syn_engine_set_trace(syn_engine* e, uint8_t* action, uint32_t* tree_nodes, float* child_visits /*[cap][9]*/);
 
-/* Lanes per game: 0 (default) = chosen per launch from the games in flight — a lane group per game (32 lanes up to 2,368 games,
- * 16 up to 4,736 with network leaves in either tensor-core chain; 32 up to 4,736 with rollout leaves: children scored and
- * playouts played in parallel, the shortest time per explore) and a thread per game beyond (128 games = one tensor-core tile
- * of leaves: the highest throughput); 1, 16, 32 force a mapping.  The SYN_GROUP_LANES environment variable sets the default at syn_engine_create.  With rollout leaves 1 is a thread
- * per game too (the thread plays the rollout itself; SYN_ROLLOUT_THREADS = 512 / 640 / 768 / 896 / 1024 games per CTA, default
- * 1024).  Results do not depend on any of these. */
+/* Lanes per game: 0 (default) = chosen per launch from the games in flight at the measured crossovers — a lane group per
+ * game (network leaves: 32 lanes up to 2,368 games, 16 up to ~11,000; rollout leaves: 32 up to 40,000: children scored and
+ * playouts played in parallel, the shortest time per explore; seats are refilled as games end) and a thread per game beyond
+ * (128 games = one tensor-core tile of leaves: the highest throughput); 1, 16, 32 force a mapping.  The SYN_GROUP_LANES
+ * environment variable sets the default at syn_engine_create.  With rollout leaves 1 is a thread per game too (the thread
+ * plays the rollout itself; SYN_ROLLOUT_THREADS = 512 / 640 / 768 / 896 / 1024 games per CTA, default 1024).  Results do not
+ * depend on any of these. */
 int syn_engine_set_group_lanes(syn_engine* e, int lanes);
 
 /* How the thread-per-game kernels would seat a gather of num_games games on this engine: persistent CTAs launched and the

@@ -53,13 +53,19 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    // The first allocation is exact (the arenas are sized by the caller); a buffer that has to GROW takes half as much again, so
+    // that a sequence of slightly larger requests (the rows of a gather vary by a few percent from seed to seed) does not free
+    // and allocate device memory call after call — each such pair synchronises the device and showed up as 0.4-1.1 s stalls in
+    // the end-to-end leg of a 0.2 s workload.
     cudaError_t reserve(size_t want) {
         if (want <= n) return cudaSuccess;
+        size_t cap = p ? (want > n + n / 2 ? want : n + n / 2) : want;
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
-        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
-        if (e == cudaSuccess) n = want;
+        cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
+        if (e != cudaSuccess && cap != want) { cap = want; e = cudaMalloc(&p, cap * sizeof(T)); }
+        if (e == cudaSuccess) n = cap;
         return e;
     }
     void release() {
@@ -300,10 +306,9 @@ constexpr int NN_THREADS = 512;
 constexpr int NN_TC_THREADS = SYN_NN_TC_THREADS; // CTA-wide lane-group kernel (SYN_LG_TEAMS=0): 512 = one CTA per SM (faster: profiles/r2_lane_group_clocks.txt), 256 = two
 
 // Which mapping a launch uses when the caller has not forced one.  A tree is a strictly serial object, so with FEW games in
-// flight the time of an explore is what matters: a lane group per game scores a node's children in parallel and reads a family
-// with one instruction (tree.cuh), and wins below ~5 k games (profiles/r2_small_batches.txt: 4,096 network games 134 M explores/s
-// against 95 M thread-per-game; 256 rollout games 17 M against 9 M).  With many games the thread-per-game kernels win by
-// keeping every lane busy (1.37 G against 0.1-0.3 G).  The team kernels (selfplay_team.cuh) carry both tensor-core chains.
+// flight the time of one explore is what matters: a lane group per game scores a node's children in parallel, plays a
+// playout's plies in parallel windows and reads a family with one instruction (tree.cuh, selfplay_team.cuh).  With many games
+// the thread-per-game kernels win by keeping every lane busy.  The thresholds below are the measured crossovers.
 static int pick_group_lanes(const syn_engine* e, const KParams& kp) {
     if (e->group_lanes != 0) return e->group_lanes;
     const bool nn = kp.cfg.leaf_eval_kind == SYN_LEAF_NN;
@@ -311,10 +316,14 @@ static int pick_group_lanes(const syn_engine* e, const KParams& kp) {
     if (nn) {
         if (e->mlp_eff == 0 || (e->mlp_eff == 2 && e->lg_teams == 0)) return 1; // no lane-group kernel carries this chain: thread per game
         if (want <= (uint32_t)e->sm_count * 16u) return 32;    // one wave of warps: 2,368 games
-        if (want <= (uint32_t)e->sm_count * 32u) return 16;    // one wave of half warps: 4,736 games
+        // half warps: 4,736 seats, refilled as games end.  Single-fp16 chain: ahead of a thread per game up to ~11 k games
+        // (6,000: 193 vs 139 M explores/s, 10,000: 220 vs 208, 16,000: 247 vs 307); split chain: level at 4,096 (125 vs 124)
+        if (want <= (e->mlp_eff == 1 ? 11000u : (uint32_t)e->sm_count * 32u)) return 16;
         return 1;
     }
-    if (want <= (uint32_t)e->sm_count * 32u) return 32;
+    // rollout leaves: 9,472 seats of 32 lanes, refilled; ahead up to ~45 k games (9,000: 354 vs 158 M explores/s, 20,000: 437 vs 256,
+    // 40,000: 467 vs 410), then a thread per game takes over on its way to 1.2 G at 151,552 (profiles/r2_lane_group_clocks.txt)
+    if (want <= 40000u) return 32;
     return 1;
 }
 
@@ -971,7 +980,7 @@ int syn_engine_gather_wait(syn_engine* e, syn_experience* out, syn_stats* stats)
         for (auto& x : f) {
             if (x.dst && !is_device_ptr(x.dst)) { x.off = need; need += ((x.elt * total + 255) / 256) * 256; }
         }
-        CUDA_TRY(e->staging.reserve(need ? need : 256));
+        CUDA_TRY(e->staging.reserve(need ? need + need / 4 : 256)); // headroom: the next seed's gather has a few percent more rows
         auto target = [&](int i) -> void* {
             if (!f[i].dst) return nullptr;
             return is_device_ptr(f[i].dst) ? f[i].dst : (void*)(e->staging.p + f[i].off);
@@ -1543,8 +1552,17 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
     if (!e || !cfg) return fail(SYN_ERR_INVALID_ARGUMENT, "NULL argument");
     if (e->pending) return fail(SYN_ERR_INVALID_ARGUMENT, "a gather is in flight on this engine");
     if (!e->has_weights) return fail(SYN_ERR_NO_WEIGHTS, "syn_engine_set_weights has not been called");
-    if (cfg->batch_size != (uint32_t)trn::B)
-        return fail(SYN_ERR_UNSUPPORTED, "batch_size %u: the device learner is built for batches of %d (study-connect4/src/main.rs:21)", cfg->batch_size, trn::B);
+    // SYN_TRAIN_CLUSTER: 0 = the single-CTA kernel (train.cuh); 1 = a cluster of 8 CTAs exchanging through cluster.sync();
+    // 2 (default) = the cluster with asynchronous remote stores and mbarriers (train_cluster.cuh)
+    const char* tc = std::getenv("SYN_TRAIN_CLUSTER");
+    const int mode = tc ? std::atoi(tc) : 2;
+    // LearningConfig::batch_size is free in the reference (config.rs:76-94; 32 in study-connect4/src/main.rs:21).  The kernels
+    // are tiled for 32 rows; a multiple of 32 runs as micro-batches whose gradients are summed before the Adam update.
+    if (cfg->batch_size == 0 || cfg->batch_size % (uint32_t)trn::B != 0 || cfg->batch_size > 4096u)
+        return fail(SYN_ERR_UNSUPPORTED, "batch_size %u: the device learner takes multiples of %d up to 4096 (study-connect4/src/main.rs:21 uses 32)", cfg->batch_size, trn::B);
+    const uint32_t micro = cfg->batch_size / (uint32_t)trn::B;
+    if (micro > 1 && mode != 2) return fail(SYN_ERR_UNSUPPORTED, "batch_size %u needs the default learner kernel (SYN_TRAIN_CLUSTER=2)", cfg->batch_size);
+    if ((uint64_t)n_batches * micro > 0xffffffffull) return fail(SYN_ERR_CAPACITY, "too many batches");
     if (!(cfg->beta1 >= 0.0f && cfg->beta1 < 1.0f && cfg->beta2 >= 0.0f && cfg->beta2 < 1.0f && cfg->eps > 0.0f && cfg->lr >= 0.0f))
         return fail(SYN_ERR_INVALID_ARGUMENT, "bad Adam hyper-parameters");
     if (stats) std::memset(stats, 0, sizeof(*stats));
@@ -1559,7 +1577,7 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
     }
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     const void* src[5] = {my_bb, op_bb, pis, vs, batch_index};
-    const size_t bytes[5] = {8 * n_rows, 8 * n_rows, 36 * n_rows, 12 * n_rows, (size_t)n_batches * trn::B * 4};
+    const size_t bytes[5] = {8 * n_rows, 8 * n_rows, 36 * n_rows, 12 * n_rows, (size_t)n_batches * cfg->batch_size * 4};
     size_t off[5], io = 0;
     for (int i = 0; i < 5; ++i) { off[i] = io; if (!is_device_ptr(src[i])) io += al(bytes[i]); }
     const size_t o_sched = io; io += al((size_t)n_batches * sizeof(float2));
@@ -1589,12 +1607,8 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
     tp.losses = (float*)(e->tr_io.p + o_loss); tp.error = e->error.p;
     const char* tprof = std::getenv("SYN_TRAIN_PROF"); // per-phase clocks of the async cluster kernel, printed to stderr
     tp.prof = (tprof && std::atoi(tprof) == 1) ? (unsigned long long*)e->counters.p : nullptr;
-    tp.n_rows = (uint32_t)n_rows; tp.n_steps = n_batches;
+    tp.n_rows = (uint32_t)n_rows; tp.n_steps = n_batches; tp.micro = micro;
     tp.beta1 = cfg->beta1; tp.beta2 = cfg->beta2; tp.eps = cfg->eps; tp.wd = cfg->weight_decay; tp.pw = cfg->policy_weight; tp.vw = cfg->value_weight;
-    // SYN_TRAIN_CLUSTER: 0 = the single-CTA kernel (train.cuh); 1 = a cluster of 8 CTAs exchanging through cluster.sync();
-    // 2 (default) = the cluster with asynchronous remote stores and mbarriers (train_cluster.cuh)
-    const char* tc = std::getenv("SYN_TRAIN_CLUSTER");
-    const int mode = tc ? std::atoi(tc) : 2;
     if (mode == 2) CUDA_TRY(cudaFuncSetAttribute(trc::train_cluster_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trc::SmemA)));
     else if (mode == 1) CUDA_TRY(cudaFuncSetAttribute(trc::train_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trc::Smem)));
     else CUDA_TRY(cudaFuncSetAttribute(trn::train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trn::Smem)));
@@ -1623,13 +1637,13 @@ int syn_engine_train(syn_engine* e, const syn_train_cfg* cfg, const uint64_t* my
         CUDA_TRY(cudaMemcpy(pc, tp.prof, sizeof(pc), cudaMemcpyDeviceToHost));
         static const char* names[13] = {"stage", "fwd0", "fwd1", "fwd2", "fwd3", "fwd4", "loss", "bwd4", "bwd3", "bwd2", "bwd1", "bwd0", "endbar"};
         std::fprintf(stderr, "train phases (cycles/step, rank 0 thread 0):");
-        for (int k = 0; k < 13; ++k) std::fprintf(stderr, " %s %.0f", names[k], (double)pc[k] / n_batches);
+        for (int k = 0; k < 13; ++k) std::fprintf(stderr, " %s %.0f", names[k], (double)pc[k] / ((double)n_batches * micro));
         std::fprintf(stderr, "\n");
     }
     if (stats) {
         float ms = 0.0f;
         CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-        stats->rows = (uint64_t)n_batches * trn::B;
+        stats->rows = (uint64_t)n_batches * cfg->batch_size;
         stats->device_ns = (uint64_t)((double)ms * 1e6);
         stats->kernel_launches = e->launches;
         stats->h2d_bytes = e->h2d;

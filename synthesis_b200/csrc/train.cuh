@@ -58,12 +58,13 @@ struct Params {
     const uint64_t* op;
     const float* pis;          // [n][9]
     const float* vs;           // [n][3]
-    const uint32_t* batch_idx; // [n_steps][32] row indices
+    const uint32_t* batch_idx; // [n_steps][32 * micro] row indices
     const float2* sched;       // [n_steps] {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)}
     float* losses;             // [n_steps][2] {pi_loss, v_loss} or null
     int* error;
     unsigned long long* prof;  // optional [16]: cycles per phase of a step, summed over steps (rank 0, thread 0; SYN_TRAIN_PROF=1)
     uint32_t n_rows, n_steps;
+    uint32_t micro;            // micro-batches of 32 rows per optimizer step (batch_size / 32): gradients are accumulated over them
     float beta1, beta2, eps, wd, pw, vw;
 };
 

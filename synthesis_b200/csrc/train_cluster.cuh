@@ -36,7 +36,7 @@ constexpr int OWN_W = 16 * 68 + 12 * 132 + 8 * 100 + 6 * 68 + 2 * 52; // 3984
 constexpr int OWN_P = OWN_W + 48;                                    // + 44 biases, padded
 
 struct Smem {
-    float w[OWN_P], m[OWN_P], v[OWN_P];
+    float w[OWN_P], m[OWN_P], v[OWN_P], g[OWN_P]; // g: gradient sums of a batch larger than 32 rows (async kernel only)
     float act[trn::A_FLOATS]; // ALL activations of the batch (filled by every CTA's remote stores)
     float part[2][B * PS];    // partial input-deltas over the own rows, double-buffered by layer parity
     float d[B * DSL];         // delta of the own output slice of the current layer
@@ -125,9 +125,12 @@ __device__ __forceinline__ void backward_partial(Smem& s, unsigned rank) {
     }
 }
 
-// gradient of four weights of an own row (and of the row's bias), then Adam on them
+// gradient of four weights of an own row (and of the row's bias), then Adam on them.
+// accum: 0 = a batch of 32 rows (the gradient is complete); 1 = a micro-batch of a larger batch: add to s.g, no update;
+// 2 = its last micro-batch: add, update with the sum, clear s.g.  (loss = kl_div(sum) / batch_size, alpha_zero.rs:80-88: the
+// per-row deltas already carry 1 / batch_size, so the sum over micro-batches IS the batch gradient.)
 template <int L, class S>
-__device__ __forceinline__ void grad_and_adam(const trn::Params& p, S& s, float2 sc, unsigned rank) {
+__device__ __forceinline__ void grad_and_adam(const trn::Params& p, S& s, float2 sc, unsigned rank, int accum = 0) {
     constexpr Layer ly = LAYERS[L];
     constexpr int sl = Own<L>::sl, C4 = ly.kp / 4, AS = act_stride(L);
     static_assert(sl * C4 <= NT, "one tile per thread");
@@ -150,6 +153,20 @@ __device__ __forceinline__ void grad_and_adam(const trn::Params& p, S& s, float2
         for (int b = 0; b < B; ++b) gb += s.d[b * DSL + t];
     }
     __syncthreads(); // backward_partial<L> has read the weights this is about to change
+    if (accum != 0) { // the own tile's running sums live at the tile's own index: no other thread touches them
+        if (tile) {
+            const int idx = Own<L>::woff + ol * ly.ld + 4 * c;
+            const float4 pg = *reinterpret_cast<const float4*>(s.g + idx);
+            g.x += pg.x; g.y += pg.y; g.z += pg.z; g.w += pg.w;
+            *reinterpret_cast<float4*>(s.g + idx) = accum == 2 ? make_float4(0.f, 0.f, 0.f, 0.f) : g;
+        }
+        if (brow) {
+            const int bi = Own<L>::boff + t;
+            gb += s.g[bi];
+            s.g[bi] = accum == 2 ? 0.f : gb;
+        }
+        if (accum == 1) return;
+    }
     if (tile) {
         const int idx = Own<L>::woff + ol * ly.ld + 4 * c;
         float4 wv = *reinterpret_cast<float4*>(s.w + idx), mv = *reinterpret_cast<float4*>(s.m + idx), vv = *reinterpret_cast<float4*>(s.v + idx);
@@ -202,7 +219,7 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const int t = threadIdx.x, lane = t & 31;
-    for (int i = t; i < 3 * OWN_P; i += NT) s.w[i] = 0.0f; // w, m, v are adjacent
+    for (int i = t; i < 4 * OWN_P; i += NT) s.w[i] = 0.0f; // w, m, v, g are adjacent
     __syncthreads();
     sync_rows<0, true>(p, s, rank); sync_rows<1, true>(p, s, rank); sync_rows<2, true>(p, s, rank);
     sync_rows<3, true>(p, s, rank); sync_rows<4, true>(p, s, rank);
@@ -280,7 +297,7 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
 // the partial sums for the owner's columns, the owner adds the 8 slices in rank order.  One relaxed hardware cluster
 // barrier per step remains, only to keep the next step's stores from overtaking this step's readers.
 struct SmemA {
-    float w[OWN_P], m[OWN_P], v[OWN_P];
+    float w[OWN_P], m[OWN_P], v[OWN_P], g[OWN_P]; // g: gradient sums over the micro-batches of a batch larger than 32 rows
     float act[trn::A_FLOATS];
     float recv[2][NC][B * DSL]; // [layer parity][source rank]: partial input-deltas for the own columns
     float d[B * DSL];
@@ -392,9 +409,9 @@ __device__ __forceinline__ void reduce_local(SmemA& s, unsigned rank) {
 
 // grad_and_adam works on any struct with w, m, v, d, act members
 template <int L>
-__device__ __forceinline__ void backward_layer_async(const trn::Params& p, SmemA& s, float2 sc, unsigned rank, uint32_t par) {
+__device__ __forceinline__ void backward_layer_async(const trn::Params& p, SmemA& s, float2 sc, unsigned rank, uint32_t par, int accum) {
     if (L > 0) push_partial<(L > 0 ? L : 1)>(s, rank);
-    grad_and_adam<L>(p, s, sc, rank);
+    grad_and_adam<L>(p, s, sc, rank, accum);
     if (L > 0) {
         bar_wait(&s.bar_part[(L > 0 ? L : 1) - 1], par);
         reduce_local<(L > 0 ? L : 1)>(s, rank);
@@ -408,7 +425,7 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const int t = threadIdx.x, lane = t & 31;
-    for (int i = t; i < 3 * OWN_P; i += NT) s.w[i] = 0.0f;
+    for (int i = t; i < 4 * OWN_P; i += NT) s.w[i] = 0.0f;
     if (t == 0) {
         for (int k = 0; k < 5; ++k) bar_init(&s.bar_act[k]);
         for (int k = 0; k < 4; ++k) bar_init(&s.bar_part[k]);
@@ -420,9 +437,10 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
     uint64_t pf_my[2] = {0, 0}, pf_op[2] = {0, 0};
     float pf_t[2] = {0.f, 0.f};
     uint32_t pf_idx[2] = {0u, 0u};
-    auto fetch_idx = [&](uint32_t step) { // row indices first: the rows themselves are requested a whole step later
+    const uint32_t n_micro = p.n_steps * p.micro; // micro-batches of 32 rows; batch_idx is [n_steps][32 * micro] = [n_micro][32]
+    auto fetch_idx = [&](uint32_t ms) { // row indices first: the rows themselves are requested a whole micro-step later
 #pragma unroll
-        for (int h = 0; h < 2; ++h) pf_idx[h] = step < p.n_steps ? p.batch_idx[(size_t)step * B + (t >> 5) + 16 * h] : 0u;
+        for (int h = 0; h < 2; ++h) pf_idx[h] = ms < n_micro ? p.batch_idx[(size_t)ms * B + (t >> 5) + 16 * h] : 0u;
     };
     auto prefetch = [&]() {
 #pragma unroll
@@ -441,8 +459,10 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
     const bool prof = p.prof != nullptr && t == 0 && rank == 0;
     long long pc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tk = prof ? clock64() : 0;
 #define SYN_TICK(k) if (prof) { const long long now = clock64(); pc[k] += now - tk; tk = now; }
-    for (uint32_t step = 0; step < p.n_steps; ++step) {
-        const uint32_t par = step & 1u;
+    const float inv_batch = 1.0f / (float)(B * p.micro);
+    for (uint32_t ms = 0, step = 0, k_micro = 0; ms < n_micro; ++ms) {
+        const uint32_t par = ms & 1u;
+        const int accum = p.micro == 1u ? 0 : (k_micro + 1u == p.micro ? 2 : 1);
         if (t == 0) { // this step's phases: bytes that will land in THIS CTA
             bar_expect(&s.bar_act[0], 128u * 128u); bar_expect(&s.bar_act[1], 128u * 96u); bar_expect(&s.bar_act[2], 128u * 64u);
             bar_expect(&s.bar_act[3], 128u * 48u); bar_expect(&s.bar_act[4], 128u * 12u);
@@ -457,8 +477,8 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
             if (lane < 12) s.target[b][lane] = pf_t[h];
         }
         const float2 sc = p.sched[step];
-        if (step + 1u < p.n_steps) prefetch(); // rows of step + 1 (indices fetched during the previous step)
-        fetch_idx(step + 2u);
+        if (ms + 1u < n_micro) prefetch(); // rows of the next micro-step (indices fetched during the previous one)
+        fetch_idx(ms + 2u);
         __syncthreads();
         SYN_TICK(0)
         forward_async<0>(s, rank); bar_wait(&s.bar_act[0], par); SYN_TICK(1)
@@ -489,7 +509,7 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
             const float se = isp ? sep : sev, st = isp ? stp : stv;
             const float lp = z - (mx + logf(se));
             float lk = (k < 12 && tgt > 0.f) ? tgt * (logf(tgt) - lp) : 0.f; // kl_div: xlogy(t, t) - t * input
-            const float scale = (isp ? p.pw : p.vw) * (1.0f / (float)B);
+            const float scale = (isp ? p.pw : p.vw) * inv_batch;
             const int lo = (int)rank * Own<4>::sl;
             if (k >= lo && k < lo + Own<4>::sl && k < 12) s.d[b * DSL + (k - lo)] = scale * (__fdividef(ex, se) * st - tgt);
             float lpol = isp ? lk : 0.f, lval = isv ? lk : 0.f;
@@ -504,16 +524,18 @@ __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(NT, 1) train_cluste
         if (rank == 0 && t < 2 && p.losses) {
             float tot = 0.f;
             for (int r = 0; r < B; ++r) tot += s.loss_row[r][t];
-            p.losses[(size_t)step * 2 + t] = tot * (1.0f / (float)B);
+            const float part = tot * inv_batch;
+            p.losses[(size_t)step * 2 + t] = k_micro == 0u ? part : p.losses[(size_t)step * 2 + t] + part;
         }
         SYN_TICK(6)
-        backward_layer_async<4>(p, s, sc, rank, par); SYN_TICK(7)
-        backward_layer_async<3>(p, s, sc, rank, par); SYN_TICK(8)
-        backward_layer_async<2>(p, s, sc, rank, par); SYN_TICK(9)
-        backward_layer_async<1>(p, s, sc, rank, par); SYN_TICK(10)
-        backward_layer_async<0>(p, s, sc, rank, par); SYN_TICK(11)
+        backward_layer_async<4>(p, s, sc, rank, par, accum); SYN_TICK(7)
+        backward_layer_async<3>(p, s, sc, rank, par, accum); SYN_TICK(8)
+        backward_layer_async<2>(p, s, sc, rank, par, accum); SYN_TICK(9)
+        backward_layer_async<1>(p, s, sc, rank, par, accum); SYN_TICK(10)
+        backward_layer_async<0>(p, s, sc, rank, par, accum); SYN_TICK(11)
         cluster_barrier_relaxed(); // the next step's stores must not overtake this step's readers (execution order only)
         SYN_TICK(12)
+        if (++k_micro == p.micro) { k_micro = 0u; ++step; }
     }
 #undef SYN_TICK
     if (prof)

@@ -884,6 +884,37 @@ def _train_matches_torch_fp32(engine, weight_decay, pw, vw):
     np.testing.assert_allclose(pr, op_, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("batch_size", [64, 160])
+def test_train_batch_sizes_other_than_32(engine, batch_size):
+    """LearningConfig::batch_size is free in the reference (config.rs:76-94).  The learner's kernels are tiled for 32 rows; a
+    multiple of 32 runs as micro-batches whose gradients are summed before ONE Adam update per batch.  Against PyTorch fp32
+    with the same batch size: per-batch losses and all weights after 12 steps within 1e-3 abs/rel; other sizes are refused."""
+    from torch_learner import TorchLearner
+    d = _training_rows(engine, games=160)
+    n = len(d["num"])
+    rng = np.random.default_rng(1)
+    net = s.Connect4Net.new(6)
+    batches = np.concatenate([s.BatchRandSampler(n, batch_size, True, rng).all_batches() for _ in range(3)])[:12]
+    assert batches.shape == (12, batch_size)
+    ref = TorchLearner(net.blob(), 1e-3, 1e-2, 0.7, 1.3, batch_size=batch_size)
+    engine.set_weights(net.blob())
+    engine.reset_optimizer()
+    want_losses = ref.run(d["states"], d["pis"], d["vs"], batches)
+    got_losses, st = engine.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], batches, 1e-3, 1e-2, 0.7, 1.3, batch_size=batch_size)
+    assert st["rows"] == batch_size * 12
+    got, want = engine.get_weights(), ref.blob()
+    print("batch %d: max |dw| %.3g, max |dloss| %.3g" % (batch_size, np.abs(got - want).max(), np.abs(got_losses - want_losses).max()))
+    assert np.allclose(got_losses, want_losses, rtol=1e-3, atol=1e-3)
+    assert np.allclose(got, want, rtol=1e-3, atol=1e-3)
+    assert np.abs(got - net.blob()).max() > 1e-3
+    with pytest.raises(L.EngineError):  # not a multiple of 32
+        engine.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], batches[:, :48], 1e-3, batch_size=48)
+    # the two variant kernels take batches of 32 only
+    with pytest.raises(L.EngineError):
+        _with_env("SYN_TRAIN_CLUSTER", "1", lambda: engine.train(d["my_bb"], d["op_bb"], d["pis"], d["vs"], batches, 1e-3, batch_size=batch_size))
+    engine.set_weights(net.blob())
+
+
 def test_train_loss_decreases_and_edge_cases(engine):
     """Twenty epochs over a small FlatBatch through the host mirror of the epoch loop: the KL losses fall; bad
     arguments are refused the way the header says."""
@@ -1100,7 +1131,8 @@ def test_a_thousand_games_occupy_every_sm():
         e.set_weights(s.Connect4Net.new(0).blob())
         assert e.launch_geometry(1000, L.LEAF_NN)[2] == 32 and e.launch_geometry(4096, L.LEAF_NN)[2] == 16
         assert e.launch_geometry(256, L.LEAF_ROLLOUT)[2] == 32 and e.launch_geometry(4096, L.LEAF_ROLLOUT)[2] == 32
-        assert e.launch_geometry(148 * 640, L.LEAF_NN)[2] == 1 and e.launch_geometry(20000, L.LEAF_ROLLOUT)[2] == 1
+        assert e.launch_geometry(148 * 640, L.LEAF_NN)[2] == 1 and e.launch_geometry(60000, L.LEAF_ROLLOUT)[2] == 1
+        assert e.launch_geometry(10000, L.LEAF_NN)[2] == 16 and e.launch_geometry(20000, L.LEAF_ROLLOUT)[2] == 32  # seats refilled
         e.set_mlp_mode(2)  # fp32-grade leaves: the team kernels carry the split chain too
         assert e.launch_geometry(1000, L.LEAF_NN)[2] == 32 and e.launch_geometry(148 * 640, L.LEAF_NN)[2] == 1
         e.set_mlp_mode(0)  # the fp32 CUDA-core forward has no small-batch mapping of its own: thread per game's seating
