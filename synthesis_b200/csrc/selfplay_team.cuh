@@ -233,6 +233,11 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_team_kernel(const 
     lgteam::teardown<TEAMS, SLOTS>(ms);
 }
 
+// (One step further was measured and lost: every WARP running its chain alone — a warp can read the TMEM lanes of its own
+// quarter, which are the rows its lanes stand on.  Nobody waits for anybody's descent, but 16 warps then queue for the four
+// TMEM slots with a 9 k-cycle forward each: 166 against 223 M explores/s at 4,096 games in flight, 83 against 81 M at 1,000.
+// A forward shared by the eight groups of a team is the better trade.  profiles/r2_lane_group_clocks.txt)
+
 // The same schedule with the split-fp16 chain (mlp_split.cuh: x = hi + lo operands, three MMAs per K-step, activations in
 // tensor memory — fp32-grade outputs, what the engine selects for weights that the single-fp16 chain cannot carry).
 // Activations never touch shared memory here, so there is no tile to share: every lane of a group puts the group's leaf on
