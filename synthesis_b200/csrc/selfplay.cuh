@@ -297,6 +297,7 @@ __device__ __forceinline__ bool advance(const Grp<GL>& g, const KParams& p, Tree
                 t.fpu_seed = syn_stream_seed(p.seed, G, SYN_STREAM_FPU);
             }
             if (!NN) rr.init(g, rseed, rr_smem);
+            if (p.cfg.mcts.fpu_kind == SYN_FPU_NORMAL) fpu_stream_begin(g, t);
             st.phase = PH_NEW_TREE;
         }
         if (st.phase == PH_NEW_TREE) { // MCTS::with_capacity (mcts.rs:123-137): fresh arena, root only
@@ -350,12 +351,14 @@ __global__ void __launch_bounds__(THREADS) selfplay_rollout_kernel(const __grid_
     constexpr int GPB = THREADS / GL;
     __shared__ uint32_t s_path[GPB][64];
     __shared__ uint32_t s_rng[GPB][4 * GL];
+    __shared__ uint32_t s_fpu[GPB][FPU_SM_WORDS];
     Grp<GL> g;
     const int grp = threadIdx.x / GL;
     const size_t slot = (size_t)blockIdx.x * GPB + grp;
     Tree<GL> t;
     t.stat.base = t.meta.base = p.nodes + 2 * slot * p.arena_nodes;
     t.path = s_path[grp];
+    t.fpu_sm = s_fpu[grp];
     t.cap = p.arena_nodes;
     t.cfg = &p.cfg.mcts;
     t.err = 0;

@@ -38,7 +38,7 @@ struct __align__(128) LgTeamSmem {
 };
 
 template <int TEAMS, int SLOTS, int GL>
-constexpr size_t nn_team_smem_bytes() { return sizeof(LgTeamSmem<TEAMS, SLOTS>) + (size_t)(128 * TEAMS / GL) * 64 * sizeof(uint32_t); }
+constexpr size_t nn_team_smem_bytes() { return sizeof(LgTeamSmem<TEAMS, SLOTS>) + (size_t)(128 * TEAMS / GL) * (64 + FPU_SM_WORDS) * sizeof(uint32_t); }
 
 namespace lgteam {
 using namespace mlptc;
@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_team_kernel(const 
     Tree<GL> t;
     t.stat.base = t.meta.base = p.nodes + 2 * slot_id * p.arena_nodes;
     t.path = s_path + (team * GPT + gt) * 64;
+    t.fpu_sm = s_path + GPB * 64 + (team * GPT + gt) * FPU_SM_WORDS; // after the path tables
     t.cap = p.arena_nodes;
     t.cfg = &p.cfg.mcts;
     t.err = 0;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_team_kernel(const 
 // ITS OWN tile row (the rows of a group are copies), runs its row's epilogue in lockstep with the others, and ends up
 // holding all 12 outputs — no hand-over by shuffles.  Four teams take turns on two slots of 256 TMEM columns.
 template <int TEAMS, int GL>
-constexpr size_t nn_team_split_smem_bytes() { return sizeof(mlps::Smem<TEAMS, 2>) + (size_t)(128 * TEAMS / GL) * 64 * sizeof(uint32_t); }
+constexpr size_t nn_team_split_smem_bytes() { return sizeof(mlps::Smem<TEAMS, 2>) + (size_t)(128 * TEAMS / GL) * (64 + FPU_SM_WORDS) * sizeof(uint32_t); }
 
 template <int GL, int TEAMS>
 __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_team_split_kernel(const __grid_constant__ KParams p) {
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_team_split_kernel(
     Tree<GL> t;
     t.stat.base = t.meta.base = p.nodes + 2 * slot_id * p.arena_nodes;
     t.path = s_path + (team * GPT + gt) * 64;
+    t.fpu_sm = s_path + GPB * 64 + (team * GPT + gt) * FPU_SM_WORDS; // after the path tables
     t.cap = p.arena_nodes;
     t.cfg = &p.cfg.mcts;
     t.err = 0;

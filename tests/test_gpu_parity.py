@@ -232,6 +232,31 @@ def test_group_lanes_do_not_change_results(engine, leaf):
             assert res[gl][1][k] == res[32][1][k], (gl, k)
 
 
+@pytest.mark.parametrize("leaf", ["rollout", "nn", "nn_split"])
+def test_group_lanes_with_the_shipped_normal_fpu(engine, leaf):
+    """study-connect4/src/main.rs:43-47 ships Fpu::Func(Normal(1.0, 0.1)): the closure runs for every unvisited child every
+    time its parent is selected through.  The lane-group kernels keep that stream's key and current block in shared memory
+    between calls; a thread per game re-derives them.  Same draws, same rows, same counters."""
+    m = s.study_connect4_mcts_cfg(fpu=s.Fpu.Normal(1.0, 0.1))
+    cfg = s.study_connect4_rollout_cfg(num_explores=120, mcts_cfg=m, sample_actions_until=12)
+    kind = L.LEAF_ROLLOUT if leaf == "rollout" else L.LEAF_NN
+    if leaf != "rollout":
+        engine.set_weights(s.Connect4Net.new(3).blob())
+        engine.set_mlp_mode(1 if leaf == "nn" else 2)
+    res = {}
+    try:
+        for gl in (32, 16, 1):
+            engine.set_group_lanes(gl)
+            res[gl] = engine.gather(cfg, kind, 3, 150, 4, trace=True)
+    finally:
+        engine.set_group_lanes(1)
+        engine.set_mlp_mode(3)
+    for gl in (16, 32):
+        assert_rows_equal(res[gl][0], res[1][0], f"GL{gl} vs thread per game: experience")
+        assert_rows_equal(res[gl][2], res[1][2], f"GL{gl} vs thread per game: trace")
+        assert res[gl][1]["explores"] == res[1][1]["explores"] and res[gl][1]["nodes"] == res[1][1]["nodes"]
+
+
 @pytest.mark.parametrize("threads", [512, 640, 768, 896])
 def test_rollout_threads_per_cta_do_not_change_results(threads):
     """selfplay_rollout_tpg2_kernel is instantiated for 1024 (default), 896, 768, 640 and 512 games per CTA (different ring
