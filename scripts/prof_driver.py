@@ -9,6 +9,8 @@ gl = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 modes = sys.argv[4].split(",") if len(sys.argv) > 4 else ["rollout", "nn"]
 in_flight = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # games in flight (default: as many as the GPU seats)
 cfg = s.study_connect4_rollout_cfg(num_explores=explores)
+if len(sys.argv) > 6 and sys.argv[6] == "normalfpu":  # the shipped first-play urgency, study-connect4/src/main.rs:43-47
+    cfg = s.study_connect4_rollout_cfg(num_explores=explores, mcts_cfg=s.study_connect4_mcts_cfg(fpu=s.Fpu.Normal(1.0, 0.1)), sample_actions_until=30)
 if len(sys.argv) > 6 and sys.argv[6] == "config2":  # bench.py --config 2: Dirichlet(1.0, 0.25) root noise, sample_actions_until = 30
     m = s.study_connect4_mcts_cfg()
     m.root_policy_noise = s.PolicyNoise.Dirichlet(1.0, 0.25)
