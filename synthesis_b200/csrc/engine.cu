@@ -91,6 +91,7 @@ struct syn_engine {
     bool tpg_prof = false; // SYN_TPG_PROF=1: the instantiation with per-warp phase clocks
    // 2 = round-synchronous kernel (tpg2.cuh), 1 = the first thread-per-game kernel (tpg.cuh)
     DevBuf<uint32_t> slot_state;
+    DevBuf<uint32_t> fpu_state; // tp2::FS_WORDS per slot
     DevBuf<uint4> nodes; // 2 x uint4 = one 32-byte record per tree node
     DevBuf<float> weights;
     DevBuf<uint8_t> weight_image; // mlptc layout (fp16 weights + fp32 biases)
@@ -477,6 +478,7 @@ static void fill_common(syn_engine* e, KParams& kp, const syn_rollout_cfg* cfg) 
     kp.nodes = e->nodes.p;
     kp.next_game = e->next_game.p;
     kp.slot_state = e->slot_state.p;
+    kp.fpu_state = e->fpu_state.p;
     kp.counters = e->counters.p;
     kp.error = e->error.p;
     kp.weights = e->weights.p;
@@ -779,7 +781,7 @@ int syn_engine_create(int cuda_device, uint32_t max_games_in_flight, uint32_t ma
     size_t total = (size_t)e->max_games * e->arena_nodes;
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
-        (ce = e->nodes.reserve(2 * total)) != cudaSuccess || (ce = e->slot_state.reserve((size_t)e->max_games * tp2::SS_WORDS)) != cudaSuccess ||
+        (ce = e->nodes.reserve(2 * total)) != cudaSuccess || (ce = e->slot_state.reserve((size_t)e->max_games * tp2::SS_WORDS)) != cudaSuccess || (ce = e->fpu_state.reserve((size_t)e->max_games * tp2::FS_WORDS)) != cudaSuccess ||
         (ce = e->weights.reserve(SYN_N_WEIGHTS)) != cudaSuccess || (ce = e->weight_image.reserve(mlptc::IMG_BYTES)) != cudaSuccess || (ce = e->weight_image_lo.reserve(mlptc::W_TOTAL)) != cudaSuccess || (ce = e->next_game.reserve(1)) != cudaSuccess ||
         (ce = e->counters.reserve(CNT_ALL)) != cudaSuccess || (ce = e->error.reserve(1)) != cudaSuccess) {
         int rc = fail(SYN_ERR_CUDA, "engine allocation failed (%zu arena nodes = %.1f MiB): %s", total,
@@ -795,7 +797,7 @@ void syn_engine_destroy(syn_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->nodes.release(); e->slot_state.release(); e->weights.release(); e->weight_image.release(); e->weight_image_lo.release(); e->calib_pos.release(); e->calib_out.release(); e->weights2.release(); e->weight_image2.release(); e->next_game.release(); e->counters.release(); e->error.release();
+    e->nodes.release(); e->slot_state.release(); e->fpu_state.release(); e->weights.release(); e->weight_image.release(); e->weight_image_lo.release(); e->calib_pos.release(); e->calib_out.release(); e->weights2.release(); e->weight_image2.release(); e->next_game.release(); e->counters.release(); e->error.release();
     e->row_my.release(); e->row_op.release(); e->row_off.release(); e->row_pi.release(); e->row_v.release(); e->row_visits.release();
     e->row_action.release(); e->row_nodes.release(); e->game_len.release(); e->staging.release();
     e->pos_my.release(); e->pos_op.release(); e->pos_seed.release(); e->s_visits.release(); e->s_q.release();

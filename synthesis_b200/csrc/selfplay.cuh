@@ -54,6 +54,7 @@ struct KParams {
     uint8_t* s_root_sol;
     uint8_t* s_best;
     uint32_t* s_nodes;
+    uint32_t* fpu_state;          // [max_games][tp2::FS_WORDS]: per-slot cache of the Normal-FPU stream (thread-per-game kernels)
     unsigned long long* counters; // [CNT_N]
     int* error;
     const float* weights; // device blob, NN mode

@@ -73,11 +73,13 @@ __device__ __forceinline__ void prefetch_l2(const uint4* nodes, uint32_t i) { as
 __device__ __forceinline__ uint32_t* meta_words(uint4* nodes, uint32_t i) { return reinterpret_cast<uint32_t*>(nodes + 2 * (size_t)i + 1); }
 enum { MW_PRIOR = 0, MW_PARENT = 1, MW_FC = 2, MW_PK = 3 };
 
-// Per-slot state outside the registers (global memory, 192 bytes per game in flight): the root position of
-// the current tree (read once per round next to the root record), what only changes once per move, and — for the shipped
-// Normal first-play urgency — the FPU stream's expanded key, its current ChaCha12 block and its position (fpu_normal_draw).
-enum { SS_MY = 0, SS_OP = 2, SS_GI = 4, SS_PLY = 5, SS_APOS = 6, SS_NOISE_POS = 8,
-       SS_FPU_KEY = 16, SS_FPU_BLOCK = 24, SS_FPU_BLK = 40, SS_FPU_KEYED = 41, SS_FPU_POS = 42, SS_WORDS = 48 };
+// Per-slot state outside the registers (global memory, 64 bytes per game in flight): the root position of
+// the current tree (read once per round next to the root record) and what only changes once per move.
+enum { SS_MY = 0, SS_OP = 2, SS_GI = 4, SS_PLY = 5, SS_APOS = 6, SS_NOISE_POS = 8, SS_WORDS = 16 };
+// A second record per slot, touched only by the shipped Normal first-play urgency (fpu_normal_draw): the FPU stream's
+// expanded key, its current ChaCha12 block, and {block held, keyed, position} in one 16-byte quad.  (Kept out of the slot
+// record above: growing that one from 64 to 192 bytes cost the Fpu::Const bench 4 %.)
+enum { FS_KEY = 0, FS_BLOCK = 8, FS_BLK = 24, FS_KEYED = 25, FS_POS = 26, FS_WORDS = 32 };
 
 
 // Hot per-thread state is three registers: the arena pointer is recomputed from the slot index, and
@@ -113,10 +115,10 @@ __device__ __forceinline__ uint64_t stream_seed(const KParams& p, uint32_t gi, u
 // mcts.rs:354 with the shipped closure (study-connect4/src/main.rs:43-47).  The closure runs for EVERY unvisited child EVERY
 // time its parent is selected through, so with the shipped configuration this is on the hot path: re-deriving the stream's
 // key (PCG32 x 8) and its ChaCha12 block (~700 instructions) per draw made the thread-per-game kernels 4.6 x slower than with
-// a constant FPU (265 M against 1,232 M explores/s, profiles/r2_normal_fpu.txt).  Key and current block now live in the
-// game's slot record (L2-resident: 94,720 x 192 bytes) and a block is generated once per 16 words.
+// a constant FPU (265 M against 1,232 M explores/s, profiles/r2_normal_fpu.txt).  Key and current block now live in a
+// 128-byte record per game in flight (KParams::fpu_state, L2-resident) and a block is generated once per 16 words.
 struct SlotFpuStream { // R-concept of include/syn_sampling.h; words come out of the record four at a time (one LDG.128)
-    uint32_t* ss;
+    uint32_t* fs;
     uint32_t pos, have_blk;
     uint4 quad;
     uint32_t have_quad; // pos >> 2 of the four words in `quad`, or ~0u
@@ -124,30 +126,32 @@ struct SlotFpuStream { // R-concept of include/syn_sampling.h; words come out of
         const uint32_t blk = pos >> 4, qi = pos >> 2;
         if (qi != have_quad) {
             if (blk != have_blk) {
-                rng::chacha12_block(ss + SS_FPU_KEY, (uint64_t)blk, ss + SS_FPU_BLOCK);
-                ss[SS_FPU_BLK] = blk;
+                rng::chacha12_block(fs + FS_KEY, (uint64_t)blk, fs + FS_BLOCK);
+                fs[FS_BLK] = blk;
                 have_blk = blk;
             }
-            quad = *reinterpret_cast<const uint4*>(ss + SS_FPU_BLOCK + (pos & 12u));
+            quad = *reinterpret_cast<const uint4*>(fs + FS_BLOCK + (pos & 12u));
             have_quad = qi;
         }
         const uint32_t k = (pos++) & 3u;
         return k == 0u ? quad.x : (k == 1u ? quad.y : (k == 2u ? quad.z : quad.w));
     }
 };
+__device__ __forceinline__ uint32_t* fpu_state_of(const KParams& p, const uint32_t* ss) { return p.fpu_state + (size_t)FS_WORDS * (size_t)((ss - p.slot_state) / SS_WORDS); }
 __device__ __noinline__ float fpu_normal_draw(const KParams& p, uint32_t* ss) {
-    const uint4 hdr = *reinterpret_cast<const uint4*>(ss + SS_FPU_BLK); // {block held, keyed, position, -}
+    uint32_t* fs = fpu_state_of(p, ss);
+    const uint4 hdr = *reinterpret_cast<const uint4*>(fs + FS_BLK); // {block held, keyed, position, -}
     if (hdr.y == 0u) { // first draw of this game: expand the key once (next_game cleared the flag)
         uint32_t key[8];
         rng::seed_key(stream_seed(p, ss[SS_GI], SYN_STREAM_FPU), key);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss[SS_FPU_KEY + i] = key[i];
-        ss[SS_FPU_BLK] = 0xffffffffu;
-        ss[SS_FPU_KEYED] = 1u;
+        for (int i = 0; i < 8; ++i) fs[FS_KEY + i] = key[i];
+        fs[FS_BLK] = 0xffffffffu;
+        fs[FS_KEYED] = 1u;
     }
-    SlotFpuStream st{ss, hdr.z, hdr.y == 0u ? 0xffffffffu : hdr.x, make_uint4(0u, 0u, 0u, 0u), 0xffffffffu};
+    SlotFpuStream st{fs, hdr.z, hdr.y == 0u ? 0xffffffffu : hdr.x, make_uint4(0u, 0u, 0u, 0u), 0xffffffffu};
     const float v = syn_normal(st, p.cfg.mcts.fpu_a, p.cfg.mcts.fpu_b);
-    ss[SS_FPU_POS] = st.pos;
+    fs[FS_POS] = st.pos;
     return v;
 }
 
@@ -552,7 +556,8 @@ __device__ __noinline__ int end_of_move(const KParams& p, uint32_t* ss, uint4* n
 __device__ __noinline__ int next_game(const KParams& p, uint32_t* ss) {
     uint32_t gi = atomicAdd(p.next_game, 1u);
     if (gi >= p.num_games || *(volatile int*)p.error != 0) return PH_DONE;
-    ss[SS_GI] = gi; ss[SS_PLY] = 0u; ss[SS_APOS] = 0u; ss[SS_FPU_POS] = 0u; ss[SS_FPU_KEYED] = 0u; ss[SS_NOISE_POS] = 0u;
+    ss[SS_GI] = gi; ss[SS_PLY] = 0u; ss[SS_APOS] = 0u; ss[SS_NOISE_POS] = 0u;
+    if (p.cfg.mcts.fpu_kind == SYN_FPU_NORMAL) { uint32_t* fs = fpu_state_of(p, ss); fs[FS_KEYED] = 0u; fs[FS_POS] = 0u; }
     ss_store64(ss, SS_MY, p.search_mode ? p.pos_my[gi] : 0ull);
     ss_store64(ss, SS_OP, p.search_mode ? p.pos_op[gi] : 0ull);
     return PH_NEW_TREE;
