@@ -217,6 +217,12 @@ static int launch_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
         selfplay_nn_tpg2_kernel<TEAMS, SLOTS, true><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
         return SYN_OK;
     }
+    if (TEAMS == 5 && kp.cfg.mcts.fpu_kind == SYN_FPU_NORMAL) { // the shipped first-play urgency: its own instantiation with the cached stream
+        constexpr int T = TEAMS == 5 ? 5 : 1, S = TEAMS == 5 ? SLOTS : 1; // (only <5, 4> is instantiated)
+        CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2_kernel<T, S, false, tp2::FPU_NORMAL_CACHED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        selfplay_nn_tpg2_kernel<T, S, false, tp2::FPU_NORMAL_CACHED><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+        return SYN_OK;
+    }
     CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2_kernel<TEAMS, SLOTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     selfplay_nn_tpg2_kernel<TEAMS, SLOTS, false><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
     return SYN_OK;
@@ -230,6 +236,12 @@ static int launch_tpg_split(syn_engine* e, KParams& kp, uint32_t blocks) { // ne
         selfplay_nn_tpg2s_kernel<TEAMS, true><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
         return SYN_OK;
     }
+    if (TEAMS == 5 && kp.cfg.mcts.fpu_kind == SYN_FPU_NORMAL) {
+        constexpr int T = TEAMS == 5 ? 5 : 1;
+        CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2s_kernel<T, false, tp2::FPU_NORMAL_CACHED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        selfplay_nn_tpg2s_kernel<T, false, tp2::FPU_NORMAL_CACHED><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
+        return SYN_OK;
+    }
     CUDA_TRY(cudaFuncSetAttribute(selfplay_nn_tpg2s_kernel<TEAMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     selfplay_nn_tpg2s_kernel<TEAMS, false><<<blocks, 128 * TEAMS, smem, e->stream>>>(kp);
     return SYN_OK;
@@ -238,6 +250,12 @@ static int launch_tpg_split(syn_engine* e, KParams& kp, uint32_t blocks) { // ne
 template <int NT, int CW>
 static int launch_rollout_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
     const size_t smem = tp2r::smem_bytes(NT);
+    if (NT == 1024 && CW == 3 && kp.cfg.mcts.fpu_kind == SYN_FPU_NORMAL) { // the default geometry with the cached FPU stream
+        constexpr int N = (NT == 1024 && CW == 3) ? 1024 : 512, C = (NT == 1024 && CW == 3) ? 3 : 5;
+        CUDA_TRY(cudaFuncSetAttribute(selfplay_rollout_tpg2_kernel<N, C, tp2::FPU_NORMAL_CACHED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        selfplay_rollout_tpg2_kernel<N, C, tp2::FPU_NORMAL_CACHED><<<blocks, NT, smem, e->stream>>>(kp);
+        return SYN_OK;
+    }
     CUDA_TRY(cudaFuncSetAttribute(selfplay_rollout_tpg2_kernel<NT, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     selfplay_rollout_tpg2_kernel<NT, CW><<<blocks, NT, smem, e->stream>>>(kp);
     return SYN_OK;

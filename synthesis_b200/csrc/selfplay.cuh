@@ -54,13 +54,14 @@ struct KParams {
     uint8_t* s_root_sol;
     uint8_t* s_best;
     uint32_t* s_nodes;
-    uint32_t* fpu_state;          // [max_games][tp2::FS_WORDS]: per-slot cache of the Normal-FPU stream (thread-per-game kernels)
     unsigned long long* counters; // [CNT_N]
     int* error;
     const float* weights; // device blob, NN mode
     const uint8_t* weight_image; // mlptc image (fp16 UMMA layout), NN mode on tensor cores
     const uint8_t* weight_image_lo; // mlp_split.cuh: the fp16 remainders W - fp16(W) in the same layout
     float mlp_bias[mlptc::BIAS_FLOATS]; // the image's padded fp32 biases again, in the parameter space: constant-bank operands (mlp_team.cuh forward_cb)
+    uint32_t* fpu_state;                // [max_games][tp2::FS_WORDS]: per-slot cache of the Normal-FPU stream (thread-per-game kernels); last member:
+                                        // the offsets of everything above are what the kernels were tuned with
 };
 
 enum Phase { PH_NEED_GAME = 0, PH_NEW_TREE = 1, PH_EXPLORE = 2, PH_DONE = 3 };

@@ -75,11 +75,12 @@ enum { MW_PRIOR = 0, MW_PARENT = 1, MW_FC = 2, MW_PK = 3 };
 
 // Per-slot state outside the registers (global memory, 64 bytes per game in flight): the root position of
 // the current tree (read once per round next to the root record) and what only changes once per move.
-enum { SS_MY = 0, SS_OP = 2, SS_GI = 4, SS_PLY = 5, SS_APOS = 6, SS_NOISE_POS = 8, SS_WORDS = 16 };
+enum { SS_MY = 0, SS_OP = 2, SS_GI = 4, SS_PLY = 5, SS_APOS = 6, SS_FPU_POS = 7, SS_NOISE_POS = 8, SS_WORDS = 16 };
 // A second record per slot, touched only by the shipped Normal first-play urgency (fpu_normal_draw): the FPU stream's
-// expanded key, its current ChaCha12 block, and {block held, keyed, position} in one 16-byte quad.  (Kept out of the slot
-// record above: growing that one from 64 to 192 bytes cost the Fpu::Const bench 4 %.)
-enum { FS_KEY = 0, FS_BLOCK = 8, FS_BLK = 24, FS_KEYED = 25, FS_POS = 26, FS_WORDS = 32 };
+// expanded key, its current ChaCha12 block and which block that is.  (Kept out of the slot record above: growing that one
+// from 64 to 192 bytes cost the Fpu::Const bench 4 %.  The stream position stays in the slot record: position 0 = the
+// game's first draw = the moment to expand its key.)
+enum { FS_KEY = 0, FS_BLOCK = 8, FS_BLK = 24, FS_WORDS = 32 };
 
 
 // Hot per-thread state is three registers: the arena pointer is recomputed from the slot index, and
@@ -117,41 +118,48 @@ __device__ __forceinline__ uint64_t stream_seed(const KParams& p, uint32_t gi, u
 // key (PCG32 x 8) and its ChaCha12 block (~700 instructions) per draw made the thread-per-game kernels 4.6 x slower than with
 // a constant FPU (265 M against 1,232 M explores/s, profiles/r2_normal_fpu.txt).  Key and current block now live in a
 // 128-byte record per game in flight (KParams::fpu_state, L2-resident) and a block is generated once per 16 words.
-struct SlotFpuStream { // R-concept of include/syn_sampling.h; words come out of the record four at a time (one LDG.128)
+__device__ __noinline__ float fpu_normal_draw(const KParams& p, uint32_t* ss) { // mcts.rs:354 with the shipped closure; cold
+    rng::Stream st;
+    st.init(stream_seed(p, ss[SS_GI], SYN_STREAM_FPU), ss[SS_FPU_POS]);
+    float v = syn_normal(st, p.cfg.mcts.fpu_a, p.cfg.mcts.fpu_b);
+    ss[SS_FPU_POS] = (uint32_t)st.pos;
+    return v;
+}
+
+// The same draw with the stream's expanded key and current ChaCha12 block cached per game in flight (KParams::fpu_state, 128 bytes
+// per slot, L2-resident; position 0 = the game's first draw = the moment to expand its key): a block is generated once per 16
+// words instead of once per draw — 265 -> ~500 M explores/s with NN leaves at full scale (profiles/r2_normal_fpu.txt).
+// Only the Normal-only kernel instantiations (FPUK = FPU_NORMAL_CACHED) call it, and it has its own block function: the tuned
+// runtime-dispatch kernels must not see a changed callee — giving rng::chacha12_block one new caller moved the register
+// allocation of selfplay_nn_tpg2_kernel<5,4> and cost the Fpu::Const bench 2.5 % (found by diffing SASS between builds).
+constexpr int FPU_NORMAL_CACHED = 100 + SYN_FPU_NORMAL;
+struct SlotFpuStream { // R-concept of include/syn_sampling.h
     uint32_t* fs;
     uint32_t pos, have_blk;
-    uint4 quad;
-    uint32_t have_quad; // pos >> 2 of the four words in `quad`, or ~0u
     __device__ uint32_t next_u32() {
-        const uint32_t blk = pos >> 4, qi = pos >> 2;
-        if (qi != have_quad) {
-            if (blk != have_blk) {
-                rng::chacha12_block(fs + FS_KEY, (uint64_t)blk, fs + FS_BLOCK);
-                fs[FS_BLK] = blk;
-                have_blk = blk;
-            }
-            quad = *reinterpret_cast<const uint4*>(fs + FS_BLOCK + (pos & 12u));
-            have_quad = qi;
+        const uint32_t blk = pos >> 4;
+        if (blk != have_blk) {
+            chacha12_block_smem(fs, blk); // key at fs[0, 8), block to fs[8, 24): the layout of the lane-group kernels' copy (tree.cuh)
+            fs[FS_BLK] = blk;
+            have_blk = blk;
         }
-        const uint32_t k = (pos++) & 3u;
-        return k == 0u ? quad.x : (k == 1u ? quad.y : (k == 2u ? quad.z : quad.w));
+        return fs[FS_BLOCK + ((pos++) & 15u)];
     }
 };
-__device__ __forceinline__ uint32_t* fpu_state_of(const KParams& p, const uint32_t* ss) { return p.fpu_state + (size_t)FS_WORDS * (size_t)((ss - p.slot_state) / SS_WORDS); }
-__device__ __noinline__ float fpu_normal_draw(const KParams& p, uint32_t* ss) {
-    uint32_t* fs = fpu_state_of(p, ss);
-    const uint4 hdr = *reinterpret_cast<const uint4*>(fs + FS_BLK); // {block held, keyed, position, -}
-    if (hdr.y == 0u) { // first draw of this game: expand the key once (next_game cleared the flag)
+__device__ __noinline__ float fpu_normal_draw_cached(const KParams& p, uint32_t* ss) {
+    uint32_t* fs = p.fpu_state + (size_t)FS_WORDS * (size_t)((ss - p.slot_state) / SS_WORDS);
+    const uint32_t pos = ss[SS_FPU_POS];
+    uint32_t have = fs[FS_BLK];
+    if (pos == 0u) { // first draw of this game (next_game reset the position): expand the key once
         uint32_t key[8];
         rng::seed_key(stream_seed(p, ss[SS_GI], SYN_STREAM_FPU), key);
 #pragma unroll
         for (int i = 0; i < 8; ++i) fs[FS_KEY + i] = key[i];
-        fs[FS_BLK] = 0xffffffffu;
-        fs[FS_KEYED] = 1u;
+        have = 0xffffffffu;
     }
-    SlotFpuStream st{fs, hdr.z, hdr.y == 0u ? 0xffffffffu : hdr.x, make_uint4(0u, 0u, 0u, 0u), 0xffffffffu};
+    SlotFpuStream st{fs, pos, have};
     const float v = syn_normal(st, p.cfg.mcts.fpu_a, p.cfg.mcts.fpu_b);
-    fs[FS_POS] = st.pos;
+    ss[SS_FPU_POS] = st.pos;
     return v;
 }
 
@@ -227,6 +235,7 @@ __device__ __forceinline__ int descend(const KParams& p, uint32_t* ss, Game& g, 
                     q = cfg.select_solved_nodes ? (kd == SYN_KIND_WIN ? -1.0f : (kd == SYN_KIND_LOSE ? 1.0f : 0.0f)) : __uint_as_float(0xff800000u);
                 } else if (cn == 0u) {
                     if (FPU == SYN_FPU_NORMAL) q = k < nch ? fpu_normal_draw(p, ss) : 0.0f;
+                    else if (FPU == FPU_NORMAL_CACHED) q = k < nch ? fpu_normal_draw_cached(p, ss) : 0.0f;
                     else q = fpu_q;
                 } else {
                     q = -__fdiv_rn(__fsub_rn(ch.o2, ch.o0), ch.vis);
@@ -556,8 +565,7 @@ __device__ __noinline__ int end_of_move(const KParams& p, uint32_t* ss, uint4* n
 __device__ __noinline__ int next_game(const KParams& p, uint32_t* ss) {
     uint32_t gi = atomicAdd(p.next_game, 1u);
     if (gi >= p.num_games || *(volatile int*)p.error != 0) return PH_DONE;
-    ss[SS_GI] = gi; ss[SS_PLY] = 0u; ss[SS_APOS] = 0u; ss[SS_NOISE_POS] = 0u;
-    if (p.cfg.mcts.fpu_kind == SYN_FPU_NORMAL) { uint32_t* fs = fpu_state_of(p, ss); fs[FS_KEYED] = 0u; fs[FS_POS] = 0u; }
+    ss[SS_GI] = gi; ss[SS_PLY] = 0u; ss[SS_APOS] = 0u; ss[SS_FPU_POS] = 0u; ss[SS_NOISE_POS] = 0u;
     ss_store64(ss, SS_MY, p.search_mode ? p.pos_my[gi] : 0ull);
     ss_store64(ss, SS_OP, p.search_mode ? p.pos_op[gi] : 0ull);
     return PH_NEW_TREE;
@@ -568,7 +576,9 @@ __device__ __noinline__ int next_game(const KParams& p, uint32_t* ss) {
 namespace eng {
 
 // One persistent CTA per SM, TEAMS teams of 128 threads sharing SLOTS MLP slots (mlp_team.cuh).
-template <int TEAMS, int SLOTS, bool PROF>
+// FPUK = -1: the configured syn_fpu_kind is dispatched at run time (the tuned kernels); tp2::FPU_NORMAL_CACHED: a kernel for the shipped
+// Normal first-play urgency alone, with the cached stream.
+template <int TEAMS, int SLOTS, bool PROF, int FPUK = -1>
 __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ unsigned long long s_cnt[CNT_ALL];
@@ -631,7 +641,8 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2_kernel(const 
             }
             if (go && !err) {
                 const uint32_t init = root.vis == 0.0f ? (uint32_t)tp2::K_INIT : 0u; // the construction visit (mcts.rs:133)
-                if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                if (FPUK == tp2::FPU_NORMAL_CACHED) err = tp2::descend<CW, tp2::FPU_NORMAL_CACHED, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                else if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 else err = tp2::descend<CW, SYN_FPU_NORMAL, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 pd.kind |= init;

@@ -124,7 +124,7 @@ __host__ __device__ constexpr size_t smem_bytes(int nt) { return (size_t)nt * (s
 namespace eng {
 
 // One persistent CTA per SM, NT threads, thread = game (or search root).  CW = child records per memory round trip.
-template <int NT, int CW>
+template <int NT, int CW, int FPUK = -1> // FPUK: see selfplay_nn_tpg2_kernel
 __global__ void __launch_bounds__(NT, 1) selfplay_rollout_tpg2_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ unsigned long long s_cnt[CNT_N];
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(NT, 1) selfplay_rollout_tpg2_kernel(const __gr
             }
             if (go && !err) {
                 const uint32_t init = root.vis == 0.0f ? (uint32_t)tp2::K_INIT : 0u; // the construction visit (mcts.rs:133)
-                if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                if (FPUK == tp2::FPU_NORMAL_CACHED) err = tp2::descend<CW, tp2::FPU_NORMAL_CACHED, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                else if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 else err = tp2::descend<CW, SYN_FPU_NORMAL, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 pd.kind |= init;

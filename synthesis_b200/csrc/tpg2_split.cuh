@@ -16,7 +16,7 @@ constexpr size_t smem_bytes() { return sizeof(mlps::Smem<TEAMS, (TEAMS < 2 ? TEA
 namespace eng {
 
 // One persistent CTA per SM, TEAMS teams of 128 threads sharing two MLP slots of tensor memory (mlp_split.cuh).
-template <int TEAMS, bool PROF>
+template <int TEAMS, bool PROF, int FPUK = -1> // FPUK: see selfplay_nn_tpg2_kernel
 __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2s_kernel(const __grid_constant__ KParams p) {
     constexpr int SLOTS = TEAMS < 2 ? TEAMS : 2;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2s_kernel(const
             }
             if (go && !err) {
                 const uint32_t init = root.vis == 0.0f ? (uint32_t)tp2::K_INIT : 0u; // the construction visit (mcts.rs:133)
-                if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                if (FPUK == tp2::FPU_NORMAL_CACHED) err = tp2::descend<CW, tp2::FPU_NORMAL_CACHED, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                else if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 else err = tp2::descend<CW, SYN_FPU_NORMAL, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 pd.kind |= init;

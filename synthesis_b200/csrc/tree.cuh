@@ -327,13 +327,33 @@ __device__ __forceinline__ void backprop(const Grp<GL>& g, Tree<GL>& t, int d, f
 // and its current ChaCha12 block stay in shared memory between calls (re-deriving both per call — ~800 instructions of one
 // lane — made a 1,600-explore move 2.4 x slower than with a constant FPU).
 constexpr int FPU_SM_WORDS = 28; // [0, 8) key, [8, 24) block, [24] index of the block held (~0u: none)
+// rng::chacha12_block for a key and a destination in shared memory.  A separate function on purpose: rng::chacha12_block is
+// shared (noinline) with the thread-per-game kernels, and giving it a new kind of caller changed ITS register footprint and
+// with it the register allocation of selfplay_nn_tpg2_kernel around its calls: 2.5 % of the headline bench, found by
+// diffing SASS between builds.
+__device__ __noinline__ void chacha12_block_smem(uint32_t* sm, uint32_t counter) {
+    const uint32_t k0 = sm[0], k1 = sm[1], k2 = sm[2], k3 = sm[3], k4 = sm[4], k5 = sm[5], k6 = sm[6], k7 = sm[7];
+    uint32_t x0 = 0x61707865u, x1 = 0x3320646eu, x2 = 0x79622d32u, x3 = 0x6b206574u;
+    uint32_t x4 = k0, x5 = k1, x6 = k2, x7 = k3, x8 = k4, x9 = k5, x10 = k6, x11 = k7;
+    uint32_t x12 = counter, x13 = 0u, x14 = 0u, x15 = 0u;
+#pragma unroll 1
+    for (int r = 0; r < 6; ++r) {
+        SYN_QR(x0, x4, x8, x12) SYN_QR(x1, x5, x9, x13) SYN_QR(x2, x6, x10, x14) SYN_QR(x3, x7, x11, x15)
+        SYN_QR(x0, x5, x10, x15) SYN_QR(x1, x6, x11, x12) SYN_QR(x2, x7, x8, x13) SYN_QR(x3, x4, x9, x14)
+    }
+    uint32_t* out = sm + 8;
+    out[0] = x0 + 0x61707865u; out[1] = x1 + 0x3320646eu; out[2] = x2 + 0x79622d32u; out[3] = x3 + 0x6b206574u;
+    out[4] = x4 + k0; out[5] = x5 + k1; out[6] = x6 + k2; out[7] = x7 + k3;
+    out[8] = x8 + k4; out[9] = x9 + k5; out[10] = x10 + k6; out[11] = x11 + k7;
+    out[12] = x12 + counter; out[13] = x13; out[14] = x14; out[15] = x15;
+}
 struct FpuSmemStream { // R-concept of include/syn_sampling.h; used by lane 0 of a group
     uint32_t* sm;
     uint32_t pos;
     __device__ uint32_t next_u32() {
         const uint32_t blk = pos >> 4;
         if (blk != sm[24]) {
-            rng::chacha12_block(sm, (uint64_t)blk, sm + 8);
+            chacha12_block_smem(sm, blk);
             sm[24] = blk;
         }
         return sm[8 + ((pos++) & 15u)];
