@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(128 * TEAMS, 1) selfplay_nn_tpg2s_kernel(const
                 const uint32_t init = root.vis == 0.0f ? (uint32_t)tp2::K_INIT : 0u; // the construction visit (mcts.rs:133)
                 if (FPUK == tp2::FPU_NORMAL_CACHED) err = tp2::descend<CW, tp2::FPU_NORMAL_CACHED, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 else if (cfg.fpu_kind == SYN_FPU_CONST) err = tp2::descend<CW, SYN_FPU_CONST, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
-                else if (cfg.fpu_kind == SYN_FPU_PARENT_Q) err = tp2::descend<CW, SYN_FPU_PARENT_Q, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
+                // <5, false> never sees Fpu Normal (engine.cu::launch_tpg_split sends it to the FPU_NORMAL_CACHED instantiation): one inlined descent less
+                else if (cfg.fpu_kind == SYN_FPU_PARENT_Q || (FPUK == -1 && TEAMS == 5 && !PROF)) err = tp2::descend<CW, SYN_FPU_PARENT_Q, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 else err = tp2::descend<CW, SYN_FPU_NORMAL, NT, PATH_CAP>(p, ss, g, root, my, op, pd, rc, path);
                 pd.kind |= init;
             }
