@@ -484,10 +484,11 @@ def run_ours(args):
                     "algorithmic_bytes_per_explore": round(bpe, 1), "explores_per_launch": per_launch,
                     "tree_bytes_per_explore": round(bpe_tree, 1), "frac_tree_only": bpe_tree * per_launch / kernel_s / 1e9 / peak,
                     "launch_ms": 1e3 * kernel_s, "peak_source": peak_src, **shape,
-                    "second_roofline": {"what": "L2-miss sector rate of the memory system (scripts/probe/family_read_probe.cu, profiles/r2_family_read_probe.txt)",
-                                        "peak_sectors_per_s": 36.5e9,
-                                        "note": "a family of nine 32-byte child records is nine sector misses; at ~22 misses per explore (ncu DRAM read bytes / 64) "
-                                                "the kernel runs at 85-90 % of this rate while DRAM bytes stay at 30-40 % of the copy peak"},
+                    "second_roofline": {"what": "dependent reads of whole child families that miss L2 (scripts/probe/family_read_probe.cu, profiles/r2_family_read_probe.txt)",
+                                        "peak_families_per_s": 4.06e9, "peak_sectors_per_s": 36.5e9,
+                                        "achieved_families_per_s": max(0.0, shape["select_depth"] - 1.0) * per_launch / kernel_s,
+                                        "note": "an estimate, not a bound: the probe serves 4.06 G nine-record families/s when EVERY read misses; the kernel reads "
+                                                "(select_depth - 1) families per explore below the root's own, of which the L2 serves a part (hit rate ~40 %)"},
                     "note": "latency-bound pointer chasing over per-game trees; see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -256,6 +256,12 @@ static int launch_rollout_tpg(syn_engine* e, KParams& kp, uint32_t blocks) {
         selfplay_rollout_tpg2_kernel<N, C, tp2::FPU_NORMAL_CACHED><<<blocks, NT, smem, e->stream>>>(kp);
         return SYN_OK;
     }
+    if (NT == 1024 && CW == 3 && kp.cfg.mcts.fpu_kind == SYN_FPU_CONST) { // the default geometry and the default FPU: an instantiation with ONE inlined descent
+        constexpr int N = (NT == 1024 && CW == 3) ? 1024 : 512, C = (NT == 1024 && CW == 3) ? 3 : 5;
+        CUDA_TRY(cudaFuncSetAttribute(selfplay_rollout_tpg2_kernel<N, C, SYN_FPU_CONST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        selfplay_rollout_tpg2_kernel<N, C, SYN_FPU_CONST><<<blocks, NT, smem, e->stream>>>(kp);
+        return SYN_OK;
+    }
     CUDA_TRY(cudaFuncSetAttribute(selfplay_rollout_tpg2_kernel<NT, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     selfplay_rollout_tpg2_kernel<NT, CW><<<blocks, NT, smem, e->stream>>>(kp);
     return SYN_OK;
