@@ -183,7 +183,8 @@ __device__ __forceinline__ int rollout(const Grp<GL>& g, uint64_t my, uint64_t o
         const uint32_t first_bad = bad ? (uint32_t)__ffs(bad) - 1u : (uint32_t)GL;
         const uint32_t fillm = g.ballot(fills) & ((first_bad >= 32u) ? 0xffffffffu : ((1u << first_bad) - 1u));
         uint32_t end = first_bad;                          // plies 0..end-1 of the window are the sequential playout's
-        if (fillm) { const uint32_t f = (uint32_t)__ffs(fillm); if (f < end) end = f; }
+        bool filled_last = false;                          // the window's last ply filled a column
+        if (fillm) { const uint32_t f = (uint32_t)__ffs(fillm); if (f <= end) { end = f; filled_last = true; } }
         // every mover's board after its ply: the mover's board at the start of the window | its stones so far
         uint64_t x = (has && row < 7u) ? (1ull << (7 * col + (int)row)) : 0ull;
 #pragma unroll
@@ -212,7 +213,9 @@ __device__ __forceinline__ int rollout(const Grp<GL>& g, uint64_t my, uint64_t o
             op = last;
         }
         k += end;
-        rr.pos += end + ((end == first_bad && end < w && ((rejm >> end) & 1u)) ? 1u : 0u);
+        // a rejected word right behind the window is consumed with it — unless the window ended on a filled column: then the next
+        // word meets a different n, and whether IT is rejected is for the next window to say (tests/test_windowed_playout_logic.py)
+        rr.pos += end + ((!filled_last && end == first_bad && end < w && ((rejm >> end) & 1u)) ? 1u : 0u);
     }
 }
 
